@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the vanilla-NeRF ray-march path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|bf16] [--impl ours|reference]
+
+One "step" = one optimisation step of `train_nerf.py --vanilla` (train/trainer.py:702-729): stratified
+coarse sampling, coarse pass, sample_pdf + merge, fine pass, loss, backward, Adam -- over one batch of
+1024 synthetic Blender-shaped rays per GPU.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS, NC, NF = 1024, 64, 128
+H = W = 800
+FX = 0.5 * W / np.tan(0.5 * 0.6911112)            # camera_angle_x of the Blender scenes -> 1111.11
+FLOP_TRAIN_PER_POINT = 3_489_024                   # fwd 1,186,816 + dgrad 1,115,392 + wgrad 1,186,816
+FLOP_FWD_PER_POINT = 1_186_816
+POINTS_PER_RAY = NC + (NC + NF)
+
+
+def blender_rays(rng, n, step):
+    """Synthetic Blender-shape batch: one random pose on the r=4.0311 sphere looking at the origin, `n`
+    random pixels of an 800x800 pinhole image (precrop to the central 50% for the first 500 steps,
+    samplers.py:119-127), targets U(0,1) composited on white.  Keys as trainer.py:880-884."""
+    th, ph = rng.uniform(0, 2 * np.pi), rng.uniform(np.deg2rad(-60), np.deg2rad(10))
+    c = 4.0311 * np.array([np.cos(ph) * np.cos(th), np.cos(ph) * np.sin(th), -np.sin(ph)])
+    fwd = -c / np.linalg.norm(c); right = np.cross(fwd, [0, 0, 1.0]); right /= np.linalg.norm(right); up = np.cross(right, fwd)
+    R = np.stack([right, up, -fwd], 1)                                   # OpenGL camera: looks down -z
+    lo, hi = (W // 4, 3 * W // 4) if step < 500 else (0, W)
+    px = rng.integers(lo, hi, size=(n, 2))
+    d_cam = np.stack([(px[:, 0] + 0.5 - W / 2) / FX, -(px[:, 1] + 0.5 - H / 2) / FX, -np.ones(n)], -1)
+    d = d_cam @ R.T
+    nrm = np.linalg.norm(d, axis=-1, keepdims=True)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(rays_o_marching=f32(np.broadcast_to(c, (n, 3))), rays_d_marching_unit=f32(d / nrm), rays_d_marching_norm=f32(nrm),
+                rays_d_world_unit=f32(d / nrm), rgb=f32(rng.uniform(0, 1, (n, 3))))
+
+
+def frame_rays(rng):
+    th = rng.uniform(0, 2 * np.pi)
+    b = blender_rays(np.random.default_rng(1), 1, 1000)
+    c = b["rays_o_marching"][0].astype(np.float64)
+    fwd = -c / np.linalg.norm(c); right = np.cross(fwd, [0, 0, 1.0]); right /= np.linalg.norm(right); up = np.cross(right, fwd)
+    R = np.stack([right, up, -fwd], 1)
+    jj, ii = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    d_cam = np.stack([(ii + 0.5 - W / 2) / FX, -(jj + 0.5 - H / 2) / FX, -np.ones_like(ii, dtype=np.float64)], -1).reshape(-1, 3)
+    d = d_cam @ R.T
+    nrm = np.linalg.norm(d, axis=-1, keepdims=True)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return f32(np.broadcast_to(c, d.shape)), f32(d / nrm), f32(nrm[:, 0])
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_step_fn(rays_per_step):
+    """The reference's CPU implementation of the step, as restated by the oracle (numpy, all host threads
+    through the BLAS pool).  Returns a callable running one full step (fwd+bwd+Adam) on `rays_per_step` rays."""
+    from oracle import nerf_oracle as O
+    rng = np.random.default_rng(0)
+    st = dict(pc=O.init_params(rng, 0.3), pf=O.init_params(rng, 0.3), t=0)
+    st["Pc"], st["Pf"] = O.flatten_params(st["pc"]), O.flatten_params(st["pf"])
+    st["m"] = [np.zeros_like(st["Pc"]) for _ in range(4)]
+
+    def step():
+        B = rays_per_step
+        batch = blender_rays(rng, B, st["t"])
+        out = O.train_step(st["pc"], st["pf"], batch, near=2.0, far=6.0, nc=NC, nf=NF, U=rng.uniform(0, 1, (B, NC)).astype(np.float32),
+                           u_fine=rng.uniform(0, 1, (B, NF)).astype(np.float32), noise_c=rng.standard_normal(B * NC).astype(np.float32),
+                           noise_f=rng.standard_normal(B * (NC + NF)).astype(np.float32))
+        st["t"] += 1
+        st["Pc"], st["m"][0], st["m"][1] = O.adam_step(st["Pc"], O.flatten_params(out["grads_c"]), st["m"][0], st["m"][1], st["t"])
+        st["Pf"], st["m"][2], st["m"][3] = O.adam_step(st["Pf"], O.flatten_params(out["grads_f"]), st["m"][2], st["m"][3], st["t"])
+        st["pc"], st["pf"] = O.unflatten_params(st["Pc"]), O.unflatten_params(st["Pf"])
+        return float(out["loss"])
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    rays = RAYS if (args.steps + args.warmup) <= 24 else 256
+    step = cpu_reference_step_fn(rays)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = rays * args.steps / dt
+    sample = f"{args.steps} full steps (fwd+bwd+Adam) of {rays} rays x (64+192) samples, numpy fp32, BLAS threads={cores}"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step, 64 coarse + 128 fine, "
+                               "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])", "rays_per_step": rays},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("NSB_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frame", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph (N=1)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import nerf_sandbox_b200 as nsb
+    from nerf_sandbox_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(args.warmup, 3)
+    K = args.steps
+
+    tr = nsb.VanillaTrainer(dev, rays_per_batch=RAYS, nc=NC, nf=NF, near=2.0, far=6.0, mode=args.mode, seed=0, sigma_bias=0.3)
+    rng = np.random.default_rng(1000 + rank)
+    pool_n = 8
+    host = [{k: torch.from_numpy(v).pin_memory() for k, v in blender_rays(rng, RAYS, s).items()} for s in range(pool_n)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d = sum(v.numel() * 4 for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ("value") --------------------------------------------------------------
+    for i in range(W_):
+        tr.step(devb[i % pool_n])
+    barrier()
+    clk = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        tr.step(devb[i % pool_n])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0 + (2 * K if world > 1 else 0)
+    clocks = clk.stop() if clk else None
+    loss_dev = float(tr.scalars[0])
+
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------------------
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+    for i in range(3):
+        for k in stage:
+            stage[k].copy_(host[i % pool_n][k], non_blocking=True)
+        tr.step(stage); tr.scalars.cpu()
+    barrier()
+    e0.record()
+    for i in range(K):
+        for k in stage:
+            stage[k].copy_(host[i % pool_n][k], non_blocking=True)
+        loss_host = tr.step(stage).cpu()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- roofline of the dominant kernel family (encoder+MLP fwd+bwd of the fine pass), timed alone ------
+    L = _lib.lib()
+    Q = RAYS * (NC + NF)
+    b0 = devb[0]
+    z = torch.sort(torch.rand((RAYS, NC + NF), device=dev) * 4 + 2, -1).values.contiguous()
+    wsb = L.nsb_field_workspace_bytes(Q, tr.mode, 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    raw = torch.empty((Q, 4), device=dev); d_raw = torch.randn((Q, 4), device=dev) * 1e-3
+    gbuf = torch.zeros(_lib.N_PARAMS, device=dev)
+    st = _lib.stream()
+
+    def field():
+        _lib.check(L.nsb_field_fwd_rays(_lib.ptr(b0["rays_o_marching"]), _lib.ptr(b0["rays_d_marching_unit"]), _lib.ptr(z),
+                                        _lib.ptr(b0["rays_d_marching_norm"].reshape(-1)), _lib.ptr(b0["rays_d_world_unit"]),
+                                        _lib.ptr(tr.nerf_f.packed()), _lib.ptr(raw), _lib.ptr(ws), wsb, RAYS, NC + NF, tr.mode, 1, st))
+        _lib.check(L.nsb_field_bwd(_lib.ptr(d_raw), _lib.ptr(tr.nerf_f.packed()), _lib.ptr(gbuf), _lib.ptr(ws), wsb, Q, tr.mode, st))
+    for _ in range(3):
+        field()
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        field()
+    e1.record(); torch.cuda.synchronize()
+    ms_field = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    ach_tf = Q * FLOP_TRAIN_PER_POINT / (ms_field * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                "kernel": f"field fwd+bwd ({args.mode}) on the fine pass, {Q} points, {ms_field:.3f} ms/launch-set",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"}
+
+    # ---- secondary metric: 800x800 eval frame (configs[2]) -----------------------------------------------
+    extra = {}
+    if not args.no_frame and rank == 0:
+        o, d, rn = (torch.from_numpy(a).to(dev) for a in frame_rays(rng))
+        chunk = 65536
+        nrays = H * W if args.mode == "bf16" else 2 * chunk            # fp32 mode: bounded sample, extrapolated
+        pe, de = tr.pos_enc, tr.dir_enc
+        def frame():
+            for s in range(0, nrays, chunk):
+                e = min(nrays, s + chunk)
+                nsb.render_rays(o[s:e], d[s:e], rn[s:e], d[s:e], tr.nerf_c, tr.nerf_f, near=2.0, far=6.0, nc=NC, nf=NF, white_bkgd=True)
+        frame(); torch.cuda.synchronize()
+        e0.record(); frame(); e1.record(); torch.cuda.synchronize()
+        ms_frame = e0.elapsed_time(e1) * (H * W / nrays)
+        extra = {"render_800x800_frames_per_s": 1e3 / ms_frame, "render_ms_per_frame": ms_frame, "render_rays_timed": nrays,
+                 "render_eval_chunk": chunk,
+                 "render_mlp_tflops": H * W * POINTS_PER_RAY * FLOP_FWD_PER_POINT / (ms_frame * 1e-3) / 1e12}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        stepf = cpu_reference_step_fn(RAYS)
+        stepf()
+        t0 = time.perf_counter(); n = 0
+        while n < 2:
+            stepf(); n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": RAYS * n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{n} full steps (fwd+bwd+Adam) of {RAYS} rays after 1 warm-up, numpy fp32 oracle, BLAS threads={os.cpu_count()}"}
+
+    if rank == 0:
+        ws_gb = L.nsb_train_workspace_bytes(RAYS, NC, NF, tr.mode) / 1e9
+        print(json.dumps({
+            "metric": "train_rays_per_s", "value": world * RAYS * K / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": K,
+            "warmup": W_, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step/GPU, 64 coarse + 128 fine, "
+                                   "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])",
+                       "rays_per_step_per_gpu": RAYS, "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of 2x595,844 fp32 grads",
+                       "mode": args.mode, "l2": f"no flush: per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * RAYS * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+            "loss_after": loss_dev, "loss_e2e_last": float(loss_host[0]),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/* nsb.h -- C ABI of libnsb.so, the B200 (sm_100a) engine for the vanilla-NeRF ray-march path of
+ * evan-wes/nerf-sandbox.
+ *
+ * The reference has no FFI: its seam is a set of Python callables bound by name
+ * (train/trainer.py:46-54, utils/render_utils.py:24-25, utils/validation_renderer.py:16-24).  Each
+ * entry point below states which of those callables (file:line in the reference) it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch) owns all
+ *     memory including workspaces, so the caching allocator and CUDA-graph capture keep working;
+ *   - fp32, contiguous, row-major; ray-major then sample-major: z[b*N+i], raw[(b*N+i)*4+c];
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises or allocates;
+ *   - return 0 on success, a negative NSB_E_* code otherwise (nsb_error_string explains it);
+ *     the Python wrappers raise RuntimeError/ValueError like the reference does;
+ *   - nullable arguments are marked [opt].
+ */
+#ifndef NSB_H_
+#define NSB_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_OK 0
+#define NSB_E_BADARG (-1)     /* shape / flag the path does not support                         */
+#define NSB_E_WORKSPACE (-2)  /* workspace too small (see nsb_field_workspace_bytes)            */
+#define NSB_E_CUDA (-3)       /* a CUDA runtime call or launch failed; see nsb_last_cuda_error  */
+#define NSB_E_ARCH (-4)       /* device is not sm_100 (tensor-core mode only)                   */
+
+/* flags for the compositor / forward pass */
+#define NSB_WHITE_BKGD 1u        /* render_utils.py:161-162 */
+#define NSB_INFINITE_LAST_BIN 2u /* render_utils.py:132-135 */
+#define NSB_TRAINING 4u          /* render_utils.py:239: add raw noise to sigma before ReLU */
+
+/* arithmetic mode of the field (encoder + MLP) kernels */
+#define NSB_MODE_FP32 0  /* CUDA-core FFMA, fp32 everywhere: the 1e-4 parity mode           */
+#define NSB_MODE_BF16 1  /* tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM     */
+
+/* NeRF(63,27,8,256,skip_pos=4) -- models/mlps.py:41-134.  Flat parameter order is the reference's
+ * state_dict order: mlp.0.weight, mlp.0.bias, ..., mlp.7.*, feature.*, sigma_out.*, color_fc.*,
+ * color_out.* (SURVEY.md section 5). */
+#define NSB_N_PARAMS 595844
+
+int nsb_version(void);
+const char* nsb_error_string(int code);
+const char* nsb_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t nsb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  samplers
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stratified coarse samples; replaces the inline code of Trainer._train_step, train/trainer.py:901-908
+ * (jittered) and render_image_chunked, utils/render_utils.py:330-331,351 (U == NULL && !jitter: plain
+ * linspace).  z[B,Nc].  U[B,Nc] [opt] explicit uniforms in [0,1) (parity tests); when NULL and jitter!=0
+ * uniforms come from Philox(seed, offset). Bit-exact with the reference given the same U. */
+int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, float near_, float far_, int jitter,
+                     uint64_t seed, uint64_t offset, void* stream);
+
+/* sample_pdf, utils/sampling_utils.py:5-64.  bins[B,bins_cols] with bins_cols == M (midpoints) or M+1
+ * (edges); weights[B,M]; out[B,n].  u[B,n] [opt] explicit uniforms; cdf_in[B,M+1] [opt] replaces the
+ * CDF built from weights (the bit-exact index test feeds the reference's CDF); inds_out[B,n] [opt]
+ * receives searchsorted(cdf,u,right=True) as int64.  deterministic != 0: u = linspace(0,1,n). */
+int nsb_sample_pdf(const float* bins, int bins_cols, const float* weights, int M, const float* u,
+                   const float* cdf_in, float* out, int64_t* inds_out, int64_t B, int n, int deterministic,
+                   uint64_t seed, uint64_t offset, void* stream);
+
+/* Fused hierarchical resampling: interval weights (train/trainer.py:926-928) + sample_pdf (:930) +
+ * sort(cat(zc,zf)) (:981).  zc[B,Nc] sorted, w_c[B,Nc]; z_all[B,Nc+Nf]; z_fine[B,Nf] [opt] unsorted
+ * samples as sample_pdf returns them; u[B,Nf] [opt]. */
+int nsb_resample_merge(const float* zc, const float* w_c, const float* u, float* z_all, float* z_fine,
+                       int64_t B, int Nc, int Nf, int deterministic, uint64_t seed, uint64_t offset,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  compositor
+ * ---------------------------------------------------------------------------------------------- */
+
+/* volume_render_rays, utils/render_utils.py:108-167.  rgb[B,N,3], sigma[B,N], z[B,N],
+ * ray_norm[B] [opt]; comp[B,3], weights[B,N] [opt], acc[B], depth[B]. flags: NSB_WHITE_BKGD,
+ * NSB_INFINITE_LAST_BIN. */
+int nsb_composite_fwd(const float* rgb, const float* sigma, const float* z, const float* ray_norm,
+                      float* comp, float* weights, float* acc, float* depth, int64_t B, int N,
+                      uint32_t flags, float eps, void* stream);
+/* autograd of the above w.r.t. (rgb, sigma).  g_comp[B,3]; g_weights[B,N], g_acc[B], g_depth[B] [opt].
+ * d_rgb[B,N,3], d_sigma[B,N]. */
+int nsb_composite_bwd(const float* rgb, const float* sigma, const float* z, const float* ray_norm,
+                      const float* g_comp, const float* g_weights, const float* g_acc, const float* g_depth,
+                      float* d_rgb, float* d_sigma, int64_t B, int N, uint32_t flags, float eps, void* stream);
+
+/* Fused head activation + compositor: the tail of nerf_forward_pass, utils/render_utils.py:230-247
+ * (sigmoid on rgb logits, sigma = relu(raw + noise*std) when NSB_TRAINING) followed by :269-276.
+ * raw[B*N,4] = NeRF.forward output [r,g,b,sigma]; noise[B*N] [opt] explicit N(0,1) draws, else
+ * Philox(seed, offset) when NSB_TRAINING and noise_std > 0. */
+int nsb_composite_raw_fwd(const float* raw, const float* noise, float noise_std, const float* z,
+                          const float* ray_norm, float* comp, float* weights, float* acc, float* depth,
+                          int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset, void* stream);
+int nsb_composite_raw_bwd(const float* raw, const float* noise, float noise_std, const float* z,
+                          const float* ray_norm, const float* g_comp, float* d_raw, int64_t B, int N,
+                          uint32_t flags, uint64_t seed, uint64_t offset, void* stream);
+
+/* Loss of Trainer._train_step, train/trainer.py:999-1006: guards + mse(comp_c)+mse(comp_f) and its
+ * gradient.  scalars[4] = {loss, psnr, mse_c, mse_f} (device).  g_c/g_f[B,3] = dloss/dcomp * grad_scale.
+ * comp_c may be NULL (coarse-only). */
+int nsb_mse_loss(const float* comp_c, const float* comp_f, const float* target, float* g_c, float* g_f,
+                 float* scalars, int64_t B, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  field: positional encoder + 8x256 skip MLP
+ * ---------------------------------------------------------------------------------------------- */
+
+/* PositionalEncoder.forward, models/encoders.py:73-106.  x[Q,D] -> out[Q, D*(include_input + 2L)],
+ * order [x | sin(2^k x_d) k-major | cos(...)]. */
+int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream);
+
+/* Packed weights of one NeRF: fp32 padded rows for the FFMA path and a bf16 image in tcgen05 operand
+ * layout for the tensor path.  Sizes in bytes. */
+size_t nsb_packed_weights_bytes(void);
+/* params: flat fp32 [NSB_N_PARAMS] in state_dict order -> packed (call after every optimiser step). */
+int nsb_pack_weights(const float* params, void* packed, void* stream);
+
+/* Workspace for one pass over Q = B*N points.  stash != 0 keeps what the backward needs. */
+size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash);
+
+/* NeRF.forward, models/mlps.py:192-278, on materialised encodings: enc_pos[Q,63], enc_dir[Q,27] ->
+ * raw[Q,4].  (The module-level drop-in; the fused entry below never materialises the encodings.) */
+int nsb_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw,
+                      void* ws, size_t ws_bytes, int64_t Q, int mode, int stash, void* stream);
+
+/* Points + encodings + MLP of nerf_forward_pass, utils/render_utils.py:211-261: pts = o + d*(z*norm),
+ * viewdirs normalised (:219) and broadcast per sample, gamma(x), gamma(d), NeRF.forward.
+ * rays_o[B,3], rays_d[B,3], z[B,N], ray_norm[B] [opt], viewdirs[B,3] [opt: falls back to rays_d]. */
+int nsb_field_fwd_rays(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm,
+                       const float* viewdirs, const void* packed, float* raw, void* ws, size_t ws_bytes,
+                       int64_t B, int N, int mode, int stash, void* stream);
+
+/* Parameter gradients of the pass whose activations are stashed in ws: grads[NSB_N_PARAMS] (flat,
+ * state_dict order) += dL/dparams given d_raw[Q,4].  Inputs carry no gradient. */
+int nsb_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, size_t ws_bytes,
+                  int64_t Q, int mode, void* stream);
+
+/* torch.optim.Adam step (train/trainer.py:383-386, :722) on flat buffers; grads are multiplied by
+ * grad_scale first (1/world_size after a sum-allreduce). t is the 1-based step count. */
+int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t t, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-path entry points (one host call per step / per ray tile)
+ * ---------------------------------------------------------------------------------------------- */
+
+size_t nsb_train_workspace_bytes(int64_t B, int Nc, int Nf, int mode);
+
+/* Trainer._train_step + loss.backward(), train/trainer.py:876-1013 and :717.  Batch tensors as
+ * trainer.py:880-884.  grads_c/grads_f[NSB_N_PARAMS] are overwritten with dloss/dparams * grad_scale.
+ * Explicit random draws [opt]: U[B,Nc], u_fine[B,Nf], noise_c[B*Nc], noise_f[B*(Nc+Nf)].
+ * scalars[4] = {loss, psnr, mse_c, mse_f}; comp_c/comp_f[B,3] [opt]. */
+int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
+                      const float* target, const void* packed_c, const void* packed_f, float* grads_c,
+                      float* grads_f, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes,
+                      int64_t B, int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags,
+                      int det_fine, int mode, float grad_scale, uint64_t seed, uint64_t step, const float* U,
+                      const float* u_fine, const float* noise_c, const float* noise_f, void* stream);
+
+size_t nsb_render_workspace_bytes(int64_t B, int Nc, int Nf, int mode);
+
+/* One ray tile of render_image_chunked, utils/render_utils.py:337-417 (perturb=False): coarse linspace,
+ * coarse pass, interval weights + deterministic sample_pdf + merge, fine pass.  Nf <= 0 or packed_f ==
+ * NULL: coarse only (:381-385).  rgb[B,3], acc[B], depth[B]. */
+int nsb_render_rays(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
+                    const void* packed_c, const void* packed_f, float* rgb, float* acc, float* depth, void* ws,
+                    size_t ws_bytes, int64_t B, int Nc, int Nf, float near_, float far_, uint32_t flags, int mode,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB_H_ */

@@ -1,0 +1,231 @@
+// Library core + whole-path entry points: the host-side sequencing of Trainer._train_step
+// (train/trainer.py:876-1013, + backward) and of one ray tile of render_image_chunked
+// (utils/render_utils.py:337-417) as back-to-back launches on one stream -- no host syncs, no
+// allocation, so a caller can capture a step in a CUDA graph.
+#include <cstdio>
+#include <cstring>
+#include "nsb_common.cuh"
+
+namespace nsb {
+
+int64_t g_launches = 0;
+char g_cuda_err[256] = "";
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+        return NSB_E_CUDA;
+    }
+    return NSB_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// field_fp32.cu
+size_t fp32_workspace_bytes(int64_t Q, int stash);
+int pack_fp32(const float* params, void* packed, cudaStream_t st);
+int fp32_prepare_rays(const float*, const float*, const float*, const float*, const float*, void*, int64_t, int, int, cudaStream_t);
+int fp32_prepare_enc(const float*, const float*, void*, int64_t, int, cudaStream_t);
+int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash, cudaStream_t st);
+int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
+// field_tc.cu
+size_t tc_workspace_bytes(int64_t Q, int stash);
+int tc_pack(const float* params, void* packed_bf16, cudaStream_t st);
+int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
+                      float* raw, void* ws, int64_t B, int N, int stash, cudaStream_t st);
+int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, void* ws, int64_t Q,
+                     int stash, cudaStream_t st);
+int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
+
+static size_t field_ws(int64_t Q, int mode, int stash) {
+    return mode == NSB_MODE_BF16 ? tc_workspace_bytes(Q, stash) : fp32_workspace_bytes(Q, stash);
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_version(void) { return 100; }
+extern "C" const char* nsb_error_string(int code) {
+    switch (code) {
+        case NSB_OK: return "ok";
+        case NSB_E_BADARG: return "bad argument (shape/flag not supported by this path)";
+        case NSB_E_WORKSPACE: return "workspace too small";
+        case NSB_E_CUDA: return "CUDA error (see nsb_last_cuda_error)";
+        case NSB_E_ARCH: return "device is not sm_100";
+        default: return "unknown error";
+    }
+}
+extern "C" const char* nsb_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int64_t nsb_launch_count(void) { return g_launches; }
+
+extern "C" size_t nsb_packed_weights_bytes(void) { return packed_layout().total; }
+extern "C" int nsb_pack_weights(const float* params, void* packed, void* stream) {
+    if (!params || !packed) return NSB_E_BADARG;
+    NSB_TRY(pack_fp32(params, packed, as_stream(stream)));
+    return tc_pack(params, reinterpret_cast<char*>(packed) + packed_layout().bf16_off, as_stream(stream));
+}
+
+extern "C" size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash) { return field_ws(Q, mode, stash); }
+
+extern "C" int nsb_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, void* ws,
+                                 size_t ws_bytes, int64_t Q, int mode, int stash, void* stream) {
+    if (!enc_pos || !enc_dir || !packed || !raw || !ws || Q < 0) return NSB_E_BADARG;
+    if (Q == 0) return NSB_OK;
+    if (ws_bytes < field_ws(Q, mode, stash)) return NSB_E_WORKSPACE;
+    if (mode == NSB_MODE_BF16)
+        return tc_field_fwd_enc(enc_pos, enc_dir, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw,
+                                ws, Q, stash, as_stream(stream));
+    NSB_TRY(fp32_prepare_enc(enc_pos, enc_dir, ws, Q, stash, as_stream(stream)));
+    return fp32_mlp_fwd(packed, raw, ws, Q, stash, as_stream(stream));
+}
+
+extern "C" int nsb_field_fwd_rays(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm,
+                                  const float* viewdirs, const void* packed, float* raw, void* ws, size_t ws_bytes,
+                                  int64_t B, int N, int mode, int stash, void* stream) {
+    if (!rays_o || !rays_d || !z || !packed || !raw || !ws || B < 0 || N < 1) return NSB_E_BADARG;
+    if (B == 0) return NSB_OK;
+    const int64_t Q = B * (int64_t)N;
+    if (ws_bytes < field_ws(Q, mode, stash)) return NSB_E_WORKSPACE;
+    if (mode == NSB_MODE_BF16)
+        return tc_field_fwd_rays(rays_o, rays_d, z, ray_norm, viewdirs,
+                                 reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw, ws, B, N, stash,
+                                 as_stream(stream));
+    NSB_TRY(fp32_prepare_rays(rays_o, rays_d, z, ray_norm, viewdirs, ws, B, N, stash, as_stream(stream)));
+    return fp32_mlp_fwd(packed, raw, ws, Q, stash, as_stream(stream));
+}
+
+extern "C" int nsb_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, size_t ws_bytes, int64_t Q,
+                             int mode, void* stream) {
+    if (!d_raw || !packed || !grads || !ws || Q < 0) return NSB_E_BADARG;
+    if (Q == 0) return NSB_OK;
+    if (ws_bytes < field_ws(Q, mode, 1)) return NSB_E_WORKSPACE;
+    if (mode == NSB_MODE_BF16)
+        return tc_field_bwd(d_raw, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, grads, ws, Q,
+                            as_stream(stream));
+    return fp32_mlp_bwd(d_raw, packed, grads, ws, Q, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whole train step
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct TrainWs {
+    float *zc, *w_c, *z_all, *raw_c, *raw_f, *d_raw, *comp_c, *comp_f, *g_c, *g_f;
+    void *field_c, *field_f;
+    size_t field_c_bytes, field_f_bytes, bytes;
+};
+TrainWs carve_train(void* base, int64_t B, int Nc, int Nf, int mode) {
+    TrainWs t;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p + off; off += align_up(bytes, 256); return r; };
+    const int64_t Qc = B * (int64_t)Nc, Qf = B * (int64_t)(Nc + Nf);
+    t.zc = (float*)take(Qc * 4); t.w_c = (float*)take(Qc * 4); t.z_all = (float*)take(Qf * 4);
+    t.raw_c = (float*)take(Qc * 16); t.raw_f = (float*)take(Qf * 16); t.d_raw = (float*)take(Qf * 16);
+    t.comp_c = (float*)take(B * 12); t.comp_f = (float*)take(B * 12); t.g_c = (float*)take(B * 12); t.g_f = (float*)take(B * 12);
+    t.field_c_bytes = field_ws(Qc, mode, 1); t.field_f_bytes = field_ws(Qf, mode, 1);
+    t.field_c = take(t.field_c_bytes); t.field_f = take(t.field_f_bytes);
+    t.bytes = off;
+    return t;
+}
+}  // namespace
+
+extern "C" size_t nsb_train_workspace_bytes(int64_t B, int Nc, int Nf, int mode) {
+    return carve_train(nullptr, B, Nc, Nf, mode).bytes;
+}
+
+extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
+                                 const float* target, const void* packed_c, const void* packed_f, float* grads_c,
+                                 float* grads_f, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes,
+                                 int64_t B, int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags,
+                                 int det_fine, int mode, float grad_scale, uint64_t seed, uint64_t step, const float* U,
+                                 const float* u_fine, const float* noise_c, const float* noise_f, void* stream) {
+    if (!rays_o || !rays_d || !target || !packed_c || !packed_f || !grads_c || !grads_f || !scalars || !ws) return NSB_E_BADARG;
+    if (B < 1 || Nc < 2 || Nf < 1) return NSB_E_BADARG;
+    TrainWs t = carve_train(ws, B, Nc, Nf, mode);
+    if (ws_bytes < t.bytes) return NSB_E_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int Nt = Nc + Nf;
+    const int64_t Qc = B * (int64_t)Nc, Qf = B * (int64_t)Nt;
+    const uint32_t f = flags | NSB_TRAINING;
+    // independent Philox streams per (step, purpose)
+    const uint64_t s_jit = step * 8 + 0, s_u = step * 8 + 1, s_nc = step * 8 + 2, s_nf = step * 8 + 3;
+    if (cudaMemsetAsync(grads_c, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+    if (cudaMemsetAsync(grads_f, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+    // coarse
+    NSB_TRY(nsb_stratified_z(t.zc, U, B, Nc, near_, far_, 1, seed, s_jit, stream));                                    // trainer.py:901-908
+    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.zc, ray_norm, viewdirs, packed_c, t.raw_c, t.field_c, t.field_c_bytes, B, Nc, mode, 1, stream));
+    NSB_TRY(nsb_composite_raw_fwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.comp_c, t.w_c, nullptr, nullptr, B, Nc, f, seed, s_nc, stream));   // :911-923
+    // resample + merge, fine
+    NSB_TRY(nsb_resample_merge(t.zc, t.w_c, u_fine, t.z_all, nullptr, B, Nc, Nf, det_fine, seed, s_u, stream));       // :926-934, :981
+    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.z_all, ray_norm, viewdirs, packed_f, t.raw_f, t.field_f, t.field_f_bytes, B, Nt, mode, 1, stream));
+    NSB_TRY(nsb_composite_raw_fwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.comp_f, nullptr, nullptr, nullptr, B, Nt, f, seed, s_nf, stream));   // :984-996
+    // loss (:999-1006) and backward (:717)
+    NSB_TRY(nsb_mse_loss(t.comp_c, t.comp_f, target, t.g_c, t.g_f, scalars, B, grad_scale, stream));
+    NSB_TRY(nsb_composite_raw_bwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.g_f, t.d_raw, B, Nt, f, seed, s_nf, stream));
+    NSB_TRY(nsb_field_bwd(t.d_raw, packed_f, grads_f, t.field_f, t.field_f_bytes, Qf, mode, stream));
+    NSB_TRY(nsb_composite_raw_bwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.g_c, t.d_raw, B, Nc, f, seed, s_nc, stream));
+    NSB_TRY(nsb_field_bwd(t.d_raw, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, stream));
+    if (comp_c && cudaMemcpyAsync(comp_c, t.comp_c, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
+    if (comp_f && cudaMemcpyAsync(comp_f, t.comp_f, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// eval ray tile
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct RenderWs {
+    float *zc, *w_c, *z_all, *raw;
+    void* field;
+    size_t field_bytes, bytes;
+};
+RenderWs carve_render(void* base, int64_t B, int Nc, int Nf, int mode) {
+    RenderWs t;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p + off; off += align_up(bytes, 256); return r; };
+    const int Nt = Nc + (Nf > 0 ? Nf : 0);
+    t.zc = (float*)take(B * (int64_t)Nc * 4); t.w_c = (float*)take(B * (int64_t)Nc * 4);
+    t.z_all = (float*)take(B * (int64_t)Nt * 4); t.raw = (float*)take(B * (int64_t)Nt * 16);
+    t.field_bytes = field_ws(B * (int64_t)Nt, mode, 0);
+    t.field = take(t.field_bytes);
+    t.bytes = off;
+    return t;
+}
+}  // namespace
+
+extern "C" size_t nsb_render_workspace_bytes(int64_t B, int Nc, int Nf, int mode) {
+    return carve_render(nullptr, B, Nc, Nf, mode).bytes;
+}
+
+extern "C" int nsb_render_rays(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
+                               const void* packed_c, const void* packed_f, float* rgb, float* acc, float* depth, void* ws,
+                               size_t ws_bytes, int64_t B, int Nc, int Nf, float near_, float far_, uint32_t flags,
+                               int mode, void* stream) {
+    if (!rays_o || !rays_d || !packed_c || !rgb || !ws || B < 0 || Nc < 1) return NSB_E_BADARG;
+    if (B == 0) return NSB_OK;
+    const bool fine = Nf > 0 && packed_f != nullptr;                                                                   // render_utils.py:381
+    if (fine && Nc < 2) return NSB_E_BADARG;
+    RenderWs t = carve_render(ws, B, Nc, fine ? Nf : 0, mode);
+    if (ws_bytes < t.bytes) return NSB_E_WORKSPACE;
+    const uint32_t f = flags & ~NSB_TRAINING;
+    NSB_TRY(nsb_stratified_z(t.zc, nullptr, B, Nc, near_, far_, 0, 0, 0, stream));                                      // :330-331,351
+    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.zc, ray_norm, viewdirs, packed_c, t.raw, t.field, t.field_bytes, B, Nc, mode, 0, stream));
+    if (!fine)
+        return nsb_composite_raw_fwd(t.raw, nullptr, 0.f, t.zc, ray_norm, rgb, nullptr, acc, depth, B, Nc, f, 0, 0, stream);
+    NSB_TRY(nsb_composite_raw_fwd(t.raw, nullptr, 0.f, t.zc, ray_norm, rgb, t.w_c, nullptr, nullptr, B, Nc, f, 0, 0, stream));   // :362-375
+    NSB_TRY(nsb_resample_merge(t.zc, t.w_c, nullptr, t.z_all, nullptr, B, Nc, Nf, 1, 0, 0, stream));                   // :388-395
+    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.z_all, ray_norm, viewdirs, packed_f, t.raw, t.field, t.field_bytes, B, Nc + Nf, mode, 0, stream));
+    return nsb_composite_raw_fwd(t.raw, nullptr, 0.f, t.z_all, ray_norm, rgb, nullptr, acc, depth, B, Nc + Nf, f, 0, 0, stream);   // :399-417
+}

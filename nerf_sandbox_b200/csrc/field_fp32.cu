@@ -1,0 +1,586 @@
+// K1 (fp32 mode) -- positional encoder + NeRF MLP on CUDA cores, fp32 end to end.
+// This is the 1e-4 parity mode of the field: layer-by-layer register-tiled SGEMMs (128x128x16 tiles,
+// 8x8 micro-tiles, FFMA) with the bias/ReLU/mask epilogues fused, concat-free activation layout
+// (layer 3 writes straight into the [h | gamma(x)] buffer of the skip layer, `feature` into the
+// [feat | gamma(d)] buffer of color_fc), dedicated warp-per-point kernels for the N=1/N=3 heads.
+// The tensor-core mode lives in field_tc.cu.
+#include "nsb_common.cuh"
+
+namespace nsb {
+
+// ---------------------------------------------------------------------------------------------------
+// workspace carve-up (floats per point)
+// ---------------------------------------------------------------------------------------------------
+struct Fp32Ws {
+    float *X0, *X4, *XC, *C;            // [Q,64] [Q,320] [Q,288] [Q,128]
+    float* out[8];                      // output buffer of trunk layer l (ld = out_ld[l])
+    int out_ld[8];
+    float *dA, *dB, *dC;                // backward ping-pong [Q,256] x2, [Q,128]
+    size_t bytes;
+};
+
+static Fp32Ws carve_fp32(void* base, int64_t Q, int stash) {
+    Fp32Ws w;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](int64_t floats_per_pt) {
+        float* r = reinterpret_cast<float*>(p + off);
+        off += align_up((size_t)Q * floats_per_pt * sizeof(float), 256);
+        return r;
+    };
+    w.X0 = take(kPosPad); w.X4 = take(kSkipPad); w.XC = take(kColorPad); w.C = take(kColorHidden);
+    if (stash) {
+        for (int l = 0; l < 8; ++l) {
+            if (l == 3) { w.out[l] = w.X4; w.out_ld[l] = kSkipPad; }
+            else { w.out[l] = take(kHidden); w.out_ld[l] = kHidden; }
+        }
+        w.dA = take(kHidden); w.dB = take(kHidden); w.dC = take(kColorHidden);
+    } else {
+        float* Ha = take(kHidden); float* Hb = take(kHidden);
+        for (int l = 0; l < 8; ++l) {
+            if (l == 3) { w.out[l] = w.X4; w.out_ld[l] = kSkipPad; }
+            else { w.out[l] = (l % 2 == 0) ? Ha : Hb; w.out_ld[l] = kHidden; }
+        }
+        // l=7 -> Hb, l=6 -> Ha, l=5 -> Hb, l=4 -> Ha: consecutive layers never alias
+        w.dA = w.dB = w.dC = nullptr;
+    }
+    w.bytes = off;
+    return w;
+}
+
+size_t fp32_workspace_bytes(int64_t Q, int stash) { return carve_fp32(nullptr, Q, stash).bytes; }
+
+// ---------------------------------------------------------------------------------------------------
+// encoders
+// ---------------------------------------------------------------------------------------------------
+// PositionalEncoder.forward, generic (models/encoders.py:88-106)
+__global__ void encode_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t Q, int D, int L,
+                              int include_input) {
+    const int od = D * (include_input ? 1 : 0) + 2 * L * D;
+    const int64_t total = Q * od;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = idx / od;
+        int j = (int)(idx % od);
+        float v;
+        if (include_input && j < D) v = x[q * D + j];
+        else {
+            j -= include_input ? D : 0;
+            const bool is_cos = j >= L * D;
+            if (is_cos) j -= L * D;
+            const int k = j / D, d = j % D;
+            const float arg = x[q * D + d] * exp2f((float)k);      // exact power-of-two scaling (:95)
+            v = is_cos ? cosf(arg) : sinf(arg);
+        }
+        out[idx] = v;
+    }
+}
+
+// points + both encodings into the padded activation buffers; 16 threads per point
+__global__ void prepare_from_rays_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                         const float* __restrict__ z, const float* __restrict__ ray_norm,
+                                         const float* __restrict__ viewdirs, float* __restrict__ X0,
+                                         float* __restrict__ X4, float* __restrict__ XC, int64_t B, int N) {
+    const int64_t Q = B * (int64_t)N;
+    const int sub = threadIdx.x & 15;
+    for (int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4; q < Q;
+         q += ((int64_t)gridDim.x * blockDim.x) >> 4) {
+        const int64_t b = q / N;
+        if (sub < 10 || sub == 14) {
+            // render_utils.py:211-215 -- z*norm, then d*that, then + o, each rounded separately
+            const float zm = ray_norm ? __fmul_rn(z[q], ray_norm[b]) : z[q];
+            float p[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) p[d] = __fadd_rn(rays_o[b * 3 + d], __fmul_rn(rays_d[b * 3 + d], zm));
+            float* r0 = X0 + q * kPosPad;
+            float* r4 = X4 + q * kSkipPad + kHidden;
+            if (sub == 14) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { r0[d] = p[d]; r4[d] = p[d]; }
+                r0[63] = 0.f; r4[63] = 0.f;
+            } else {
+                const float f = exp2f((float)sub);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(p[d] * f, &s, &c);
+                    r0[3 + 3 * sub + d] = s; r0[33 + 3 * sub + d] = c;
+                    r4[3 + 3 * sub + d] = s; r4[33 + 3 * sub + d] = c;
+                }
+            }
+        } else {
+            const float* vsrc = viewdirs ? viewdirs : rays_d;        // :218-222
+            const float vx = vsrc[b * 3 + 0], vy = vsrc[b * 3 + 1], vz = vsrc[b * 3 + 2];
+            const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);   // F.normalize
+            const float v[3] = {vx / nrm, vy / nrm, vz / nrm};
+            float* rc = XC + q * kColorPad + kHidden;
+            if (sub == 15) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) rc[d] = v[d];
+                for (int j = kDirDim; j < kColorPad - kHidden; ++j) rc[j] = 0.f;
+            } else {
+                const int k = sub - 10;
+                const float f = exp2f((float)k);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(v[d] * f, &s, &c);
+                    rc[3 + 3 * k + d] = s; rc[15 + 3 * k + d] = c;
+                }
+            }
+        }
+    }
+}
+
+// materialised encodings -> padded buffers (NeRF.forward module boundary)
+__global__ void prepare_from_enc_kernel(const float* __restrict__ enc_pos, const float* __restrict__ enc_dir,
+                                        float* __restrict__ X0, float* __restrict__ X4, float* __restrict__ XC,
+                                        int64_t Q) {
+    const int64_t total = Q * 96;       // 64 pos slots + 32 dir slots per point
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = idx / 96;
+        const int j = (int)(idx % 96);
+        if (j < 64) {
+            const float v = j < kPosDim ? enc_pos[q * kPosDim + j] : 0.f;
+            X0[q * kPosPad + j] = v; X4[q * kSkipPad + kHidden + j] = v;
+        } else {
+            const int jj = j - 64;
+            XC[q * kColorPad + kHidden + jj] = jj < kDirDim ? enc_dir[q * kDirDim + jj] : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SGEMM  C[m,n] = sum_k A(m,k) * B(n,k)
+// ---------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16, PITCH = 132;
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
+
+struct GemmArgs {
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    int64_t Mdim, Ndim, Kdim;           // Kdim = contraction length
+    const float* bias; int relu;        // FWD
+    const float* mask; int64_t ldm;     // DGRAD: multiply by (mask > 0)
+    const float* addend; int64_t ldadd; // DGRAD: += addend
+    int n_valid;                        // WGRAD: columns < n_valid are written
+    int64_t k_per_split;                // WGRAD: contraction rows per blockIdx.z
+};
+
+template <bool T>
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t rows,
+                                          int64_t k0, int64_t kend, int tid, float4 (&reg)[2]) {
+    // T=false: P[(row0+r)*ld + k0+kk], float4 along k.   T=true: P[(k0+kk)*ld + row0+r], float4 along r.
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * 256;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!T) {
+            const int r = idx >> 2, kq = idx & 3;
+            if (row0 + r < rows && k0 + kq * 4 < kend) v = __ldg(reinterpret_cast<const float4*>(P + (row0 + r) * ld + k0 + kq * 4));
+        } else {
+            const int kk = idx >> 5, rq = idx & 31;
+            if (k0 + kk < kend && row0 + rq * 4 < rows) v = __ldg(reinterpret_cast<const float4*>(P + (k0 + kk) * ld + row0 + rq * 4));
+        }
+        reg[i] = v;
+    }
+}
+template <bool T>
+__device__ __forceinline__ void store_tile(float (*S)[PITCH], int tid, const float4 (&reg)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * 256;
+        if (!T) {
+            const int r = idx >> 2, kq = idx & 3;
+            S[kq * 4 + 0][r] = reg[i].x; S[kq * 4 + 1][r] = reg[i].y; S[kq * 4 + 2][r] = reg[i].z; S[kq * 4 + 3][r] = reg[i].w;
+        } else {
+            const int kk = idx >> 5, rq = idx & 31;
+            *reinterpret_cast<float4*>(&S[kk][rq * 4]) = reg[i];
+        }
+    }
+}
+
+template <bool AT, bool BT, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[BK][PITCH];
+    __shared__ __align__(16) float Bs[BK][PITCH];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+    int64_t kbeg = 0, kend = g.Kdim;
+    if (EPI == EPI_WGRAD) {
+        kbeg = (int64_t)blockIdx.z * g.k_per_split;
+        kend = kbeg + g.k_per_split < g.Kdim ? kbeg + g.k_per_split : g.Kdim;
+        if (kbeg >= kend) return;
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 ra[2], rb[2];
+    load_tile<AT>(g.A, g.lda, m0, g.Mdim, kbeg, kend, tid, ra);
+    load_tile<BT>(g.B, g.ldb, n0, g.Ndim, kbeg, kend, tid, rb);
+    store_tile<AT>(As, tid, ra); store_tile<BT>(Bs, tid, rb);
+    __syncthreads();
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        const bool more = k0 + BK < kend;
+        if (more) {
+            load_tile<AT>(g.A, g.lda, m0, g.Mdim, k0 + BK, kend, tid, ra);
+            load_tile<BT>(g.B, g.ldb, n0, g.Ndim, k0 + BK, kend, tid, rb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        if (more) {
+            store_tile<AT>(As, tid, ra); store_tile<BT>(Bs, tid, rb);
+            __syncthreads();
+        }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.Mdim) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int64_t n = n0 + jh * 64 + tx * 4;
+            if (n >= g.Ndim) continue;
+            float v[4] = {acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]};
+            if (EPI == EPI_FWD) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+                if (g.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+                *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (EPI == EPI_DGRAD) {
+                if (g.addend) {
+                    const float4 ad = *reinterpret_cast<const float4*>(g.addend + m * g.ldadd + n);
+                    v[0] += ad.x; v[1] += ad.y; v[2] += ad.z; v[3] += ad.w;
+                }
+                if (g.mask) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + m * g.ldm + n));
+                    v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+                    v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+                }
+                *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < g.n_valid) atomicAdd(g.C + m * g.ldc + n + j, v[j]);
+            }
+        }
+    }
+}
+
+// column sums for the bias gradients: out[n] += sum_m Y[m*ld + n]
+__global__ void colsum_kernel(const float* __restrict__ Y, int64_t ld, float* __restrict__ out, int64_t Q, int Ncols,
+                              int64_t rows_per_block) {
+    const int col = threadIdx.x % Ncols, sub = threadIdx.x / Ncols, nsub = blockDim.x / Ncols;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < Q ? r0 + rows_per_block : Q;
+    float s = 0.f;
+    for (int64_t r = r0 + sub; r < r1; r += nsub) s += Y[r * ld + col];
+    atomicAdd(out + col, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// heads: sigma_out (256->1) and color_out (128->3), warp per point
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ C, const float* __restrict__ H8, int64_t ldh, const float* __restrict__ Wo,
+                const float* __restrict__ bo, const float* __restrict__ ws, const float* __restrict__ bs,
+                float* __restrict__ raw, int64_t Q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wo) + lane);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wo + 128) + lane);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(Wo + 256) + lane);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(ws) + lane);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(ws) + 32 + lane);
+    for (int64_t q = warp; q < Q; q += nwarps) {
+        const float4 c = *(reinterpret_cast<const float4*>(C + q * kColorHidden) + lane);
+        const float4 h0 = *(reinterpret_cast<const float4*>(H8 + q * ldh) + lane);
+        const float4 h1 = *(reinterpret_cast<const float4*>(H8 + q * ldh) + 32 + lane);
+        float r = c.x * w0.x + c.y * w0.y + c.z * w0.z + c.w * w0.w;
+        float g = c.x * w1.x + c.y * w1.y + c.z * w1.z + c.w * w1.w;
+        float b = c.x * w2.x + c.y * w2.y + c.z * w2.z + c.w * w2.w;
+        float s = h0.x * s0.x + h0.y * s0.y + h0.z * s0.z + h0.w * s0.w + h1.x * s1.x + h1.y * s1.y + h1.z * s1.z + h1.w * s1.w;
+        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); s = warp_sum(s);
+        if (lane == 0) reinterpret_cast<float4*>(raw)[q] = make_float4(r + bo[0], g + bo[1], b + bo[2], s + bs[0]);
+    }
+}
+
+// d_raw -> dC (masked by c>0), dH8 seed (= d_sigma * w_sigma), and the head parameter grads
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ d_raw, const float* __restrict__ C, const float* __restrict__ H8, int64_t ldh,
+                const float* __restrict__ Wo, const float* __restrict__ ws, float* __restrict__ dC,
+                float* __restrict__ dH8, float* __restrict__ gWo, float* __restrict__ gbo, float* __restrict__ gws,
+                float* __restrict__ gbs, int64_t Q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wo) + lane);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wo + 128) + lane);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(Wo + 256) + lane);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(ws) + lane);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(ws) + 32 + lane);
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, as0 = a0, as1 = a0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, bsig = 0.f;
+    for (int64_t q = warp; q < Q; q += nwarps) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(d_raw) + q);
+        const float4 c = *(reinterpret_cast<const float4*>(C + q * kColorHidden) + lane);
+        const float4 h0 = *(reinterpret_cast<const float4*>(H8 + q * ldh) + lane);
+        const float4 h1 = *(reinterpret_cast<const float4*>(H8 + q * ldh) + 32 + lane);
+        float4 dc;
+        dc.x = c.x > 0.f ? d.x * w0.x + d.y * w1.x + d.z * w2.x : 0.f;
+        dc.y = c.y > 0.f ? d.x * w0.y + d.y * w1.y + d.z * w2.y : 0.f;
+        dc.z = c.z > 0.f ? d.x * w0.z + d.y * w1.z + d.z * w2.z : 0.f;
+        dc.w = c.w > 0.f ? d.x * w0.w + d.y * w1.w + d.z * w2.w : 0.f;
+        *(reinterpret_cast<float4*>(dC + q * kColorHidden) + lane) = dc;
+        *(reinterpret_cast<float4*>(dH8 + q * kHidden) + lane) = make_float4(d.w * s0.x, d.w * s0.y, d.w * s0.z, d.w * s0.w);
+        *(reinterpret_cast<float4*>(dH8 + q * kHidden) + 32 + lane) = make_float4(d.w * s1.x, d.w * s1.y, d.w * s1.z, d.w * s1.w);
+        a0.x += d.x * c.x; a0.y += d.x * c.y; a0.z += d.x * c.z; a0.w += d.x * c.w;
+        a1.x += d.y * c.x; a1.y += d.y * c.y; a1.z += d.y * c.z; a1.w += d.y * c.w;
+        a2.x += d.z * c.x; a2.y += d.z * c.y; a2.z += d.z * c.z; a2.w += d.z * c.w;
+        as0.x += d.w * h0.x; as0.y += d.w * h0.y; as0.z += d.w * h0.z; as0.w += d.w * h0.w;
+        as1.x += d.w * h1.x; as1.y += d.w * h1.y; as1.z += d.w * h1.z; as1.w += d.w * h1.w;
+        if (lane == 0) { b0 += d.x; b1 += d.y; b2 += d.z; bsig += d.w; }
+    }
+    // block-level reduction in shared memory, then one atomic per element per block
+    __shared__ float red[3 * 128 + 256 + 4];
+    for (int i = threadIdx.x; i < 3 * 128 + 256 + 4; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w}, av2[4] = {a2.x, a2.y, a2.z, a2.w};
+    const float sv0[4] = {as0.x, as0.y, as0.z, as0.w}, sv1[4] = {as1.x, as1.y, as1.z, as1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        atomicAdd(&red[lane * 4 + j], av0[j]); atomicAdd(&red[128 + lane * 4 + j], av1[j]);
+        atomicAdd(&red[256 + lane * 4 + j], av2[j]);
+        atomicAdd(&red[384 + lane * 4 + j], sv0[j]); atomicAdd(&red[384 + 128 + lane * 4 + j], sv1[j]);
+    }
+    if (lane == 0) { atomicAdd(&red[640], b0); atomicAdd(&red[641], b1); atomicAdd(&red[642], b2); atomicAdd(&red[643], bsig); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 644; i += blockDim.x) {
+        const float v = red[i];
+        if (i < 384) atomicAdd(gWo + i, v);
+        else if (i < 640) atomicAdd(gws + (i - 384), v);
+        else if (i < 643) atomicAdd(gbo + (i - 640), v);
+        else atomicAdd(gbs, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing (fp32 section): flat state_dict order -> rows padded to Kpad, zero filled
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_fp32_kernel(const float* __restrict__ params, float* __restrict__ dstw, float* __restrict__ dstb,
+                                 int N, int K, int Kpad, int64_t w_off, int64_t b_off) {
+    const int total = N * Kpad;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx / Kpad, k = idx % Kpad;
+        dstw[idx] = k < K ? params[w_off + (int64_t)n * K + k] : 0.f;
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) dstb[n] = params[b_off + n];
+}
+
+PackedLayout packed_layout() {
+    PackedLayout L;
+    size_t off = 0;
+    for (int l = 0; l < 12; ++l) {
+        const LayerDesc d = layer_desc(l);
+        L.f32_w[l] = off; off += align_up((size_t)d.N * d.Kpad * sizeof(float), 256);
+        L.f32_b[l] = off; off += align_up((size_t)d.N * sizeof(float), 256);
+    }
+    L.bf16_off = off;
+    L.bf16_bytes = tc_packed_bytes();
+    L.total = off + L.bf16_bytes;
+    return L;
+}
+
+int pack_fp32(const float* params, void* packed, cudaStream_t st) {
+    const PackedLayout L = packed_layout();
+    char* base = reinterpret_cast<char*>(packed);
+    for (int l = 0; l < 12; ++l) {
+        const LayerDesc d = layer_desc(l);
+        const int total = d.N * d.Kpad;
+        pack_fp32_kernel<<<(total + 255) / 256, 256, 0, st>>>(params, reinterpret_cast<float*>(base + L.f32_w[l]),
+                                                            reinterpret_cast<float*>(base + L.f32_b[l]), d.N, d.K, d.Kpad,
+                                                            d.w_off, d.b_off);
+        NSB_LAUNCH_CHECK("pack_fp32_kernel");
+    }
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------
+static inline const float* PW(const void* packed, const PackedLayout& L, int l) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + L.f32_w[l]);
+}
+static inline const float* PB(const void* packed, const PackedLayout& L, int l) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + L.f32_b[l]);
+}
+
+static int gemm_fwd(const float* X, int64_t ldx, const float* W, int Kpad, const float* bias, float* Y, int64_t ldy,
+                    int64_t Q, int N, int relu, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = X; g.lda = ldx; g.B = W; g.ldb = Kpad; g.C = Y; g.ldc = ldy; g.Mdim = Q; g.Ndim = N; g.Kdim = Kpad;
+    g.bias = bias; g.relu = relu;
+    dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(N, BN), 1);
+    sgemm_kernel<false, false, EPI_FWD><<<grid, 256, 0, st>>>(g);
+    NSB_LAUNCH_CHECK("sgemm_fwd");
+    return NSB_OK;
+}
+// dX[Q, n_in] = dY[Q, n_out] . W[n_out, ldw]  (first n_in columns), (+addend) (*mask)
+static int gemm_dgrad(const float* dY, int64_t ldy, const float* W, int ldw, float* dX, int64_t ldx, int64_t Q,
+                      int n_out, int n_in, const float* mask, int64_t ldm, const float* addend, int64_t ldadd,
+                      cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dY; g.lda = ldy; g.B = W; g.ldb = ldw; g.C = dX; g.ldc = ldx; g.Mdim = Q; g.Ndim = n_in; g.Kdim = n_out;
+    g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd;
+    dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(n_in, BN), 1);
+    sgemm_kernel<false, true, EPI_DGRAD><<<grid, 256, 0, st>>>(g);
+    NSB_LAUNCH_CHECK("sgemm_dgrad");
+    return NSB_OK;
+}
+// gW[n_out, K] += dY[Q, n_out]^T . X[Q, Kpad] ; gb[n_out] += colsum(dY)
+static int gemm_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* gW, float* gb, int64_t Q,
+                      int n_out, int K, int Kpad, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dY; g.lda = ldy; g.B = X; g.ldb = ldx; g.C = gW; g.ldc = K; g.Mdim = n_out; g.Ndim = Kpad; g.Kdim = Q;
+    g.n_valid = K;
+    const int tiles = (int)(cdiv(n_out, BM) * cdiv(Kpad, BN));
+    int64_t splits = (int64_t)num_sms() * 2 / tiles;
+    if (splits < 1) splits = 1;
+    int64_t kps = cdiv(cdiv(Q, splits), BK) * BK;
+    if (kps < 256) kps = 256;
+    splits = cdiv(Q, kps);
+    g.k_per_split = kps;
+    dim3 grid((unsigned)cdiv(n_out, BM), (unsigned)cdiv(Kpad, BN), (unsigned)splits);
+    sgemm_kernel<true, true, EPI_WGRAD><<<grid, 256, 0, st>>>(g);
+    NSB_LAUNCH_CHECK("sgemm_wgrad");
+    const int64_t rpb = 2048;
+    colsum_kernel<<<(unsigned)cdiv(Q, rpb), 256, 0, st>>>(dY, ldy, gb, Q, n_out, rpb);
+    NSB_LAUNCH_CHECK("colsum_kernel");
+    return NSB_OK;
+}
+
+static int elem_grid(int64_t total) {
+    const int64_t want = cdiv(total, 256), cap = (int64_t)num_sms() * 16;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int fp32_prepare_rays(const float* o, const float* d, const float* z, const float* rn, const float* vd, void* ws,
+                      int64_t B, int N, int stash, cudaStream_t st) {
+    Fp32Ws w = carve_fp32(ws, B * (int64_t)N, stash);
+    prepare_from_rays_kernel<<<elem_grid(B * (int64_t)N * 16), 256, 0, st>>>(o, d, z, rn, vd, w.X0, w.X4, w.XC, B, N);
+    NSB_LAUNCH_CHECK("prepare_from_rays_kernel");
+    return NSB_OK;
+}
+int fp32_prepare_enc(const float* ep, const float* ed, void* ws, int64_t Q, int stash, cudaStream_t st) {
+    Fp32Ws w = carve_fp32(ws, Q, stash);
+    prepare_from_enc_kernel<<<elem_grid(Q * 96), 256, 0, st>>>(ep, ed, w.X0, w.X4, w.XC, Q);
+    NSB_LAUNCH_CHECK("prepare_from_enc_kernel");
+    return NSB_OK;
+}
+
+// mlps.py:221-278 on the prepared buffers
+int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash, cudaStream_t st) {
+    const PackedLayout L = packed_layout();
+    Fp32Ws w = carve_fp32(ws, Q, stash);
+    const float* in = w.X0; int64_t ldin = kPosPad;
+    for (int l = 0; l < 8; ++l) {
+        const LayerDesc d = layer_desc(l);
+        if (l == 4) { in = w.X4; ldin = kSkipPad; }
+        NSB_TRY(gemm_fwd(in, ldin, PW(packed, L, l), d.Kpad, PB(packed, L, l), w.out[l], w.out_ld[l], Q, 256, 1, st));
+        in = w.out[l]; ldin = w.out_ld[l];
+    }
+    const float* H8 = w.out[7];
+    NSB_TRY(gemm_fwd(H8, kHidden, PW(packed, L, 8), 256, PB(packed, L, 8), w.XC, kColorPad, Q, 256, 0, st));       // feature
+    NSB_TRY(gemm_fwd(w.XC, kColorPad, PW(packed, L, 10), kColorPad, PB(packed, L, 10), w.C, kColorHidden, Q, 128, 1, st));  // color_fc
+    head_fwd_kernel<<<elem_grid(Q * 32), 256, 0, st>>>(w.C, H8, kHidden, PW(packed, L, 11), PB(packed, L, 11),
+                                                      PW(packed, L, 9), PB(packed, L, 9), raw, Q);
+    NSB_LAUNCH_CHECK("head_fwd_kernel");
+    return NSB_OK;
+}
+
+// parameter grads (accumulated into flat `grads`) from the stashed activations
+int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st) {
+    const PackedLayout L = packed_layout();
+    Fp32Ws w = carve_fp32(ws, Q, 1);
+    const float* H8 = w.out[7];
+    const LayerDesc dsg = layer_desc(9), dco = layer_desc(11), dfc = layer_desc(10), dft = layer_desc(8);
+    int hb_grid = num_sms() * 4;
+    if ((int64_t)hb_grid * 8 > Q) hb_grid = (int)cdiv(Q, 8);
+    head_bwd_kernel<<<hb_grid, 256, 0, st>>>(d_raw, w.C, H8, kHidden, PW(packed, L, 11), PW(packed, L, 9), w.dC, w.dA,
+                                             grads + dco.w_off, grads + dco.b_off, grads + dsg.w_off, grads + dsg.b_off, Q);
+    NSB_LAUNCH_CHECK("head_bwd_kernel");
+    // color_fc
+    NSB_TRY(gemm_wgrad(w.dC, kColorHidden, w.XC, kColorPad, grads + dfc.w_off, grads + dfc.b_off, Q, 128, dfc.K, dfc.Kpad, st));
+    NSB_TRY(gemm_dgrad(w.dC, kColorHidden, PW(packed, L, 10), kColorPad, w.dB, kHidden, Q, 128, 256, nullptr, 0, nullptr, 0, st));  // dFeat
+    // feature (no activation); dH8 = (dFeat.Wf + dsigma*w_sigma) * (H8>0)
+    NSB_TRY(gemm_wgrad(w.dB, kHidden, H8, kHidden, grads + dft.w_off, grads + dft.b_off, Q, 256, 256, 256, st));
+    NSB_TRY(gemm_dgrad(w.dB, kHidden, PW(packed, L, 8), 256, w.dA, kHidden, Q, 256, 256, H8, kHidden, w.dA, kHidden, st));
+    float* dcur = w.dA; float* dnext = w.dB;
+    for (int l = 7; l >= 0; --l) {
+        const LayerDesc d = layer_desc(l);
+        const float* Xin = l == 0 ? w.X0 : (l == 4 ? w.X4 : w.out[l - 1]);
+        const int64_t ldx = l == 0 ? kPosPad : (l == 4 ? kSkipPad : w.out_ld[l - 1]);
+        NSB_TRY(gemm_wgrad(dcur, kHidden, Xin, ldx, grads + d.w_off, grads + d.b_off, Q, 256, d.K, d.Kpad, st));
+        if (l > 0) {
+            // input of layer l is relu(out[l-1]) -> mask by out[l-1] > 0 (first 256 columns only at the skip layer)
+            NSB_TRY(gemm_dgrad(dcur, kHidden, PW(packed, L, l), d.Kpad, dnext, kHidden, Q, 256, 256, w.out[l - 1],
+                               w.out_ld[l - 1], nullptr, 0, st));
+            float* t = dcur; dcur = dnext; dnext = t;
+        }
+    }
+    return NSB_OK;
+}
+
+// ---- Adam --------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
+                            float inv_sqrt_bc2, float grad_scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr_over_bc1 * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    }
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
+    if (!x || !out || Q < 0 || D < 1 || L < 0) return NSB_E_BADARG;
+    if (Q == 0) return NSB_OK;
+    const int od = D * (include_input ? 1 : 0) + 2 * L * D;
+    encode_kernel<<<elem_grid(Q * od), 256, 0, as_stream(stream)>>>(x, out, Q, D, L, include_input);
+    NSB_LAUNCH_CHECK("encode_kernel");
+    return NSB_OK;
+}
+
+extern "C" int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+    if (!params || !grads || !m || !v || n < 1 || t < 1) return NSB_E_BADARG;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+    adam_kernel<<<elem_grid(n), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
+                                                            (float)(1.0 / sqrt(bc2)), grad_scale);
+    NSB_LAUNCH_CHECK("adam_kernel");
+    return NSB_OK;
+}

@@ -1,0 +1,119 @@
+// Shared helpers for the libnsb kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nsb.h"
+
+namespace nsb {
+
+// ---- launch bookkeeping -------------------------------------------------------------------------
+extern int64_t g_launches;          // nsb_launch_count()
+extern char g_cuda_err[256];
+int check_launch(const char* what);  // cudaGetLastError -> NSB_E_CUDA
+int num_sms();
+
+#define NSB_LAUNCH_CHECK(name)                        \
+    do {                                              \
+        ++::nsb::g_launches;                          \
+        int _e = ::nsb::check_launch(name);           \
+        if (_e) return _e;                            \
+    } while (0)
+
+#define NSB_TRY(expr)          \
+    do {                       \
+        int _e = (expr);       \
+        if (_e) return _e;     \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- Philox4x32-10 (counter based; one call -> 4 x 32 random bits) --------------------------------
+__host__ __device__ inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                             uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__host__ __device__ inline uint4 philox4(uint64_t seed, uint64_t stream_id, uint64_t idx) {
+    uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = (uint32_t)stream_id, c3 = (uint32_t)(stream_id >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// uniform in [0,1) on the 2^-24 grid (what torch.rand yields for fp32)
+__host__ __device__ inline float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__device__ inline float philox_uniform(uint64_t seed, uint64_t stream_id, uint64_t idx) {
+    uint4 r = philox4(seed, stream_id, idx >> 2);
+    uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    return u01(w);
+}
+// one N(0,1) draw per index (Box-Muller on two words of the same Philox block)
+__device__ inline float philox_normal(uint64_t seed, uint64_t stream_id, uint64_t idx) {
+    uint4 r = philox4(seed, stream_id, idx >> 1);
+    uint32_t a = (idx & 1) ? r.z : r.x, b = (idx & 1) ? r.w : r.y;
+    float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0,1]
+    float u2 = u01(b);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ---- warp helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ATen linspace(0,1,n)[i] in fp32 (symmetric fill; the upper half is one fused multiply-add)
+__host__ __device__ inline float linspace01(int i, int n) {
+    if (n <= 1) return 0.0f;
+    const float step = 1.0f / (float)(n - 1);
+    if (i < n / 2) return step * (float)i;
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
+#else
+    return (float)(1.0 - (double)step * (double)(n - 1 - i));
+#endif
+}
+
+// ---- NeRF(63,27,8,256,4) geometry ---------------------------------------------------------------------
+constexpr int kHidden = 256;
+constexpr int kPosDim = 63, kPosPad = 64;
+constexpr int kDirDim = 27;
+constexpr int kSkipIn = 319, kSkipPad = 320;     // [h(256) | gamma(x)(63) | 0]
+constexpr int kColorIn = 283, kColorPad = 288;   // [feat(256) | gamma(d)(27) | 0...]
+constexpr int kColorHidden = 128;
+constexpr int kNumGemmLayers = 10;               // mlp.0..7, feature, color_fc  (sigma_out/color_out are "heads")
+
+struct LayerDesc { int N, K, Kpad; int64_t w_off, b_off; };   // offsets into the flat state_dict-ordered params
+// index: 0..7 trunk, 8 feature, 9 sigma_out, 10 color_fc, 11 color_out
+__host__ __device__ inline LayerDesc layer_desc(int l) {
+    const int Ns[12] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 128, 3};
+    const int Ks[12] = {63, 256, 256, 256, 319, 256, 256, 256, 256, 256, 283, 128};
+    const int Kp[12] = {64, 256, 256, 256, 320, 256, 256, 256, 256, 256, 288, 128};
+    int64_t off = 0;
+    for (int i = 0; i < l; ++i) off += (int64_t)Ns[i] * Ks[i] + Ns[i];
+    LayerDesc d; d.N = Ns[l]; d.K = Ks[l]; d.Kpad = Kp[l]; d.w_off = off; d.b_off = off + (int64_t)Ns[l] * Ks[l];
+    return d;
+}
+
+// Packed weights of one net (nsb_pack_weights): [fp32 padded section | bf16 tensor-core section]
+struct PackedLayout {
+    size_t f32_w[12], f32_b[12];   // byte offsets; rows padded to Kpad floats
+    size_t bf16_off;               // start of the bf16 image (layout owned by field_tc.cu)
+    size_t bf16_bytes;
+    size_t total;
+};
+PackedLayout packed_layout();
+size_t tc_packed_bytes();          // field_tc.cu
+
+}  // namespace nsb

@@ -1,0 +1,150 @@
+"""The vanilla train step (train/trainer.py:876-1013 + :717-725) on libnsb.
+
+``VanillaTrainer`` owns what the reference ``Trainer`` owns for the hot path -- encoders, coarse/fine
+NeRF, Adam state -- and exposes
+
+* ``_train_step(batch)``: the reference's method contract (dict with an autograd ``loss``; the caller runs
+  ``loss.backward()`` and any torch optimizer over ``parameters()``), implemented as ONE library call that
+  computes forward and backward together, and
+* ``step(batch)``: the fast path -- forward+backward, optional gradient all-reduce, fused Adam and weight
+  re-pack as three library calls on the current stream, capturable in a CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .encoders import get_vanilla_nerf_encoders
+from .mlps import NeRF
+
+BATCH_KEYS = ("rays_o_marching", "rays_d_marching_unit", "rays_d_marching_norm", "rays_d_world_unit", "rgb")
+
+
+def mse2psnr(mse: torch.Tensor) -> torch.Tensor:                       # trainer.py:77-78
+    return -10.0 * torch.log10(mse.clamp_min(1e-10))
+
+
+class _FusedStepFn(torch.autograd.Function):
+    """loss = mse(comp_c)+mse(comp_f); forward already ran the backward kernels, so ``backward`` only scales."""
+
+    @staticmethod
+    def forward(ctx, tr, batch, draws, *params):
+        scal, comp_c, comp_f = tr._fwd_bwd(batch, draws, grad_scale=1.0)
+        ctx.tr = tr
+        ctx.mark_non_differentiable(comp_c, comp_f)
+        return scal[0].clone(), scal[1].clone(), comp_c, comp_f
+
+    @staticmethod
+    def backward(ctx, g_loss, g_psnr, g_cc, g_cf):
+        tr = ctx.tr
+        gc = tr.nerf_c.unflatten(tr.grads_c * g_loss)
+        gf = tr.nerf_f.unflatten(tr.grads_f * g_loss)
+        return (None, None, None) + tuple(gc) + tuple(gf)
+
+
+class VanillaTrainer:
+    def __init__(self, device="cuda", *, rays_per_batch=1024, nc=64, nf=128, near=2.0, far=6.0, white_bkgd=True,
+                 raw_noise_std=1.0, infinite_last_bin=True, det_fine=False, lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
+                 mode="fp32", seed=0, sigma_bias=None, process_group=None):
+        # hard-coded vanilla settings of the reference: trainer.py:277-291, :411-416; train_nerf.py:275,281
+        self.device = torch.device(device)
+        self.nc, self.nf, self.samp_near, self.samp_far = int(nc), int(nf), float(near), float(far)
+        self.white_bkgd, self.raw_noise_std = bool(white_bkgd), float(raw_noise_std)
+        self.infinite_last_bin, self.det_fine = bool(infinite_last_bin), bool(det_fine)
+        self.sigma_activation = "relu"
+        self.rays_per_batch = int(rays_per_batch)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.mode = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}[mode]
+        self.seed, self.global_step, self.adam_t = int(seed), 0, 0
+        self.pg = process_group
+        gen_state = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        self.pos_enc, self.dir_enc = get_vanilla_nerf_encoders()
+        self.nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu", mode=mode)      # trainer.py:326-341
+        self.nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu", mode=mode)
+        torch.random.set_rng_state(gen_state)
+        if sigma_bias is not None:
+            with torch.no_grad():
+                self.nerf_c.sigma_out.bias.fill_(sigma_bias); self.nerf_f.sigma_out.bias.fill_(sigma_bias)
+        for m in (self.pos_enc, self.dir_enc, self.nerf_c, self.nerf_f):
+            m.to(self.device)
+        n = _lib.N_PARAMS
+        z = lambda: torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.grads_c, self.grads_f = z(), z()
+        self.m_c, self.v_c, self.m_f, self.v_f = z(), z(), z(), z()
+        self.scalars = torch.zeros(4, device=self.device, dtype=torch.float32)
+        self._ws = None
+        self.nerf_c.packed(); self.nerf_f.packed()
+
+    # ---- helpers ---------------------------------------------------------------------------------------
+    def parameters(self):
+        return list(self.nerf_c.parameters()) + list(self.nerf_f.parameters())     # trainer.py:383-386
+
+    def _flags(self):
+        return (_lib.WHITE_BKGD if self.white_bkgd else 0) | (_lib.INFINITE_LAST_BIN if self.infinite_last_bin else 0)
+
+    def _workspace(self, B):
+        need = _lib.lib().nsb_train_workspace_bytes(B, self.nc, self.nf, self.mode)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def _fwd_bwd(self, batch, draws=None, grad_scale=1.0):
+        """nsb_train_fwd_bwd: fills self.grads_c/grads_f and self.scalars; returns (scalars, comp_c, comp_f)."""
+        L = _lib.lib()
+        o, d, rn, vd, tgt = (_lib.f32c(batch[k]) for k in BATCH_KEYS)
+        B = o.shape[0]
+        ws, wsb = self._workspace(B)
+        comp_c = torch.empty((B, 3), device=self.device); comp_f = torch.empty((B, 3), device=self.device)
+        draws = draws or {}
+        g = lambda k: None if draws.get(k) is None else _lib.f32c(draws[k])
+        _lib.check(L.nsb_train_fwd_bwd(
+            _lib.ptr(o), _lib.ptr(d), _lib.ptr(rn.reshape(B)), _lib.ptr(vd), _lib.ptr(tgt),
+            _lib.ptr(self.nerf_c.packed()), _lib.ptr(self.nerf_f.packed()), _lib.ptr(self.grads_c), _lib.ptr(self.grads_f),
+            _lib.ptr(self.scalars), _lib.ptr(comp_c), _lib.ptr(comp_f), _lib.ptr(ws), wsb, B, self.nc, self.nf,
+            self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode,
+            float(grad_scale), self.seed, self.global_step, _lib.ptr(g("U")), _lib.ptr(g("u_fine")),
+            _lib.ptr(g("noise_c")), _lib.ptr(g("noise_f")), _lib.stream()), "nsb_train_fwd_bwd")
+        return self.scalars, comp_c, comp_f
+
+    # ---- reference-compatible step ---------------------------------------------------------------------
+    def _train_step(self, batch, draws=None) -> dict:
+        """Same contract as Trainer._train_step (trainer.py:876-1013): ``loss`` carries autograd history to the
+        48 parameters, so ``loss.backward(); torch.optim.Adam(...).step()`` works unchanged."""
+        loss, psnr, comp_c, comp_f = _FusedStepFn.apply(self, batch, draws, *self.nerf_c.ordered_params(),
+                                                        *self.nerf_f.ordered_params())
+        return {"loss": loss, "psnr": psnr.detach(), "comp_f": comp_f.detach(), "comp_c": comp_c.detach()}
+
+    # ---- fast path ---------------------------------------------------------------------------------------
+    def step(self, batch, draws=None):
+        """forward + backward (+ all-reduce) + Adam + re-pack.  Returns the device scalars tensor
+        [loss, psnr, mse_c, mse_f] of this rank's shard (no host sync)."""
+        world = 1
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(self.pg)
+        self._fwd_bwd(batch, draws, grad_scale=1.0)
+        if world > 1:                                        # one sum-allreduce per net on the flat fp32 buffers
+            torch.distributed.all_reduce(self.grads_c, group=self.pg)
+            torch.distributed.all_reduce(self.grads_f, group=self.pg)
+        self.adam_t += 1
+        self.global_step += 1
+        L = _lib.lib()
+        for nerf, g, m, v in ((self.nerf_c, self.grads_c, self.m_c, self.v_c), (self.nerf_f, self.grads_f, self.m_f, self.v_f)):
+            flat = nerf.flat_params()
+            _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, self.lr,
+                                       self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.stream()),
+                       "nsb_adam_step")
+            nerf.packed(force=True)
+        return self.scalars
+
+    def state_dict(self):                                      # trainer.py:596-621 (hot-path subset)
+        return {"step": self.global_step, "nerf_c": self.nerf_c.state_dict(), "nerf_f": self.nerf_f.state_dict(),
+                "opt": {"t": self.adam_t, "m_c": self.m_c, "v_c": self.v_c, "m_f": self.m_f, "v_f": self.v_f}}
+
+    def load_state_dict(self, sd):
+        self.global_step = int(sd["step"])
+        self.nerf_c.load_state_dict(sd["nerf_c"]); self.nerf_f.load_state_dict(sd["nerf_f"])
+        self.adam_t = int(sd["opt"]["t"])
+        for k in ("m_c", "v_c", "m_f", "v_f"):
+            getattr(self, k).copy_(sd["opt"][k])
+        self.nerf_c.packed(force=True); self.nerf_f.packed(force=True)

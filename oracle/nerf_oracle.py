@@ -113,49 +113,74 @@ def unflatten_params(flat: np.ndarray) -> dict:
     return out
 
 
-def mlp_forward(p: dict, enc_pos: np.ndarray, enc_dir: np.ndarray, keep: bool = False):
-    """mlps.py:221-278.  Returns raw [r,g,b,sigma] (Q,4); with keep=True also the
-    tensors the backward needs."""
-    h = _f(enc_pos)
+_CHUNK = 8192     # rows per block: keeps the elementwise passes cache-resident (numpy runs them on one thread)
+
+
+def _mlp_forward_block(p, enc_pos, enc_dir, keep):
+    h = enc_pos
     xs, hs = [], []
     for i in range(8):
         if i == 4:                                        # mlps.py:225-227: cat([h, enc_pos]) (h first)
             h = np.concatenate([h, enc_pos], axis=-1)
         xs.append(h)
-        h = np.maximum(h @ p[f"mlp.{i}.weight"].T + p[f"mlp.{i}.bias"], F32(0))   # :244
+        h = h @ p[f"mlp.{i}.weight"].T
+        h += p[f"mlp.{i}.bias"]
+        np.maximum(h, F32(0), out=h)                      # :244
         hs.append(h)
     sigma_raw = h @ p["sigma_out.weight"].T + p["sigma_out.bias"]                 # :265
     feat = h @ p["feature.weight"].T + p["feature.bias"]                          # :268 (no act)
-    cin = np.concatenate([feat, _f(enc_dir)], axis=-1)                            # :271
+    cin = np.concatenate([feat, enc_dir], axis=-1)                                # :271
     c = np.maximum(cin @ p["color_fc.weight"].T + p["color_fc.bias"], F32(0))     # :272
     rgb_raw = c @ p["color_out.weight"].T + p["color_out.bias"]                   # :273
     out = np.concatenate([rgb_raw, sigma_raw], axis=-1).astype(F32)               # :276
-    if keep:
-        return out, dict(xs=xs, hs=hs, cin=cin, c=c)
-    return out
+    return out, (dict(xs=xs, hs=hs, cin=cin, c=c) if keep else None)
 
 
-def mlp_backward(p: dict, cache: dict, d_out: np.ndarray) -> dict:
-    """Autograd of mlp_forward w.r.t. the parameters only (inputs carry no grad,
-    SURVEY section 8 a12)."""
-    g = {}
+def mlp_forward(p: dict, enc_pos: np.ndarray, enc_dir: np.ndarray, keep: bool = False):
+    """mlps.py:221-278.  Returns raw [r,g,b,sigma] (Q,4); with keep=True also the
+    tensors the backward needs (a list of per-row-block caches)."""
+    enc_pos, enc_dir = _f(enc_pos), _f(enc_dir)
+    outs, caches = [], []
+    for s in range(0, max(enc_pos.shape[0], 1), _CHUNK):
+        o, c = _mlp_forward_block(p, enc_pos[s:s + _CHUNK], enc_dir[s:s + _CHUNK], keep)
+        outs.append(o); caches.append(c)
+    out = np.concatenate(outs, axis=0)
+    return (out, caches) if keep else out
+
+
+def _mlp_backward_block(p, cache, d_out, g):
     xs, hs, cin, c = cache["xs"], cache["hs"], cache["cin"], cache["c"]
     h8 = hs[7]
     d_rgb = _f(d_out[:, :3]); d_sig = _f(d_out[:, 3:4])
-    g["color_out.weight"] = d_rgb.T @ c; g["color_out.bias"] = d_rgb.sum(0)
+
+    def acc(name, val):
+        g[name] = val if name not in g else g[name] + val
+
+    acc("color_out.weight", d_rgb.T @ c); acc("color_out.bias", d_rgb.sum(0))
     dc = (d_rgb @ p["color_out.weight"]) * (c > 0)
-    g["color_fc.weight"] = dc.T @ cin; g["color_fc.bias"] = dc.sum(0)
+    acc("color_fc.weight", dc.T @ cin); acc("color_fc.bias", dc.sum(0))
     dfeat = (dc @ p["color_fc.weight"])[:, :256]
-    g["feature.weight"] = dfeat.T @ h8; g["feature.bias"] = dfeat.sum(0)
-    g["sigma_out.weight"] = d_sig.T @ h8; g["sigma_out.bias"] = d_sig.sum(0)
+    acc("feature.weight", dfeat.T @ h8); acc("feature.bias", dfeat.sum(0))
+    acc("sigma_out.weight", d_sig.T @ h8); acc("sigma_out.bias", d_sig.sum(0))
     dh = dfeat @ p["feature.weight"] + d_sig @ p["sigma_out.weight"]
     for i in range(7, -1, -1):
-        dh = dh * (hs[i] > 0)
-        g[f"mlp.{i}.weight"] = dh.T @ xs[i]; g[f"mlp.{i}.bias"] = dh.sum(0)
+        dh *= (hs[i] > 0)
+        acc(f"mlp.{i}.weight", dh.T @ xs[i]); acc(f"mlp.{i}.bias", dh.sum(0))
         if i > 0:
             dh = dh @ p[f"mlp.{i}.weight"]
             if i == 4:
-                dh = dh[:, :256]
+                dh = np.ascontiguousarray(dh[:, :256])
+
+
+def mlp_backward(p: dict, caches: list, d_out: np.ndarray) -> dict:
+    """Autograd of mlp_forward w.r.t. the parameters only (inputs carry no grad,
+    SURVEY section 8 a12)."""
+    g = {}
+    s = 0
+    for cache in caches:
+        n = cache["c"].shape[0]
+        _mlp_backward_block(p, cache, d_out[s:s + n], g)
+        s += n
     return {k: _f(v) for k, v in g.items()}
 
 

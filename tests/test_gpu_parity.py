@@ -1,0 +1,291 @@
+"""Parity of the CUDA path (through the C ABI, via the Python host mirror) against the oracle and the
+reference-generated golden vectors.  Tolerances: bit-exact for sample_pdf bin indices, stratified z and
+the merge; 1e-4 relative (+1e-6 absolute floor) for composited rgb/depth/opacity in fp32 mode."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, pdf_tolerance
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+def N(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close(a, b, rtol=1e-4, atol=1e-6):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def load_nerf(seed, sigma_bias, mode="fp32"):
+    import nerf_sandbox_b200 as nsb
+    p = O.init_params(np.random.default_rng(int(seed)), sigma_bias=float(sigma_bias))
+    net = nsb.NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu", mode=mode).to(DEV)
+    net.load_state_dict({k: T(v) for k, v in p.items()})
+    return net, p
+
+
+@pytest.fixture(scope="module")
+def nsb():
+    import nerf_sandbox_b200 as m
+    from nerf_sandbox_b200 import _lib
+    _lib.lib()                                   # loud failure if the CUDA library is missing
+    assert torch.cuda.is_available()
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------- K1 encoder
+def test_encoder(nsb):
+    g = golden("encoder")
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    ep = N(pe.to(DEV)(T(g["x"]))); ed = N(de.to(DEV)(T(g["d"])))
+    close(ep, g["enc_pos"], 0, 3e-4)             # |arg| up to 3072 rad; sinf vs Sleef ulps
+    close(ed, g["enc_dir"], 0, 2e-6)
+    assert ep.shape == (96, 63) and ed.shape == (96, 27)
+    close(N(pe(T(g["x"]).reshape(8, 12, 3))).reshape(96, 63), ep, 0, 0)      # leading dims preserved
+    assert pe(torch.zeros((0, 3), device=DEV)).shape == (0, 63)                # empty input
+
+
+# ---------------------------------------------------------------------------------------------------- K2 samplers
+def test_stratified_bit_exact(nsb):
+    from nerf_sandbox_b200 import _lib
+    g = golden("sampler")
+    L = _lib.lib()
+    for i in range(int(g["n_cases"])):
+        near, far, nc = float(g[f"near{i}"]), float(g[f"far{i}"]), int(g[f"nc{i}"])
+        U = T(g[f"U{i}"])
+        z = torch.empty_like(U)
+        _lib.check(L.nsb_stratified_z(_lib.ptr(z), _lib.ptr(U), U.shape[0], nc, near, far, 1, 0, 0, _lib.stream()))
+        assert np.array_equal(N(z), g[f"z{i}"]), f"case {i}"
+        _lib.check(L.nsb_stratified_z(_lib.ptr(z), None, U.shape[0], nc, near, far, 0, 0, 0, _lib.stream()))
+        assert np.array_equal(N(z)[3], g[f"zlin{i}"]), f"linspace case {i}"
+        # Philox jitter: stays inside its stratum, sorted
+        _lib.check(L.nsb_stratified_z(_lib.ptr(z), None, U.shape[0], nc, near, far, 1, 123, 7, _lib.stream()))
+        zz = N(z)
+        assert (np.diff(zz, axis=-1) >= 0).all() and zz.min() >= near and zz.max() <= far
+        assert np.unique(zz[:, 1]).size > 1
+
+
+def test_sample_pdf_indices_bit_exact_and_values(nsb):
+    g = golden("sample_pdf")
+    M = g["wb"].shape[1]
+    edges = O.pdf_edges(g["bins_mid"], M)
+    # north star: bit-exact bin indices given the same CDF and uniforms
+    out, inds = nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 128, u=T(g["u"]), cdf=T(g["cdf_mid"]), return_inds=True)
+    assert np.array_equal(N(inds).astype(np.int64), g["inds_mid_rand128"])
+    assert inds.dtype == torch.int64
+    close(N(out), g["out_mid_rand128"], 0, 1e-6)
+    out, inds = nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 128, deterministic=True, cdf=T(g["cdf_mid"]), return_inds=True)
+    assert np.array_equal(N(inds).astype(np.int64), g["inds_mid_det128"])
+    close(N(out), g["out_mid_det128"], 0, 1e-6)
+    # own CDF (warp scan): indices may flip where u sits on a CDF value; values continuous
+    out, inds = nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 128, u=T(g["u"]), return_inds=True)
+    same = N(inds).astype(np.int64) == g["inds_mid_rand128"]
+    assert same.mean() > 0.999
+    tol = pdf_tolerance(edges, g["cdf_mid"], g["inds_mid_rand128"])
+    assert (np.abs(N(out) - g["out_mid_rand128"]) <= tol)[same].all()
+    # edges input, deterministic (author's recipe, compare_nerf_repos.py:439-463: OK threshold 1e-5)
+    close(N(nsb.sample_pdf(T(g["edges"]), T(g["w_edges"]), 64, deterministic=True)), g["out_edges_det64"], 0, 1e-5)
+    close(N(nsb.sample_pdf(T(g["m1_bins"]), T(g["m1_w"]), 8, deterministic=True)), g["out_m1_det8"], 0, 1e-6)
+    close(N(nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 1, deterministic=True)), g["out_mid_det1"], 0, 1e-5)
+    # Philox uniforms: in range, reproducible with a seed, ~uniform in CDF space
+    a = nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 128, seed=5); b = nsb.sample_pdf(T(g["bins_mid"]), T(g["wb"]), 128, seed=5)
+    assert torch.equal(a, b) and float(a.min()) >= edges.min() - 1e-6 and float(a.max()) <= edges.max() + 1e-6
+    with pytest.raises(ValueError):
+        nsb.sample_pdf(T(g["bins_mid"])[:, :10], T(g["wb"]), 8)
+    assert nsb.sample_pdf(T(g["bins_mid"])[:0], T(g["wb"])[:0], 8, deterministic=True).shape == (0, 8)
+
+
+def test_resample_merge(nsb):
+    from nerf_sandbox_b200 import _lib
+    g = golden("sample_pdf")
+    L = _lib.lib()
+    zc, w_c, u = T(g["zc"]), T(g["w_c"]), T(g["u"])
+    B, Nc = zc.shape
+    for det in (0, 1):
+        z_all = torch.empty((B, Nc + 128), device=DEV); zf = torch.empty((B, 128), device=DEV)
+        _lib.check(L.nsb_resample_merge(_lib.ptr(zc), _lib.ptr(w_c), _lib.ptr(u), _lib.ptr(z_all), _lib.ptr(zf), B, Nc, 128,
+                                        det, 0, 0, _lib.stream()))
+        ref_zf, ref_inds = O.sample_pdf(g["bins_mid"], g["wb"], 128, deterministic=bool(det), u=g["u"], return_inds=True)
+        gold = g["out_mid_det128"] if det else g["out_mid_rand128"]
+        gi = g["inds_mid_det128"] if det else g["inds_mid_rand128"]
+        tol = pdf_tolerance(O.pdf_edges(g["bins_mid"], Nc - 1), g["cdf_mid"], gi)
+        ok = np.abs(N(zf) - gold) <= tol
+        assert ok.mean() > 0.995                                   # rest: index flips at CDF ties (see oracle test)
+        # the merge itself is exact: z_all == sort(cat(zc, the kernel's own zf))
+        assert np.array_equal(N(z_all), np.sort(np.concatenate([g["zc"], N(zf)], -1), -1))
+    gs = golden("sampler")
+    # pure merge check against the reference's sort(cat) output: feed zf through a flat pdf is not possible,
+    # so use the kernel's zf path above; here check the golden merge with torch-free numpy sort equality
+    assert np.array_equal(np.sort(np.concatenate([gs["merge_zc"], gs["merge_zf"]], -1), -1), gs["merge_out"])
+
+
+# ---------------------------------------------------------------------------------------------------- K3 compositor
+@pytest.mark.parametrize("tag,white,inf_last,use_rn", [("a", True, True, True), ("b", False, False, True), ("c", True, False, False)])
+def test_compositor_fwd_bwd(nsb, tag, white, inf_last, use_rn):
+    g = golden("compositor")
+    rgb, sig = T(g["rgb"]).requires_grad_(), T(g["sigma"]).requires_grad_()
+    rn = T(g["ray_norm"]) if use_rn else None
+    comp, w, acc, depth = nsb.volume_render_rays(rgb, sig, T(g["z"]), rn, white, 1e-10, inf_last)
+    close(N(comp), g[f"{tag}_comp"]); close(N(w), g[f"{tag}_w"], 1e-4, 1e-7); close(N(acc), g[f"{tag}_acc"])
+    close(N(depth), g[f"{tag}_depth"], 1e-4, 1e-5)
+    assert comp.shape == (96, 3) and w.shape == (96, 64) and acc.shape == (96, 1) and depth.shape == (96, 1)
+    # author's invariant (compare_nerf_repos.py:1199-1204): weights sum to acc
+    close(N(w).sum(-1), np.clip(N(acc)[:, 0], 0, 1), 1e-5, 1e-6)
+    gi = torch.autograd.grad((comp * T(g[f"{tag}_g_c"])).sum(), [rgb, sig], retain_graph=True)
+    close(N(gi[0]), g[f"{tag}_drgb_i"], 1e-4, 1e-6); close(N(gi[1]), g[f"{tag}_dsig_i"], 2e-4, 2e-5)
+    gii = torch.autograd.grad((comp * T(g[f"{tag}_g_c"])).sum() + (w * T(g[f"{tag}_g_w"])).sum()
+                              + (acc * T(g[f"{tag}_g_a"])).sum() + (depth * T(g[f"{tag}_g_d"])).sum(), [rgb, sig])
+    close(N(gii[0]), g[f"{tag}_drgb_ii"], 1e-4, 1e-6); close(N(gii[1]), g[f"{tag}_dsig_ii"], 2e-4, 5e-5)
+
+
+def test_compositor_ragged_and_long_rays(nsb):
+    rng = np.random.default_rng(3)
+    for B, Nn in [(1, 1), (3, 7), (5, 33), (2, 768), (1, 1500)]:
+        z = np.sort(rng.uniform(2, 6, (B, Nn)).astype(np.float32), -1)
+        rgb = rng.uniform(0, 1, (B, Nn, 3)).astype(np.float32); sig = rng.uniform(0, 3, (B, Nn)).astype(np.float32)
+        rn = rng.uniform(1, 1.1, (B, 1)).astype(np.float32)
+        comp, w, acc, depth, cache = O.volume_render_rays(rgb, sig, z, rn, True, 1e-10, True, keep=True)
+        tr, ts = T(rgb).requires_grad_(), T(sig).requires_grad_()
+        c2, w2, a2, d2 = nsb.volume_render_rays(tr, ts, T(z), T(rn), True, 1e-10, True)
+        close(N(c2), comp); close(N(w2), w, 1e-4, 1e-7); close(N(a2), acc); close(N(d2), depth, 1e-4, 1e-5)
+        gc = rng.standard_normal((B, 3)).astype(np.float32)
+        drgb, dsig = O.volume_render_backward(cache, gc)
+        gr = torch.autograd.grad((c2 * T(gc)).sum(), [tr, ts])
+        close(N(gr[0]), drgb, 1e-4, 1e-6); close(N(gr[1]), dsig, 5e-4, 2e-5)
+    assert nsb.volume_render_rays(torch.zeros((0, 4, 3), device=DEV), torch.zeros((0, 4), device=DEV),
+                                  torch.zeros((0, 4), device=DEV))[0].shape == (0, 3)
+
+
+# ---------------------------------------------------------------------------------------------------- K1 MLP (fp32 mode)
+def test_mlp_forward_backward_fp32(nsb):
+    g = golden("mlp")
+    net, p = load_nerf(g["seed"], g["sigma_bias"])
+    out = net(T(g["enc_pos"]), T(g["enc_dir"]))
+    close(N(out), g["out"], 1e-4, 2e-5)
+    out.backward(T(g["d_out"]))
+    flat = torch.cat([q.grad.reshape(-1) for q in net.parameters()])
+    ref = g["grad_samples"]
+    assert np.abs(N(flat)[g["grad_idx"]] - ref).max() <= 2e-4 * np.abs(ref).max()
+    norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+    close(norms, g["grad_norms"], 2e-4, 1e-6)
+    with torch.no_grad():                                              # eval path (no stash) gives the same numbers
+        close(N(net(T(g["enc_pos"]), T(g["enc_dir"]))), N(out), 0, 0)
+    with pytest.raises(RuntimeError):
+        net(T(g["enc_pos"])[:, :60], T(g["enc_dir"]))
+
+
+@pytest.mark.parametrize("tag", ["train", "eval", "bare"])
+def test_nerf_forward_pass_fp32(nsb, tag):
+    g = golden("forward_pass")
+    net, _ = load_nerf(g["seed"], g["sigma_bias"])
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    kw = dict(train=dict(ray_norms=T(g["rays_d_marching_norm"]), viewdirs_world_unit=T(g["viewdirs"]), raw_noise=T(g["noise"]),
+                         raw_noise_std=1.0, training=True, infinite_last_bin=True, white_bkgd=True),
+              eval=dict(ray_norms=T(g["rays_d_marching_norm"]), viewdirs_world_unit=T(g["viewdirs"]),
+                        infinite_last_bin=False, white_bkgd=False),
+              bare=dict(ray_norms=None, viewdirs_world_unit=None, infinite_last_bin=True, white_bkgd=True, mlp_chunk=100))[tag]
+    comp, w, acc, depth = nsb.nerf_forward_pass(T(g["rays_o_marching"]), T(g["rays_d_marching_unit"]), T(g["z"]),
+                                                pos_enc=pe.to(DEV), dir_enc=de.to(DEV), nerf=net, **kw)
+    close(N(comp), g[f"{tag}_comp"]); close(N(w), g[f"{tag}_w"], 1e-4, 1e-6)
+    close(N(acc), g[f"{tag}_acc"]); close(N(depth), g[f"{tag}_depth"], 1e-4, 1e-5)
+    assert w.shape == (24, 64) and acc.shape == (24, 1) and depth.shape == (24, 1)
+
+
+def _train_inputs(g):
+    batch = {k: T(g[k]) for k in ("rays_o_marching", "rays_d_marching_unit", "rays_d_marching_norm", "rays_d_world_unit", "rgb")}
+    draws = dict(U=T(g["U"]), u_fine=T(g["u_fine"]), noise_c=T(g["noise_c"]), noise_f=T(g["noise_f"]))
+    return batch, draws
+
+
+def _make_trainer(nsb, g, mode="fp32"):
+    tr = nsb.VanillaTrainer(DEV, nc=int(g["nc"]), nf=int(g["nf"]), near=2.0, far=6.0, mode=mode)
+    for net, seed in ((tr.nerf_c, g["seed_c"]), (tr.nerf_f, g["seed_f"])):
+        p = O.init_params(np.random.default_rng(int(seed)), sigma_bias=float(g["sigma_bias"]))
+        net.load_state_dict({k: T(v) for k, v in p.items()})
+    return tr
+
+
+def test_train_step_fp32_matches_reference(nsb):
+    g = golden("train_step")
+    tr = _make_trainer(nsb, g)
+    batch, draws = _train_inputs(g)
+    out = tr._train_step(batch, draws)                   # reference contract: autograd loss
+    assert abs(float(out["loss"]) - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    assert abs(float(out["psnr"]) - float(g["psnr"])) <= 1e-3
+    close(N(out["comp_c"]), g["comp_c"]); close(N(out["comp_f"]), g["comp_f"])
+    out["loss"].backward()
+    for tag, net in (("c", tr.nerf_c), ("f", tr.nerf_f)):
+        flat = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
+        ref = g[f"grad_samples_{tag}"]
+        assert np.abs(flat[g["grad_idx"]] - ref).max() <= 2e-3 * np.abs(ref).max()
+        norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+        close(norms, g[f"grad_norms_{tag}"], 5e-3 if tag == "f" else 1e-3, 1e-7)   # fp32 noise floor, see oracle test
+    # torch Adam over the module parameters works unchanged (trainer.py:383-386) and re-packs the weights
+    opt = torch.optim.Adam(tr.parameters(), lr=5e-4)
+    opt.step()
+    l2 = float(tr._train_step(batch, draws)["loss"])
+    assert l2 < float(out["loss"])
+
+
+def test_fused_step_and_adam_fp32(nsb):
+    g = golden("train_step")
+    tr = _make_trainer(nsb, g)
+    batch, draws = _train_inputs(g)
+    p0 = tr.nerf_c.flat_params().clone()
+    sc = tr.step(batch, draws)
+    assert abs(float(sc[0]) - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    # Adam step 1 fed with (almost) the reference's grads: compare where |g| is well above the eps knee
+    idx = g["grad_idx"]
+    ref_g = g["grad_samples_c"]
+    well = np.abs(ref_g) > 1e-6
+    p1 = N(tr.nerf_c.flat_params())[idx]
+    close(p1[well], g["adam_c"][well], 0, 2e-6)
+    assert np.abs(p1 - N(p0)[idx]).max() <= 5.01e-4
+    losses = [float(tr.step(batch, draws)[0]) for _ in range(5)]
+    assert losses[-1] < float(g["loss"])                   # it trains
+    sd = tr.state_dict()
+    assert tuple(sd["nerf_c"]["mlp.4.weight"].shape) == (256, 319) and sd["opt"]["t"] == 6
+
+
+@pytest.mark.parametrize("tag,ilb,nf", [("fine", False, 128), ("fine_inf", True, 128), ("coarse_only", False, 0)])
+def test_eval_tile_fp32(nsb, tag, ilb, nf):
+    g = golden("eval_tile")
+    nc_, _ = load_nerf(g["seed_c"], g["sigma_bias"]); nf_, _ = load_nerf(g["seed_f"], g["sigma_bias"])
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    H, W = int(g["H"]), int(g["W"])
+    r = nsb.render_image_chunked(T(g["rays_o_marching"]), T(g["rays_d_marching_unit"]), T(g["rays_d_marching_norm"]), H, W,
+                                 2.0, 6.0, pe.to(DEV), de.to(DEV), nc_, nf_, 64, nf, True, torch.device(DEV), eval_chunk=20,
+                                 viewdirs_world_unit=T(g["rays_d_world_unit"]), infinite_last_bin=ilb)
+    assert r["rgb"].shape == (H, W, 3) and r["acc"].shape == (H, W, 1) and r["depth"].shape == (H, W, 1)
+    close(N(r["rgb"]), g[f"{tag}_rgb"]); close(N(r["acc"]), g[f"{tag}_acc"]); close(N(r["depth"]), g[f"{tag}_depth"], 1e-4, 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_fp32(nsb):
+    """BASELINE cfg2 shape (1024 rays, 64+128) with in-kernel Philox: size-independent invariants."""
+    from nerf_sandbox_b200 import _lib
+    tr = nsb.VanillaTrainer(DEV, sigma_bias=0.3, seed=1)
+    rays = O.synthetic_rays(np.random.default_rng(2), 1024)
+    batch = {k: T(v) for k, v in rays.items()}
+    s1 = N(tr._fwd_bwd(batch)[0]).copy(); g1 = tr.grads_f.clone()
+    s2 = N(tr._fwd_bwd(batch)[0]).copy()
+    assert s1[0] == pytest.approx(s2[0], rel=1e-5)                       # same (seed, step) -> same Philox draws
+    assert np.isfinite(s1).all() and abs(s1[0] - (s1[2] + s1[3])) < 1e-6
+    assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
+    # linearity of the backward in grad_scale
+    tr._fwd_bwd(batch, grad_scale=0.5)
+    close(N(tr.grads_f), 0.5 * N(g1), 2e-3, 1e-9)
+    # eval: 4096 rays, fine z sorted, acc in [0,1], rgb in [0,1]; coarse-only equals a 1-pass render
+    o, d, rn = batch["rays_o_marching"].repeat(4, 1), batch["rays_d_marching_unit"].repeat(4, 1), batch["rays_d_marching_norm"].repeat(4, 1).reshape(-1)
+    rgb, acc, depth = nsb.render_rays(o, d, rn, d, tr.nerf_c, tr.nerf_f, near=2.0, far=6.0, nc=64, nf=128, white_bkgd=True)
+    assert float(rgb.min()) >= 0 and float(rgb.max()) <= 1 and float(acc.min()) >= 0 and float(acc.max()) <= 1
+    assert torch.equal(rgb[:1024], rgb[1024:2048])                        # deterministic and tile-independent
+    assert float(depth.min()) >= 0 and float(depth.max()) <= 6.0 + 1e-3
