@@ -292,8 +292,8 @@ using namespace nsb;
 extern "C" int nsb_composite_fwd(const float* rgb, const float* sigma, const float* z, const float* ray_norm,
                                  float* comp, float* weights, float* acc, float* depth, int64_t B, int N,
                                  uint32_t flags, float eps, void* stream) {
-    if (!rgb || !sigma || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!rgb || !sigma || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     composite_fwd_kernel<false><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
         rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0);
     NSB_LAUNCH_CHECK("composite_fwd_kernel");
@@ -304,8 +304,8 @@ extern "C" int nsb_composite_bwd(const float* rgb, const float* sigma, const flo
                                  const float* g_comp, const float* g_weights, const float* g_acc, const float* g_depth,
                                  float* d_rgb, float* d_sigma, int64_t B, int N, uint32_t flags, float eps,
                                  void* stream) {
-    if (!rgb || !sigma || !z || !g_comp || !d_rgb || !d_sigma || N < 1 || B < 0) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!rgb || !sigma || !z || !g_comp || !d_rgb || !d_sigma || N < 1 || B < 0) return NSB_E_BADARG;
     return launch_bwd<false>(rgb, sigma, nullptr, 0.f, z, ray_norm, g_comp, g_weights, g_acc, g_depth, d_rgb, d_sigma,
                              B, N, flags, eps, 0, 0, stream);
 }
@@ -313,8 +313,8 @@ extern "C" int nsb_composite_bwd(const float* rgb, const float* sigma, const flo
 extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float noise_std, const float* z,
                                      const float* ray_norm, float* comp, float* weights, float* acc, float* depth,
                                      int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
-    if (!raw || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!raw || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     composite_fwd_kernel<true><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
         raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset);
     NSB_LAUNCH_CHECK("composite_raw_fwd_kernel");
@@ -324,8 +324,8 @@ extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float
 extern "C" int nsb_composite_raw_bwd(const float* raw, const float* noise, float noise_std, const float* z,
                                      const float* ray_norm, const float* g_comp, float* d_raw, int64_t B, int N,
                                      uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
-    if (!raw || !z || !g_comp || !d_raw || N < 1 || B < 0) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!raw || !z || !g_comp || !d_raw || N < 1 || B < 0) return NSB_E_BADARG;
     return launch_bwd<true>(raw, nullptr, noise, noise_std, z, ray_norm, g_comp, nullptr, nullptr, nullptr, d_raw,
                             nullptr, B, N, flags, 1e-10f, seed, offset, stream);
 }

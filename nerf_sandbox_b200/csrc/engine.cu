@@ -79,8 +79,8 @@ extern "C" size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash) { re
 
 extern "C" int nsb_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, void* ws,
                                  size_t ws_bytes, int64_t Q, int mode, int stash, void* stream) {
-    if (!enc_pos || !enc_dir || !packed || !raw || !ws || Q < 0) return NSB_E_BADARG;
     if (Q == 0) return NSB_OK;
+    if (!enc_pos || !enc_dir || !packed || !raw || !ws || Q < 0) return NSB_E_BADARG;
     if (ws_bytes < field_ws(Q, mode, stash)) return NSB_E_WORKSPACE;
     if (mode == NSB_MODE_BF16)
         return tc_field_fwd_enc(enc_pos, enc_dir, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw,
@@ -92,8 +92,8 @@ extern "C" int nsb_field_fwd_enc(const float* enc_pos, const float* enc_dir, con
 extern "C" int nsb_field_fwd_rays(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm,
                                   const float* viewdirs, const void* packed, float* raw, void* ws, size_t ws_bytes,
                                   int64_t B, int N, int mode, int stash, void* stream) {
-    if (!rays_o || !rays_d || !z || !packed || !raw || !ws || B < 0 || N < 1) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!rays_o || !rays_d || !z || !packed || !raw || !ws || B < 0 || N < 1) return NSB_E_BADARG;
     const int64_t Q = B * (int64_t)N;
     if (ws_bytes < field_ws(Q, mode, stash)) return NSB_E_WORKSPACE;
     if (mode == NSB_MODE_BF16)
@@ -106,8 +106,8 @@ extern "C" int nsb_field_fwd_rays(const float* rays_o, const float* rays_d, cons
 
 extern "C" int nsb_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, size_t ws_bytes, int64_t Q,
                              int mode, void* stream) {
-    if (!d_raw || !packed || !grads || !ws || Q < 0) return NSB_E_BADARG;
     if (Q == 0) return NSB_OK;
+    if (!d_raw || !packed || !grads || !ws || Q < 0) return NSB_E_BADARG;
     if (ws_bytes < field_ws(Q, mode, 1)) return NSB_E_WORKSPACE;
     if (mode == NSB_MODE_BF16)
         return tc_field_bwd(d_raw, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, grads, ws, Q,
@@ -213,8 +213,8 @@ extern "C" int nsb_render_rays(const float* rays_o, const float* rays_d, const f
                                const void* packed_c, const void* packed_f, float* rgb, float* acc, float* depth, void* ws,
                                size_t ws_bytes, int64_t B, int Nc, int Nf, float near_, float far_, uint32_t flags,
                                int mode, void* stream) {
-    if (!rays_o || !rays_d || !packed_c || !rgb || !ws || B < 0 || Nc < 1) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!rays_o || !rays_d || !packed_c || !rgb || !ws || B < 0 || Nc < 1) return NSB_E_BADARG;
     const bool fine = Nf > 0 && packed_f != nullptr;                                                                   // render_utils.py:381
     if (fine && Nc < 2) return NSB_E_BADARG;
     RenderWs t = carve_render(ws, B, Nc, fine ? Nf : 0, mode);

@@ -567,8 +567,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 using namespace nsb;
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
-    if (!x || !out || Q < 0 || D < 1 || L < 0) return NSB_E_BADARG;
     if (Q == 0) return NSB_OK;
+    if (!x || !out || Q < 0 || D < 1 || L < 0) return NSB_E_BADARG;
     const int od = D * (include_input ? 1 : 0) + 2 * L * D;
     encode_kernel<<<elem_grid(Q * od), 256, 0, as_stream(stream)>>>(x, out, Q, D, L, include_input);
     NSB_LAUNCH_CHECK("encode_kernel");

@@ -196,8 +196,8 @@ using namespace nsb;
 
 extern "C" int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, float near_, float far_, int jitter,
                                 uint64_t seed, uint64_t offset, void* stream) {
-    if (!z || B < 0 || Nc < 1) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!z || B < 0 || Nc < 1) return NSB_E_BADARG;
     const int64_t total = B * Nc;
     const int grid = (int)(cdiv(total, 256) < (int64_t)num_sms() * 8 ? cdiv(total, 256) : (int64_t)num_sms() * 8);
     stratified_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset);
@@ -208,9 +208,9 @@ extern "C" int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, flo
 extern "C" int nsb_sample_pdf(const float* bins, int bins_cols, const float* weights, int M, const float* u,
                               const float* cdf_in, float* out, int64_t* inds_out, int64_t B, int n, int deterministic,
                               uint64_t seed, uint64_t offset, void* stream) {
+    if (B == 0) return NSB_OK;
     if (!bins || !weights || !out || M < 1 || n < 1 || B < 0) return NSB_E_BADARG;
     if (bins_cols != M && bins_cols != M + 1) return NSB_E_BADARG;          // sampling_utils.py:34-35
-    if (B == 0) return NSB_OK;
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (M + 1) * sizeof(float);
     if (smem > 200 * 1024) return NSB_E_BADARG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -223,8 +223,8 @@ extern "C" int nsb_sample_pdf(const float* bins, int bins_cols, const float* wei
 extern "C" int nsb_resample_merge(const float* zc, const float* w_c, const float* u, float* z_all, float* z_fine,
                                   int64_t B, int Nc, int Nf, int deterministic, uint64_t seed, uint64_t offset,
                                   void* stream) {
-    if (!zc || !w_c || !z_all || Nc < 2 || Nf < 1 || B < 0) return NSB_E_BADARG;
     if (B == 0) return NSB_OK;
+    if (!zc || !w_c || !z_all || Nc < 2 || Nf < 1 || B < 0) return NSB_E_BADARG;
     int sort_len = 32;
     while (sort_len < Nc + Nf) sort_len <<= 1;
     const size_t smem = (size_t)kWarpsPerBlock * (3 * Nc + sort_len) * sizeof(float);
