@@ -45,11 +45,11 @@ class _FieldEncFn(torch.autograd.Function):
     """NeRF.forward on materialised encodings; grads w.r.t. the parameters only."""
 
     @staticmethod
-    def forward(ctx, nerf, enc_pos, enc_dir, *params):
+    def forward(ctx, nerf, grad_mode, enc_pos, enc_dir, *params):
         L = _lib.lib()
         ep, ed = _lib.f32c(enc_pos), _lib.f32c(enc_dir)
         Q = ep.shape[0]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = grad_mode and any(p.requires_grad for p in params)     # (grad mode is off inside forward)
         packed = nerf.packed()
         wsb = L.nsb_field_workspace_bytes(Q, nerf.mode, int(need_grad))
         ws = (torch.empty(wsb, dtype=torch.uint8, device=ep.device) if need_grad else nerf._ws.get(wsb, ep.device))
@@ -65,7 +65,7 @@ class _FieldEncFn(torch.autograd.Function):
         g = torch.zeros(_lib.N_PARAMS, device=d_raw.device, dtype=torch.float32)
         _lib.check(_lib.lib().nsb_field_bwd(_lib.ptr(_lib.f32c(d_raw)), _lib.ptr(ctx.packed), _lib.ptr(g), _lib.ptr(ctx.ws),
                                             ctx.wsb, ctx.Q, nerf.mode, _lib.stream()), "nsb_field_bwd")
-        return (None, None, None) + tuple(nerf.unflatten(g))
+        return (None, None, None, None) + tuple(nerf.unflatten(g))
 
 
 class NeRF(nn.Module):
@@ -162,7 +162,8 @@ class NeRF(nn.Module):
             raise RuntimeError(f"feature dims ({enc_pos.shape[-1]}, {enc_dir.shape[-1]}) do not match "
                                f"({self.enc_pos_dim}, {self.enc_dir_dim})")              # nn.Linear would raise the same
         lead = enc_pos.shape[:-1]
-        raw = _FieldEncFn.apply(self, enc_pos.reshape(-1, self.enc_pos_dim), enc_dir.reshape(-1, self.enc_dir_dim),
+        raw = _FieldEncFn.apply(self, torch.is_grad_enabled(), enc_pos.reshape(-1, self.enc_pos_dim),
+                                enc_dir.reshape(-1, self.enc_dir_dim),
                                 *self.ordered_params())
         return raw.reshape(*lead, 4).to(enc_pos.dtype)
 

@@ -75,11 +75,11 @@ class _FusedPassFn(torch.autograd.Function):
     """rays + z -> (comp, weights, acc, depth); differentiable w.r.t. the NeRF parameters through comp."""
 
     @staticmethod
-    def forward(ctx, nerf, o, d, z, rn, vd, flags, noise_std, noise, seed, *params):
+    def forward(ctx, nerf, grad_mode, o, d, z, rn, vd, flags, noise_std, noise, seed, *params):
         L = _lib.lib()
         B, N = z.shape
         dev = z.device
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = grad_mode and any(p.requires_grad for p in params)     # (grad mode is off inside forward)
         packed = nerf.packed()
         wsb = L.nsb_field_workspace_bytes(B * N, nerf.mode, int(need_grad))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if need_grad else nerf._ws.get(wsb, dev)
@@ -114,7 +114,7 @@ class _FusedPassFn(torch.autograd.Function):
         g = torch.zeros(_lib.N_PARAMS, device=raw.device, dtype=torch.float32)
         _lib.check(L.nsb_field_bwd(_lib.ptr(d_raw), _lib.ptr(ctx.packed), _lib.ptr(g), _lib.ptr(ctx.ws), ctx.wsb, B * N,
                                    nerf.mode, _lib.stream()), "nsb_field_bwd")
-        return (None,) * 10 + tuple(nerf.unflatten(g))
+        return (None,) * 11 + tuple(nerf.unflatten(g))
 
 
 def nerf_forward_pass(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, z_vals: torch.Tensor, *, pos_enc, dir_enc, nerf,
@@ -142,7 +142,7 @@ def nerf_forward_pass(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, z_vals: t
         noise = _lib.f32c(raw_noise).reshape(-1) if (use_noise and raw_noise is not None) else None
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (use_noise and noise is None) else 0
-        comp, w, acc, depth = _FusedPassFn.apply(nerf, o, d, z, rn, vd, flags, float(raw_noise_std) if use_noise else 0.0,
+        comp, w, acc, depth = _FusedPassFn.apply(nerf, torch.is_grad_enabled(), o, d, z, rn, vd, flags, float(raw_noise_std) if use_noise else 0.0,
                                                  noise, seed, *nerf.ordered_params())
         return comp, w, acc, depth
 

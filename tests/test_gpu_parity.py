@@ -289,3 +289,35 @@ def test_full_size_properties_fp32(nsb):
     assert float(rgb.min()) >= 0 and float(rgb.max()) <= 1 and float(acc.min()) >= 0 and float(acc.max()) <= 1
     assert torch.equal(rgb[:1024], rgb[1024:2048])                        # deterministic and tile-independent
     assert float(depth.min()) >= 0 and float(depth.max()) <= 6.0 + 1e-3
+
+
+def test_reference_style_step_through_module_boundary_fp32(nsb):
+    """Trainer._train_step written exactly like the reference (trainer.py:899-1006) but against this package's
+    by-name callables -- the drop-in seam -- with autograd flowing through nerf_forward_pass."""
+    import torch.nn.functional as F
+    g = golden("train_step")
+    tr = _make_trainer(nsb, g)
+    batch, draws = _train_inputs(g)
+    pe, de = tr.pos_enc, tr.dir_enc
+    B, nc, nf = int(g["B"]), int(g["nc"]), int(g["nf"])
+    t = torch.linspace(0.0, 1.0, steps=nc, device=DEV)
+    zc = (2.0 * (1.0 - t) + 6.0 * t).expand(B, nc).contiguous()
+    mids = 0.5 * (zc[:, 1:] + zc[:, :-1])
+    lower = torch.cat([zc[:, :1], mids], -1); upper = torch.cat([mids, zc[:, -1:]], -1)
+    zc = torch.sort(lower + (upper - lower) * draws["U"], -1).values
+    kw = dict(pos_enc=pe, dir_enc=de, white_bkgd=True, ray_norms=batch["rays_d_marching_norm"],
+              viewdirs_world_unit=batch["rays_d_world_unit"], sigma_activation="relu", raw_noise_std=1.0, training=True,
+              infinite_last_bin=True)
+    comp_c, w_c, _, _ = nsb.nerf_forward_pass(batch["rays_o_marching"], batch["rays_d_marching_unit"], zc, nerf=tr.nerf_c,
+                                              raw_noise=draws["noise_c"], **kw)
+    bins_mid = 0.5 * (zc[:, 1:] + zc[:, :-1]); wb = 0.5 * (w_c[:, 1:] + w_c[:, :-1]).detach() + 1e-5
+    zf = nsb.sample_pdf(bins_mid, wb, nf, deterministic=False, u=draws["u_fine"])
+    z_all = torch.sort(torch.cat([zc, zf], -1), -1).values
+    comp_f, _, _, _ = nsb.nerf_forward_pass(batch["rays_o_marching"], batch["rays_d_marching_unit"], z_all, nerf=tr.nerf_f,
+                                            raw_noise=draws["noise_f"], **kw)
+    loss = F.mse_loss(comp_c.clamp(0, 1), batch["rgb"]) + F.mse_loss(comp_f.clamp(0, 1), batch["rgb"])
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    loss.backward()
+    for tag, net in (("c", tr.nerf_c), ("f", tr.nerf_f)):
+        norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+        close(norms, g[f"grad_norms_{tag}"], 5e-3 if tag == "f" else 1e-3, 1e-7)
