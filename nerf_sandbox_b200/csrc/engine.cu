@@ -46,6 +46,9 @@ int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* pac
                      int stash, cudaStream_t st);
 int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
 
+int tc_debug_layer(const float*, const float*, const float*, const float*, const float*, const void*, float*, float*, int,
+                   int64_t, int, cudaStream_t);
+
 static size_t field_ws(int64_t Q, int mode, int stash) {
     return mode == NSB_MODE_BF16 ? tc_workspace_bytes(Q, stash) : fp32_workspace_bytes(Q, stash);
 }
@@ -113,6 +116,14 @@ extern "C" int nsb_field_bwd(const float* d_raw, const void* packed, float* grad
         return tc_field_bwd(d_raw, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, grads, ws, Q,
                             as_stream(stream));
     return fp32_mlp_bwd(d_raw, packed, grads, ws, Q, as_stream(stream));
+}
+
+// test hook (not part of include/nsb.h): tensor-core forward + fp32 dump of one layer's activations [Q,256]
+extern "C" int nsb_debug_tc_layer(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm,
+                                  const float* viewdirs, const void* packed, float* raw, float* dbg, int layer, int64_t B,
+                                  int N, void* stream) {
+    return tc_debug_layer(rays_o, rays_d, z, ray_norm, viewdirs, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off,
+                          raw, dbg, layer, B, N, as_stream(stream));
 }
 
 // ---------------------------------------------------------------------------------------------------

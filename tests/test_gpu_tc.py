@@ -1,0 +1,128 @@
+"""bf16 tensor-core mode (tcgen05 fused field kernel) against the oracle and the fp32 mode.
+Tolerance: north star asks PSNR delta <= 0.05 dB for the bf16 mode on rendered output; per-layer checks
+use a relative L2 bound of 2e-2 (bf16 operands, fp32 accumulate, 9 chained layers)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, torch.float32)
+
+
+def N(t):
+    return t.detach().float().cpu().numpy()
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import nerf_sandbox_b200 as nsb
+    from nerf_sandbox_b200 import _lib
+    p = O.init_params(np.random.default_rng(3), sigma_bias=0.3)
+    net = nsb.NeRF(63, 27, mode="bf16").to(DEV)
+    net.load_state_dict({k: T(v) for k, v in p.items()})
+    rays = O.synthetic_rays(np.random.default_rng(4), 200)          # 200*64 = 12800 points = 100 tiles
+    z = O.stratified_z(2.0, 6.0, 64, np.random.default_rng(5).uniform(0, 1, (200, 64)).astype(np.float32))
+    return nsb, _lib, net, p, rays, z
+
+
+def _oracle_acts(p, rays, z):
+    pts = O.ray_points(rays["rays_o_marching"], rays["rays_d_marching_unit"], z, rays["rays_d_marching_norm"])
+    vd = O._normalize(rays["rays_d_world_unit"])
+    epos = O.positional_encode(pts.reshape(-1, 3), 10)
+    edir = O.positional_encode(np.broadcast_to(vd[:, None, :], pts.shape).reshape(-1, 3), 4)
+    old = O._CHUNK
+    O._CHUNK = 1 << 30
+    raw, caches = O.mlp_forward(p, epos, edir, keep=True)
+    O._CHUNK = old
+    return raw, caches[0]
+
+
+@pytest.mark.parametrize("layer", [0, 1, 3, 4, 7, 8, 9])
+def test_tc_layer_activations(setup, layer):
+    nsb, _lib, net, p, rays, z = setup
+    L = _lib.lib()
+    fn = L.nsb_debug_tc_layer
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    B, Nn = z.shape
+    raw = torch.zeros((B * Nn, 4), device=DEV); dbg = torch.zeros((B * Nn, 256), device=DEV)
+    o, d, zz = T(rays["rays_o_marching"]), T(rays["rays_d_marching_unit"]), T(z)
+    rn, vd = T(rays["rays_d_marching_norm"]).reshape(-1), T(rays["rays_d_world_unit"])
+    _lib.check(fn(_lib.ptr(o), _lib.ptr(d), _lib.ptr(zz), _lib.ptr(rn), _lib.ptr(vd), _lib.ptr(net.packed()), _lib.ptr(raw),
+                  _lib.ptr(dbg), layer, B, Nn, _lib.stream()), "nsb_debug_tc_layer")
+    torch.cuda.synchronize()
+    ref_raw, c = _oracle_acts(p, rays, z)
+    if layer < 8:
+        ref = c["hs"][layer]
+    elif layer == 8:
+        ref = c["cin"][:, :256]
+    else:
+        ref = np.concatenate([c["c"], np.zeros_like(c["c"])], -1)
+    got = N(dbg)
+    if layer == 9:
+        got[:, 128:] = 0
+    err = rel_l2(got, ref)
+    assert err < 2e-2, f"layer {layer}: rel L2 {err}"
+    assert rel_l2(N(raw), ref_raw) < 3e-2
+
+
+def test_tc_forward_matches_fp32_mode(setup):
+    nsb, _lib, net, p, rays, z = setup
+    net32 = nsb.NeRF(63, 27, mode="fp32").to(DEV)
+    net32.load_state_dict(net.state_dict())
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    kw = dict(pos_enc=pe.to(DEV), dir_enc=de.to(DEV), white_bkgd=True, ray_norms=T(rays["rays_d_marching_norm"]),
+              viewdirs_world_unit=T(rays["rays_d_world_unit"]), infinite_last_bin=True)
+    with torch.no_grad():
+        a = nsb.nerf_forward_pass(T(rays["rays_o_marching"]), T(rays["rays_d_marching_unit"]), T(z), nerf=net, **kw)
+        b = nsb.nerf_forward_pass(T(rays["rays_o_marching"]), T(rays["rays_d_marching_unit"]), T(z), nerf=net32, **kw)
+    mse = float(((a[0] - b[0]) ** 2).mean())
+    assert mse < 1e-5, mse                                   # rendered colours agree to ~50 dB
+    assert float((a[2] - b[2]).abs().max()) < 2e-2
+    # module boundary with materialised encodings (NeRF.forward), ragged Q (not a multiple of 128)
+    ep = pe(T(np.random.default_rng(1).uniform(-4, 4, (333, 3)).astype(np.float32)))
+    ed = de(T(rays["rays_d_world_unit"][:1].repeat(333, 0)))
+    with torch.no_grad():
+        assert rel_l2(N(net(ep, ed)), N(net32(ep, ed))) < 3e-2
+
+
+def test_tc_eval_psnr_delta(setup):
+    """800x800-shaped eval tile through nsb_render_rays in both modes: PSNR of bf16 vs fp32 render."""
+    nsb, _lib, net, p, rays, z = setup
+    g = golden("eval_tile")
+    nets = {}
+    for mode in ("fp32", "bf16"):
+        pair = []
+        for seed in (int(g["seed_c"]), int(g["seed_f"])):
+            q = O.init_params(np.random.default_rng(seed), sigma_bias=float(g["sigma_bias"]))
+            m = nsb.NeRF(63, 27, mode=mode).to(DEV); m.load_state_dict({k: T(v) for k, v in q.items()}); pair.append(m)
+        nets[mode] = pair
+    big = O.synthetic_rays(np.random.default_rng(8), 4096)
+    args = (T(big["rays_o_marching"]), T(big["rays_d_marching_unit"]), T(big["rays_d_marching_norm"]).reshape(-1), T(big["rays_d_world_unit"]))
+    out = {m: nsb.render_rays(*args, nets[m][0], nets[m][1], near=2.0, far=6.0, nc=64, nf=128, white_bkgd=True) for m in nets}
+    torch.cuda.synchronize()
+    mse = float(((out["bf16"][0] - out["fp32"][0]) ** 2).mean())
+    psnr = -10 * np.log10(max(mse, 1e-12))
+    assert psnr > 45.0, psnr                                 # bf16 render vs fp32 render
+    # against a pseudo ground truth: PSNR(bf16, gt) within 0.05 dB of PSNR(fp32, gt)
+    gt = T(np.random.default_rng(9).uniform(0, 1, (4096, 3)).astype(np.float32))
+    ps = {m: -10 * np.log10(float(((out[m][0] - gt) ** 2).mean())) for m in out}
+    assert abs(ps["bf16"] - ps["fp32"]) <= 0.05, ps
+    # golden eval tile (reference output) at bf16 tolerance
+    H, W = int(g["H"]), int(g["W"])
+    r = nsb.render_rays(T(g["rays_o_marching"]), T(g["rays_d_marching_unit"]), T(g["rays_d_marching_norm"]).reshape(-1),
+                        T(g["rays_d_world_unit"]), nets["bf16"][0], nets["bf16"][1], near=2.0, far=6.0, nc=64, nf=128, white_bkgd=True)
+    assert float(np.abs(N(r[0]).reshape(H, W, 3) - g["fine_rgb"]).max()) < 3e-2
