@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("NSB_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("NSB_BENCH_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph (N=1)")

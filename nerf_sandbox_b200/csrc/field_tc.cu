@@ -49,6 +49,12 @@ constexpr int kBsigOfs = kWsigOfs + 256;
 constexpr int kWoOfs = kBsigOfs + 4;                              // keep 16B alignment
 constexpr int kBoOfs = kWoOfs + 384;
 constexpr int kTailFloats = kBoOfs + 4;
+// transposed images for the dgrad chain (contraction over OUT features, first 256 IN features as N):
+//   m=0 color_fc^T (K=128) | m=1 feature^T | m=2..8 mlp.7^T .. mlp.1^T (K=256 each); element (j, n) at [n/8][j][8]
+constexpr uint32_t kTImgOfs = ((kBiasOfs + kTailFloats * 4 + 255) / 256) * 256;
+constexpr int kNumDgradLayers = 9;
+__host__ __device__ inline uint32_t dgrad_layer_ofs(int m) { return kTImgOfs + (m == 0 ? 0u : 65536u + (uint32_t)(m - 1) * 131072u); }
+constexpr uint32_t kPackedTcBytes = kTImgOfs + 65536 + 8 * 131072;
 
 __host__ __device__ inline int layer_nslabs(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 9 ? 9 : 8)); }
 __host__ __device__ inline int layer_N(int l) { return l == 9 ? 128 : 256; }
@@ -162,6 +168,14 @@ struct FwdParams {
 //   gd (K=32) 8192 | c (color_fc output, K=128) 32768
 constexpr size_t kStashGx = 0, kStashH = 16384, kStashFeat = kStashH + 8 * 65536, kStashGd = kStashFeat + 65536,
                  kStashC = kStashGd + 8192, kStashTile = kStashC + 32768;   // 647,168 B / tile = 5056 B / point
+// Gradient stash of one tile, written by the dgrad chain and read by wgrad (same image layout):
+//   dY_9 (d pre-activation of color_fc, K=128) 32768 | dY_8 (d feature out) | dY_7 .. dY_0 (d pre-act of mlp.7..0), 65536 each
+constexpr size_t kDstashTile = 32768 + 9 * 65536;                           // 622,592 B / tile = 4864 B / point
+__host__ __device__ inline size_t dstash_ofs(int k) { return k == 9 ? 0 : 32768 + (size_t)(8 - k) * 65536; }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // write 8 consecutive K elements (one 16-byte core-matrix row) of row r at K-chunk `k8`
 __device__ __forceinline__ void st_chunk(uint32_t base, int k8, int r, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -321,6 +335,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             const int64_t q = tile * TILE_M + r;
             const bool valid = tile < p.num_tiles && q < p.Q;
             const int64_t qc = valid ? q : 0;
+            // training stash: bulk-store shared-memory images of the layer inputs (TMA engine, one elected thread)
+            const bool do_stash = p.stash != nullptr;
+            uint8_t* stash_tile = do_stash && tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
+            auto stash_guard = [&]() {       // earlier bulk stores must have finished READING smem before we overwrite it
+                if (do_stash) { if (r == 0) bulk_wait_read0(); named_bar_sync(1 + t, 128); }
+            };
+            auto stash_store = [&](size_t ofs, uint32_t src, uint32_t bytes) {
+                if (do_stash) {
+                    fence_async_smem();
+                    named_bar_sync(1 + t, 128);
+                    if (r == 0 && stash_tile) { bulk_s2g(stash_tile + ofs, src, bytes); bulk_commit(); }
+                }
+            };
+            stash_guard();
             // ---- layer-0 input: gamma(x) ----
             float vdir[3] = {0.f, 0.f, 1.f};
             if (FROM_ENC) {
@@ -339,11 +367,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 vdir[0] = vx * inv; vdir[1] = vy * inv; vdir[2] = vz * inv;
             }
             fence_async_smem();
+            stash_store(kStashGx, gx, kGxBytes);
             mbar_arrive(bar_in + 8 * t);
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
             for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
+                stash_guard();
                 const int N = layer_N(l);
                 const float* bias = tail + layer_bias_ofs(l);
                 const bool relu = l != 8;
@@ -387,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) p.dbg[q * 256 + c0 + j] = f[j];
                     }
-                    if (l != 9) {          // next layer's A operand, in place
+                    if (l != 9 || do_stash) {   // next layer's A operand, in place (l == 9: c, only for the stash)
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8)
                             st_chunk(act, (c0 >> 3) + j8, r, pack_bf16(f[8 * j8], f[8 * j8 + 1]), pack_bf16(f[8 * j8 + 2], f[8 * j8 + 3]),
@@ -398,6 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4);
                     else encode_dir(gx, r, vdir[0], vdir[1], vdir[2]);
                 }
+                if (l <= 7) stash_store(kStashH + (size_t)l * 65536, act, kActBytes);
+                else if (l == 8) { stash_store(kStashFeat, act, kActBytes); stash_store(kStashGd, gx, 8192); }
+                else stash_store(kStashC, act, 32768);
                 if (l != 9) {
                     tc_fence_before();
                     fence_async_smem();
@@ -410,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             }
             tc_fence_before();   // the next pair's first MMA overwrites this accumulator: order our tcgen05.ld before it
         }
+        if (p.stash && r == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -448,18 +482,477 @@ __global__ void pack_tc_kernel(const float* __restrict__ params, uint8_t* __rest
     }
 }
 
+// =======================================================================================================
+// Backward, part 1: the dgrad chain (same machinery as the forward: weights^T streamed by TMA, two tiles per
+// CTA, accumulators in TMEM).  d_raw -> dY_9 (color_fc pre-activation grad) -> dY_8 (d feature) -> dY_7 .. dY_0;
+// every dY tile is bulk-stored to the gradient stash for the wgrad kernel.  ReLU masks come from the forward
+// stash (coalesced 16-byte loads of the bf16 images straight from global memory).
+// =======================================================================================================
+struct DgradParams {
+    const float* d_raw;           // [Q,4]
+    const uint8_t* packed;        // transposed images at kTImgOfs; fp32 tail (w_sigma, Wo)
+    const uint8_t* stash;         // forward stash
+    uint8_t* dstash;              // gradient stash (output)
+    int64_t Q; int64_t num_tiles;
+};
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages, bar_in = bar_empty + 8 * kStages,
+                   bar_acc = bar_in + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 4));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t num_pairs = (p.num_tiles + 1) / 2;
+    const float* tail = reinterpret_cast<const float*>(p.packed + kBiasOfs);
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // TMA producer: K=32 x N=256 slabs of W^T
+            uint32_t stage = 0, round = 0;
+            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+                for (int m = 0; m < kNumDgradLayers; ++m) {
+                    const uint8_t* src = p.packed + dgrad_layer_ofs(m);
+                    const int ns = m == 0 ? 4 : 8;
+                    for (int s = 0; s < ns; ++s) {
+                        mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                        bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
+                        if (++stage == kStages) { stage = 0; ++round; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // MMA issuer
+            uint32_t stage = 0, round = 0, use = 0;
+            const uint32_t idesc = make_idesc(256);
+            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+                for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
+                    const int ns = m == 0 ? 4 : 8;
+                    for (int s = 0; s < ns; ++s) {
+                        const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            if (s == 0) { mbar_wait(bar_in + 8 * t, use & 1); }
+                            if (t == 0) { mbar_wait(bar_full + 8 * stage, round & 1); }
+                            tc_fence_after();
+                            const uint32_t a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 4u * 2048u;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks)
+                                tc_mma(d_tmem, make_desc(a_addr + ks * 2 * 2048, 2048, 128), make_desc(b_addr + ks * 2 * 4096, 4096, 128),
+                                       idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                            if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                        }
+                        tc_commit(bar_empty + 8 * stage);
+                        if (++stage == kStages) { stage = 0; ++round; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int t = (warp - 4) >> 2;
+        const int r = (int)threadIdx.x - 128 - t * 128;
+        const uint32_t act = sbase + kSmemAct + t * kActBytes;
+        const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t use = 0;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + t;
+            const int64_t q = tile * TILE_M + r;
+            const bool tile_ok = tile < p.num_tiles;
+            const bool valid = tile_ok && q < p.Q;
+            const uint8_t* st_tile = p.stash + (size_t)(tile_ok ? tile : 0) * kStashTile;
+            uint8_t* ds_tile = tile_ok ? p.dstash + (size_t)tile * kDstashTile : nullptr;
+            auto guard = [&]() { if (r == 0) bulk_wait_read0(); named_bar_sync(1 + t, 128); };
+            auto store = [&](size_t ofs, uint32_t bytes) {
+                fence_async_smem();
+                named_bar_sync(1 + t, 128);
+                if (r == 0 && ds_tile) { bulk_s2g(ds_tile + ofs, act, bytes); bulk_commit(); }
+            };
+            guard();
+            // ---- prologue: d_raw -> dY_9 = (d_rgb . Wo) * (c > 0)   (color_out dgrad + color_fc ReLU mask) ----
+            float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int c8 = 0; c8 < 16; ++c8) {
+                const uint4 cm = ldg16(st_tile + kStashC + (size_t)c8 * 2048 + (size_t)r * 16);
+                const uint32_t cw[4] = {cm.x, cm.y, cm.z, cm.w};
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c8 * 8 + j;
+                    const float g = d.x * __ldg(tail + kWoOfs + col) + d.y * __ldg(tail + kWoOfs + 128 + col) + d.z * __ldg(tail + kWoOfs + 256 + col);
+                    const float cv = (j & 1) ? bf16hi(cw[j >> 1]) : bf16lo(cw[j >> 1]);
+                    o[j] = cv > 0.f ? g : 0.f;
+                }
+                st_chunk(act, c8, r, pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+            store(dstash_ofs(9), 32768);
+            mbar_arrive(bar_in + 8 * t);
+            for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
+                mbar_wait(bar_acc + 8 * t, use & 1);
+                tc_fence_after();
+                guard();
+                // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (stash slot 8-m)
+                const uint8_t* mask = m >= 1 ? st_tile + kStashH + (size_t)(8 - m) * 65536 : nullptr;
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_row + (uint32_t)c0, v);
+                    uint4 mk[4];
+                    if (mask) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) mk[j8] = ldg16(mask + (size_t)((c0 >> 3) + j8) * 2048 + (size_t)r * 16);
+                    }
+                    tc_wait_ld();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (m == 1) {          // + d_sigma_raw * w_sigma  (sigma_out dgrad joins d(h8) here)
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + kWsigOfs + c0 + j));
+                            f[j] = fmaf(d.w, w4.x, f[j]); f[j + 1] = fmaf(d.w, w4.y, f[j + 1]);
+                            f[j + 2] = fmaf(d.w, w4.z, f[j + 2]); f[j + 3] = fmaf(d.w, w4.w, f[j + 3]);
+                        }
+                    }
+                    if (mask) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const uint32_t w[4] = {mk[j8].x, mk[j8].y, mk[j8].z, mk[j8].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float hv = (j & 1) ? bf16hi(w[j >> 1]) : bf16lo(w[j >> 1]);
+                                if (!(hv > 0.f)) f[8 * j8 + j] = 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8)
+                        st_chunk(act, (c0 >> 3) + j8, r, pack_bf16(f[8 * j8], f[8 * j8 + 1]), pack_bf16(f[8 * j8 + 2], f[8 * j8 + 3]),
+                                 pack_bf16(f[8 * j8 + 4], f[8 * j8 + 5]), pack_bf16(f[8 * j8 + 6], f[8 * j8 + 7]));
+                }
+                store(dstash_ofs(8 - m), kActBytes);
+                tc_fence_before();
+                if (m != kNumDgradLayers - 1) mbar_arrive(bar_in + 8 * t);
+            }
+        }
+        if (r == 0) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// =======================================================================================================
+// Backward, part 2: wgrad.  gW[n, k] = sum_points dY[pt, n] * X[pt, k]: both operands are the stashed tile
+// images used as MN-major tcgen05 operands (contraction over the 128 points of a tile), accumulators stay in
+// TMEM across all tiles a CTA owns and are flushed once with fp32 atomics.  CTAs are split over "jobs"
+// (layer x operand block) in proportion to their cost.  Bias grads = column sums of the dY image in smem.
+// =======================================================================================================
+struct WgradJob {
+    uint32_t dy_ofs;      // byte offset of the dY block inside a dstash tile
+    uint32_t dy_bytes;    // 32768 (128 cols) or 65536
+    uint32_t x_ofs;       // byte offset of the X block inside a stash tile
+    uint32_t x_bytes;
+    int halves;           // M halves (dY cols / 128)
+    int xcols;            // N of the MMA (64 / 256 / 32)
+    int64_t w_dst;        // float offset of gW[0, col0] in the flat grads
+    int ldw;              // row stride of gW (K_true)
+    int ncols_valid;      // columns actually present (<= xcols)
+    int64_t b_dst;        // float offset of the bias grad, or -1
+    int cta_begin, cta_count;
+};
+constexpr int kMaxJobs = 16;
+struct WgradParams {
+    const uint8_t* stash; const uint8_t* dstash; float* grads;
+    int64_t num_tiles; int num_jobs;
+    WgradJob jobs[kMaxJobs];
+};
+constexpr int kWgBlock = 65536;                       // ring slot (one tile image)
+constexpr int kWgSlots = 3;
+constexpr int kWgSmemBar = kWgSlots * kWgBlock;       // 196608
+constexpr int kWgSmemBytes = kWgSmemBar + 256;
+constexpr int kWgThreads = 256;                       // warp 0 producer, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 bias/flush
+
+// MN-major, no-swizzle descriptor for a tile image used with the POINT index as K: SBO = stride between 8-wide
+// column groups (2048 B), LBO = stride between 8-point groups (128 B).
+__device__ __forceinline__ uint32_t make_idesc_mn(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kWgSmemBar, bar_empty = bar_full + 8 * kWgSlots, bar_done = bar_empty + 8 * kWgSlots;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgSmemBar + 8 * (2 * kWgSlots + 2));
+    // which job does this CTA belong to?
+    int ji = 0;
+    for (int j = 0; j < p.num_jobs; ++j)
+        if ((int)blockIdx.x >= p.jobs[j].cta_begin && (int)blockIdx.x < p.jobs[j].cta_begin + p.jobs[j].cta_count) ji = j;
+    const WgradJob& job = p.jobs[ji];
+    const int part = (int)blockIdx.x - job.cta_begin;
+    const bool want_bias = job.b_dst >= 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + 4); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    int64_t my_tiles = 0;
+    for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) ++my_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {       // producer: per tile, the dY image then the X image, each into the next ring slot
+            uint32_t slot = 0, round = 0;
+            for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
+                for (int which = 0; which < 2; ++which) {
+                    const uint8_t* src = which == 0 ? p.dstash + (size_t)tile * kDstashTile + job.dy_ofs
+                                                    : p.stash + (size_t)tile * kStashTile + job.x_ofs;
+                    const uint32_t bytes = which == 0 ? job.dy_bytes : job.x_bytes;
+                    mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
+                    mbar_expect_tx(bar_full + 8 * slot, bytes);
+                    bulk_g2s(sbase + slot * kWgBlock, src, bytes, bar_full + 8 * slot);
+                    if (++slot == kWgSlots) { slot = 0; ++round; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {       // MMA issuer
+            uint32_t slot = 0, round = 0;
+            const uint32_t idesc = make_idesc_mn(job.xcols);
+            bool first = true;
+            for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
+                const uint32_t s_dy = slot, r_dy = round;
+                if (++slot == kWgSlots) { slot = 0; ++round; }
+                const uint32_t s_x = slot, r_x = round;
+                if (++slot == kWgSlots) { slot = 0; ++round; }
+                mbar_wait(bar_full + 8 * s_dy, r_dy & 1);
+                mbar_wait(bar_full + 8 * s_x, r_x & 1);
+                tc_fence_after();
+                const uint32_t a_base = sbase + s_dy * kWgBlock, b_base = sbase + s_x * kWgBlock;
+                for (int h = 0; h < job.halves; ++h) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
+                        tc_mma(tmem_base + (uint32_t)h * 256u, make_desc(a_base + h * 32768 + ks * 256, 128, 2048),
+                               make_desc(b_base + ks * 256, 128, 2048), idesc, (!first || ks > 0) ? 1u : 0u);
+                }
+                first = false;
+                tc_commit(bar_empty + 8 * s_dy);
+                tc_commit(bar_empty + 8 * s_x);
+            }
+            tc_commit(bar_done);
+        }
+    } else if (warp >= 4) {
+        // ---- bias grads: column sums of the dY image (lanes over points -> conflict-free 16-byte reads) ----
+        const int w4 = warp - 4;
+        float bsum[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[i][j] = 0.f;
+        const int nchunks = job.halves * 16;            // 8-column groups in dY
+        {
+            uint32_t slot = 0, round = 0;
+            for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
+                const uint32_t s_dy = slot, r_dy = round;
+                if (++slot == kWgSlots) { slot = 0; ++round; }
+                const uint32_t s_x = slot, r_x = round;
+                if (++slot == kWgSlots) { slot = 0; ++round; }
+                // pace on the ring even when there is no bias to sum: an early arrive would complete the wrong phase
+                mbar_wait(bar_full + 8 * s_dy, r_dy & 1);
+                mbar_wait(bar_full + 8 * s_x, r_x & 1);
+                if (want_bias) {
+                    const uint8_t* img = smem + s_dy * kWgBlock;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c8 = w4 + 4 * i;
+                        if (c8 < nchunks) {
+#pragma unroll
+                            for (int rg = 0; rg < 4; ++rg) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(img + (size_t)c8 * 2048 + (size_t)(rg * 32 + lane) * 16);
+                                bsum[i][0] += bf16lo(v.x); bsum[i][1] += bf16hi(v.x); bsum[i][2] += bf16lo(v.y); bsum[i][3] += bf16hi(v.y);
+                                bsum[i][4] += bf16lo(v.z); bsum[i][5] += bf16hi(v.z); bsum[i][6] += bf16lo(v.w); bsum[i][7] += bf16hi(v.w);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_empty + 8 * s_dy); mbar_arrive(bar_empty + 8 * s_x); }
+            }
+        }
+        if (want_bias && my_tiles > 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c8 = w4 + 4 * i;
+                if (c8 < nchunks) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float sum = warp_sum(bsum[i][j]);
+                        if (lane == 0) atomicAdd(p.grads + job.b_dst + c8 * 8 + j, sum);
+                    }
+                }
+            }
+        }
+        // ---- flush: TMEM accumulators -> fp32 atomics on the flat gradient ----
+        if (my_tiles > 0) {
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            for (int h = 0; h < job.halves; ++h) {
+                const int n = h * 128 + w4 * 32 + lane;                 // output feature (row of gW)
+                const uint32_t trow = tmem_base + (uint32_t)h * 256u + ((uint32_t)(w4 * 32) << 16);
+                for (int c0 = 0; c0 < job.xcols; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(trow + (uint32_t)c0, v);
+                    tc_wait_ld();
+                    float* dst = p.grads + job.w_dst + (int64_t)n * job.ldw + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < job.ncols_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// =======================================================================================================
+// Backward, part 3: head parameter grads on CUDA cores (fp32 accumulate):
+//   g w_sigma[j] = sum d_sigma * h8[., j];  g b_sigma;  g Wo[ch, j] = sum d_rgb[ch] * c[., j];  g bo
+// Warps own 8-column groups of the stashed h8 / c images; lanes run over points (coalesced 16-byte loads).
+// =======================================================================================================
+__global__ void __launch_bounds__(256) field_head_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict__ stash,
+                                                              float* __restrict__ g_wsig, float* __restrict__ g_bsig,
+                                                              float* __restrict__ g_wo, float* __restrict__ g_bo, int64_t Q,
+                                                              int64_t num_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float hs[4][8], cs[2][3][8], bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hs[i][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs[i][ch][j] = 0.f;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint8_t* st = stash + (size_t)tile * kStashTile;
+#pragma unroll
+        for (int rg = 0; rg < 4; ++rg) {
+            const int r = rg * 32 + lane;
+            const int64_t q = tile * TILE_M + r;
+            const float4 d = q < Q ? __ldg(reinterpret_cast<const float4*>(d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp == 0) { bs[0] += d.x; bs[1] += d.y; bs[2] += d.z; bs[3] += d.w; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {          // h8 chunks warp, warp+8, warp+16, warp+24
+                const uint4 v = ldg16(st + kStashH + 7 * 65536 + (size_t)(warp + 8 * i) * 2048 + (size_t)r * 16);
+                hs[i][0] = fmaf(d.w, bf16lo(v.x), hs[i][0]); hs[i][1] = fmaf(d.w, bf16hi(v.x), hs[i][1]);
+                hs[i][2] = fmaf(d.w, bf16lo(v.y), hs[i][2]); hs[i][3] = fmaf(d.w, bf16hi(v.y), hs[i][3]);
+                hs[i][4] = fmaf(d.w, bf16lo(v.z), hs[i][4]); hs[i][5] = fmaf(d.w, bf16hi(v.z), hs[i][5]);
+                hs[i][6] = fmaf(d.w, bf16lo(v.w), hs[i][6]); hs[i][7] = fmaf(d.w, bf16hi(v.w), hs[i][7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {          // c chunks warp, warp+8
+                const uint4 v = ldg16(st + kStashC + (size_t)(warp + 8 * i) * 2048 + (size_t)r * 16);
+                const float c[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    cs[i][0][j] = fmaf(d.x, c[j], cs[i][0][j]); cs[i][1][j] = fmaf(d.y, c[j], cs[i][1][j]);
+                    cs[i][2][j] = fmaf(d.z, c[j], cs[i][2][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = warp_sum(hs[i][j]);
+            if (lane == 0) atomicAdd(g_wsig + (warp + 8 * i) * 8 + j, v);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = warp_sum(cs[i][ch][j]);
+                if (lane == 0) atomicAdd(g_wo + ch * 128 + (warp + 8 * i) * 8 + j, v);
+            }
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bs[j] = warp_sum(bs[j]);
+        if (lane == 0) { atomicAdd(g_bo, bs[0]); atomicAdd(g_bo + 1, bs[1]); atomicAdd(g_bo + 2, bs[2]); atomicAdd(g_bsig, bs[3]); }
+    }
+}
+
+// transposed images for the dgrad chain
+__global__ void pack_tc_transposed_kernel(const float* __restrict__ params, uint8_t* __restrict__ out) {
+    for (int m = blockIdx.y; m < kNumDgradLayers; m += gridDim.y) {
+        const int pl = m == 0 ? 10 : (m == 1 ? 8 : 9 - m);
+        const LayerDesc d = layer_desc(pl);
+        const int Nout = d.N;                                  // contraction length (128 or 256)
+        __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + dgrad_layer_ofs(m));
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Nout * 256; idx += gridDim.x * blockDim.x) {
+            const int n = idx / 256, j = idx % 256;            // W[n, j], j < 256 <= K
+            img[((size_t)(n >> 3) * 256 + j) * 8 + (n & 7)] = __float2bfloat16_rn(params[d.w_off + (int64_t)n * d.K + j]);
+        }
+    }
+}
+
 }  // namespace tc
 
-size_t tc_packed_bytes() { return align_up(tc::kWeightImageBytes + tc::kTailFloats * sizeof(float), 256); }
+size_t tc_packed_bytes() { return align_up(tc::kPackedTcBytes, 256); }
 
 size_t tc_workspace_bytes(int64_t Q, int stash) {
     const int64_t tiles = cdiv(Q, tc::TILE_M);
-    return 256 + (stash ? (size_t)tiles * tc::kStashTile : 0);
+    return 256 + (stash ? (size_t)tiles * (tc::kStashTile + tc::kDstashTile) : 0);
 }
+static inline uint8_t* ws_stash(void* ws) { return reinterpret_cast<uint8_t*>(ws) + 256; }
+static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (size_t)cdiv(Q, tc::TILE_M) * tc::kStashTile; }
 
 int tc_pack(const float* params, void* packed_bf16, cudaStream_t st) {
     tc::pack_tc_kernel<<<dim3(32, tc::kNumMmaLayers), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed_bf16));
     NSB_LAUNCH_CHECK("pack_tc_kernel");
+    tc::pack_tc_transposed_kernel<<<dim3(32, tc::kNumDgradLayers), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed_bf16));
+    NSB_LAUNCH_CHECK("pack_tc_transposed_kernel");
     return NSB_OK;
 }
 
@@ -496,7 +989,7 @@ int tc_field_fwd_rays(const float* rays_o, const float* rays_d, const float* z, 
     tc::FwdParams p{};
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.ray_norm = ray_norm; p.viewdirs = viewdirs;
     p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw;
-    p.stash = stash ? reinterpret_cast<uint8_t*>(ws) + 256 : nullptr;
+    p.stash = stash ? ws_stash(ws) : nullptr;
     p.Q = B * (int64_t)N; p.N = N;
     return launch_fwd<false>(p, st);
 }
@@ -506,12 +999,75 @@ int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* pac
     tc::FwdParams p{};
     p.enc_pos = enc_pos; p.enc_dir = enc_dir;
     p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw;
-    p.stash = stash ? reinterpret_cast<uint8_t*>(ws) + 256 : nullptr;
+    p.stash = stash ? ws_stash(ws) : nullptr;
     p.Q = Q; p.N = 1;
     return launch_fwd<true>(p, st);
 }
 
-int tc_field_bwd(const float*, const void*, float*, void*, int64_t, cudaStream_t) { return NSB_E_BADARG; }
+// parameter grads (accumulated into the flat `grads`) from the forward stash in ws: dgrad chain -> wgrad -> head grads
+int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st) {
+    NSB_TRY(check_arch());
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tc::field_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(bwd kernels)");
+        attr_set = true;
+    }
+    const int64_t tiles = cdiv(Q, tc::TILE_M);
+    const int64_t pairs = (tiles + 1) / 2;
+    tc::DgradParams dp{};
+    dp.d_raw = d_raw; dp.packed = reinterpret_cast<const uint8_t*>(packed); dp.stash = ws_stash(ws); dp.dstash = ws_dstash(ws, Q);
+    dp.Q = Q; dp.num_tiles = tiles;
+    tc::field_dgrad_kernel<<<(int)(pairs < num_sms() ? pairs : num_sms()), tc::kThreads, tc::kSmemBytes, st>>>(dp);
+    NSB_LAUNCH_CHECK("field_dgrad_kernel");
+
+    tc::WgradParams wp{};
+    wp.stash = ws_stash(ws); wp.dstash = ws_dstash(ws, Q); wp.grads = grads; wp.num_tiles = tiles;
+    int nj = 0;
+    auto add = [&](int k, size_t x_ofs, uint32_t x_bytes, int xcols, int pl, int col0, int valid, bool bias) {
+        const LayerDesc d = layer_desc(pl);
+        tc::WgradJob& j = wp.jobs[nj++];
+        j.dy_ofs = (uint32_t)tc::dstash_ofs(k); j.dy_bytes = k == 9 ? 32768u : 65536u; j.halves = k == 9 ? 1 : 2;
+        j.x_ofs = (uint32_t)x_ofs; j.x_bytes = x_bytes; j.xcols = xcols;
+        j.w_dst = d.w_off + col0; j.ldw = d.K; j.ncols_valid = valid; j.b_dst = bias ? d.b_off : -1;
+    };
+    add(0, tc::kStashGx, 16384, 64, 0, 0, 63, true);
+    for (int l = 1; l <= 7; ++l) {
+        add(l, tc::kStashH + (size_t)(l - 1) * 65536, 65536, 256, l, 0, 256, true);
+        if (l == 4) add(4, tc::kStashGx, 16384, 64, 4, 256, 63, false);
+    }
+    add(8, tc::kStashH + 7 * 65536, 65536, 256, 8, 0, 256, true);           // feature
+    add(9, tc::kStashFeat, 65536, 256, 10, 0, 256, true);                   // color_fc [feat | .]
+    add(9, tc::kStashGd, 8192, 32, 10, 256, 27, false);                     // color_fc [. | gamma(d)]
+    wp.num_jobs = nj;
+    // CTAs per job in proportion to the bytes a tile costs (the kernel is HBM-bound), at least one each
+    const int total = num_sms();
+    double sum = 0;
+    for (int i = 0; i < nj; ++i) sum += wp.jobs[i].dy_bytes + wp.jobs[i].x_bytes;
+    int used = 0;
+    for (int i = 0; i < nj; ++i) {
+        int c = (int)((wp.jobs[i].dy_bytes + wp.jobs[i].x_bytes) / sum * total);
+        if (c < 1) c = 1;
+        if ((int64_t)c > tiles) c = (int)tiles;
+        wp.jobs[i].cta_count = c; used += c;
+    }
+    for (int i = 0; used < total && i < 4 * nj; ++i) {      // hand out the remainder to the big jobs
+        tc::WgradJob& j = wp.jobs[i % nj];
+        if (j.xcols == 256 && (int64_t)j.cta_count < tiles) { ++j.cta_count; ++used; }
+    }
+    int begin = 0;
+    for (int i = 0; i < nj; ++i) { wp.jobs[i].cta_begin = begin; begin += wp.jobs[i].cta_count; }
+    tc::field_wgrad_kernel<<<begin, tc::kWgThreads, tc::kWgSmemBytes, st>>>(wp);
+    NSB_LAUNCH_CHECK("field_wgrad_kernel");
+
+    const LayerDesc ds = layer_desc(9), dc = layer_desc(11);
+    const int hg = (int)(tiles < 2 * (int64_t)num_sms() ? tiles : 2 * (int64_t)num_sms());
+    tc::field_head_grad_kernel<<<hg, 256, 0, st>>>(d_raw, ws_stash(ws), grads + ds.w_off, grads + ds.b_off, grads + dc.w_off,
+                                                   grads + dc.b_off, Q, tiles);
+    NSB_LAUNCH_CHECK("field_head_grad_kernel");
+    return NSB_OK;
+}
 
 // debug hook used by tests: run the forward and dump the fp32 post-activation of one layer
 int tc_debug_layer(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,

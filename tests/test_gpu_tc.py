@@ -126,3 +126,59 @@ def test_tc_eval_psnr_delta(setup):
     r = nsb.render_rays(T(g["rays_o_marching"]), T(g["rays_d_marching_unit"]), T(g["rays_d_marching_norm"]).reshape(-1),
                         T(g["rays_d_world_unit"]), nets["bf16"][0], nets["bf16"][1], near=2.0, far=6.0, nc=64, nf=128, white_bkgd=True)
     assert float(np.abs(N(r[0]).reshape(H, W, 3) - g["fine_rgb"]).max()) < 3e-2
+
+
+def test_tc_backward_matches_reference_grads(setup):
+    """NeRF.forward/backward in bf16 mode on the golden MLP fixture: parameter grads vs the reference's autograd."""
+    nsb, _lib, _, _, _, _ = setup
+    g = golden("mlp")
+    p = O.init_params(np.random.default_rng(int(g["seed"])), sigma_bias=float(g["sigma_bias"]))
+    net = nsb.NeRF(63, 27, mode="bf16").to(DEV)
+    net.load_state_dict({k: T(v) for k, v in p.items()})
+    out = net(T(g["enc_pos"]), T(g["enc_dir"]))
+    assert rel_l2(N(out), g["out"]) < 2e-2
+    out.backward(T(g["d_out"]))
+    torch.cuda.synchronize()
+    flat = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
+    assert np.isfinite(flat).all()
+    assert rel_l2(flat[g["grad_idx"]], g["grad_samples"]) < 3e-2
+    norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=3e-2, atol=1e-5)
+    # larger, ragged Q against the oracle: 1000 points (7.8 tiles)
+    rng = np.random.default_rng(11)
+    ep = O.positional_encode(rng.uniform(-4, 4, (1000, 3)).astype(np.float32), 10)
+    ed = O.positional_encode(O._normalize(rng.standard_normal((1000, 3)).astype(np.float32)), 4)
+    d_out = rng.standard_normal((1000, 4)).astype(np.float32)
+    raw, caches = O.mlp_forward(p, ep, ed, keep=True)
+    ref = O.flatten_params(O.mlp_backward(p, caches, d_out))
+    net.zero_grad()
+    net(T(ep), T(ed)).backward(T(d_out))
+    flat = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
+    assert rel_l2(flat, ref) < 3e-2
+    off = 0
+    for name, shp in O.PARAM_SHAPES:
+        n = int(np.prod(shp))
+        assert rel_l2(flat[off:off + n], ref[off:off + n]) < 5e-2, name
+        off += n
+
+
+def test_tc_train_step(setup):
+    nsb, _lib, _, _, _, _ = setup
+    g = golden("train_step")
+    tr = nsb.VanillaTrainer(DEV, nc=int(g["nc"]), nf=int(g["nf"]), near=2.0, far=6.0, mode="bf16")
+    for net, seed in ((tr.nerf_c, g["seed_c"]), (tr.nerf_f, g["seed_f"])):
+        p = O.init_params(np.random.default_rng(int(seed)), sigma_bias=float(g["sigma_bias"]))
+        net.load_state_dict({k: T(v) for k, v in p.items()})
+    batch = {k: T(g[k]) for k in ("rays_o_marching", "rays_d_marching_unit", "rays_d_marching_norm", "rays_d_world_unit", "rgb")}
+    draws = dict(U=T(g["U"]), u_fine=T(g["u_fine"]), noise_c=T(g["noise_c"]), noise_f=T(g["noise_f"]))
+    out = tr._train_step(batch, draws)
+    loss = float(out["loss"].detach())
+    assert abs(loss - float(g["loss"])) <= 2e-2 * float(g["loss"])
+    mse = float(((out["comp_f"] - T(g["comp_f"])) ** 2).mean())
+    assert mse < 1e-4
+    out["loss"].backward()
+    for tag, net in (("c", tr.nerf_c), ("f", tr.nerf_f)):
+        norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+        np.testing.assert_allclose(norms, g[f"grad_norms_{tag}"], rtol=8e-2, atol=1e-6)
+    losses = [float(tr.step(batch, draws)[0]) for _ in range(8)]
+    assert losses[-1] < losses[0] < 1.05 * float(g["loss"])
