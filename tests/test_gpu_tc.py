@@ -128,38 +128,80 @@ def test_tc_eval_psnr_delta(setup):
     assert float(np.abs(N(r[0]).reshape(H, W, 3) - g["fine_rgb"]).max()) < 3e-2
 
 
-def test_tc_backward_matches_reference_grads(setup):
-    """NeRF.forward/backward in bf16 mode on the golden MLP fixture: parameter grads vs the reference's autograd."""
+def bf16(x):
+    """round-to-nearest-even bf16, returned as float32 (what __float2bfloat16_rn does)"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def bf16_emulated_mlp(p, ep, ed, d_out):
+    """The oracle MLP (mlps.py:221-278 + autograd) with bf16 rounding at exactly the points where the tensor-core
+    kernels round: weights and layer inputs (A/B operands), the stashed activations and every dY tile; all
+    accumulation in fp32.  Differences left vs the kernels: fp32 summation order only."""
+    W = {k: (bf16(v) if k.endswith("weight") and not k.startswith(("sigma_out", "color_out")) else v) for k, v in p.items()}
+    gx = bf16(ep); gd = bf16(ed)
+    h, xs, hb = gx, [], []
+    for l in range(8):
+        x = np.concatenate([h, gx], -1) if l == 4 else h
+        xs.append(x)
+        f = np.maximum(x @ W[f"mlp.{l}.weight"].T + p[f"mlp.{l}.bias"], 0).astype(np.float32)
+        if l == 7:
+            sig = f @ p["sigma_out.weight"].T + p["sigma_out.bias"]
+        h = bf16(f); hb.append(h)
+    featb = bf16(h @ W["feature.weight"].T + p["feature.bias"])
+    cin = np.concatenate([featb, gd], -1)
+    cf = np.maximum(cin @ W["color_fc.weight"].T + p["color_fc.bias"], 0).astype(np.float32)
+    raw = np.concatenate([cf @ p["color_out.weight"].T + p["color_out.bias"], sig], -1).astype(np.float32)
+    cb = bf16(cf)
+    g = {}
+    d_rgb, d_sig = d_out[:, :3], d_out[:, 3:4]
+    g["color_out.weight"] = d_rgb.T @ cb; g["color_out.bias"] = d_rgb.sum(0)
+    g["sigma_out.weight"] = d_sig.T @ hb[7]; g["sigma_out.bias"] = d_sig.sum(0)
+    dc = bf16((d_rgb @ p["color_out.weight"]) * (cb > 0))
+    g["color_fc.weight"] = dc.T @ cin; g["color_fc.bias"] = dc.sum(0)
+    dfeat = bf16(dc @ W["color_fc.weight"][:, :256])
+    g["feature.weight"] = dfeat.T @ hb[7]; g["feature.bias"] = dfeat.sum(0)
+    dy = bf16((dfeat @ W["feature.weight"] + d_sig @ p["sigma_out.weight"]) * (hb[7] > 0))
+    for l in range(7, -1, -1):
+        g[f"mlp.{l}.weight"] = dy.T @ xs[l]; g[f"mlp.{l}.bias"] = dy.sum(0)
+        if l > 0:
+            dy = bf16((dy @ W[f"mlp.{l}.weight"][:, :256]) * (hb[l - 1] > 0))
+    return raw, {k: v.astype(np.float32) for k, v in g.items()}
+
+
+def test_tc_backward_matches_bf16_emulation(setup):
+    """Kernel correctness of stash + dgrad chain + wgrad + head grads, independent of precision effects: compare with
+    the oracle evaluated with bf16 rounding at the same points.  (Against the fp32 reference the grads differ by
+    ~4% per layer because ReLU masks of near-zero activations flip under bf16 -- inherent to the mode.)"""
     nsb, _lib, _, _, _, _ = setup
-    g = golden("mlp")
-    p = O.init_params(np.random.default_rng(int(g["seed"])), sigma_bias=float(g["sigma_bias"]))
+    p = O.init_params(np.random.default_rng(7), sigma_bias=0.3)
     net = nsb.NeRF(63, 27, mode="bf16").to(DEV)
     net.load_state_dict({k: T(v) for k, v in p.items()})
-    out = net(T(g["enc_pos"]), T(g["enc_dir"]))
-    assert rel_l2(N(out), g["out"]) < 2e-2
-    out.backward(T(g["d_out"]))
-    torch.cuda.synchronize()
-    flat = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
-    assert np.isfinite(flat).all()
-    assert rel_l2(flat[g["grad_idx"]], g["grad_samples"]) < 3e-2
-    norms = np.array([float(q.grad.norm()) for q in net.parameters()])
-    np.testing.assert_allclose(norms, g["grad_norms"], rtol=3e-2, atol=1e-5)
-    # larger, ragged Q against the oracle: 1000 points (7.8 tiles)
     rng = np.random.default_rng(11)
-    ep = O.positional_encode(rng.uniform(-4, 4, (1000, 3)).astype(np.float32), 10)
-    ed = O.positional_encode(O._normalize(rng.standard_normal((1000, 3)).astype(np.float32)), 4)
-    d_out = rng.standard_normal((1000, 4)).astype(np.float32)
-    raw, caches = O.mlp_forward(p, ep, ed, keep=True)
-    ref = O.flatten_params(O.mlp_backward(p, caches, d_out))
+    for Q in (1000, 128 * 7, 5):                                   # ragged, exact tiles (odd count), tiny
+        ep = O.positional_encode(rng.uniform(-4, 4, (Q, 3)).astype(np.float32), 10)
+        ed = O.positional_encode(O._normalize(rng.standard_normal((Q, 3)).astype(np.float32)), 4)
+        d_out = rng.standard_normal((Q, 4)).astype(np.float32)
+        raw, ref = bf16_emulated_mlp(p, ep, ed, d_out)
+        net.zero_grad()
+        out = net(T(ep), T(ed))
+        assert rel_l2(N(out), raw) < 2e-3, Q
+        out.backward(T(d_out))
+        torch.cuda.synchronize()
+        for (name, _), q in zip(O.PARAM_SHAPES, net.parameters()):
+            e = rel_l2(N(q.grad), ref[name])
+            assert e < 2e-2, (Q, name, e)
+    # and the grads are still a sane approximation of the fp32 reference's (golden fixture, 160 points)
+    g = golden("mlp")
+    p = O.init_params(np.random.default_rng(int(g["seed"])), sigma_bias=float(g["sigma_bias"]))
+    net.load_state_dict({k: T(v) for k, v in p.items()})
     net.zero_grad()
-    net(T(ep), T(ed)).backward(T(d_out))
+    net(T(g["enc_pos"]), T(g["enc_dir"])).backward(T(g["d_out"]))
+    norms = np.array([float(q.grad.norm()) for q in net.parameters()])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=5e-2, atol=1e-5)
     flat = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
-    assert rel_l2(flat, ref) < 3e-2
-    off = 0
-    for name, shp in O.PARAM_SHAPES:
-        n = int(np.prod(shp))
-        assert rel_l2(flat[off:off + n], ref[off:off + n]) < 5e-2, name
-        off += n
+    assert rel_l2(flat[g["grad_idx"]], g["grad_samples"]) < 0.25
 
 
 def test_tc_train_step(setup):
@@ -182,3 +224,11 @@ def test_tc_train_step(setup):
         np.testing.assert_allclose(norms, g[f"grad_norms_{tag}"], rtol=8e-2, atol=1e-6)
     losses = [float(tr.step(batch, draws)[0]) for _ in range(8)]
     assert losses[-1] < losses[0] < 1.05 * float(g["loss"])
+    # trains like the fp32 mode: same init, same batch/draws, 30 Adam steps each
+    final = {}
+    for mode in ("fp32", "bf16"):
+        t2 = nsb.VanillaTrainer(DEV, nc=int(g["nc"]), nf=int(g["nf"]), near=2.0, far=6.0, mode=mode, seed=3, sigma_bias=0.4)
+        for _ in range(30):
+            sc = t2.step(batch, draws)
+        final[mode] = float(sc[0])
+    assert abs(final["bf16"] - final["fp32"]) < 0.05 * final["fp32"], final
