@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        // (whole warp runs the uniform control flow; one lane issues -- keeps operands in uniform registers)
+        {
             uint32_t stage = 0, round = 0;
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
@@ -276,8 +277,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     const int ns = layer_nslabs(l);
                     for (int s = 0; s < ns; ++s) {
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * bytes, bytes, bar_full + 8 * stage);
+                        if (lane == 0) {
+                            mbar_expect_tx(bar_full + 8 * stage, bytes);
+                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * bytes, bytes, bar_full + 8 * stage);
+                        }
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
                 }
@@ -285,7 +289,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ========================================
-        if (lane == 0) {
+        // The whole warp executes the loop (warp-uniform values -> uniform registers, no per-lane waterfall around
+        // the tcgen05 instructions); lane 0 issues.
+        {
+            const bool leader = lane == 0;
             uint32_t stage = 0, round = 0, use = 0;   // use = how many layers both tiles went through (barrier parity)
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
@@ -309,15 +316,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                             tc_fence_after();
                             const uint32_t a_addr = sbase + (from_gx ? (kSmemGx + t * kGxBytes) : (kSmemAct + t * kActBytes)) + a_off;
                             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t adesc = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
-                                const uint64_t bdesc = make_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128);
-                                tc_mma(d_tmem, adesc, bdesc, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                            const uint64_t adesc0 = make_desc(a_addr, 2048, 128), adesc1 = make_desc(a_addr + 2 * 2048, 2048, 128);
+                            const uint64_t bdesc0 = make_desc(b_addr, lbo_b, 128), bdesc1 = make_desc(b_addr + 2 * lbo_b, lbo_b, 128);
+                            if (leader) {
+                                tc_mma(d_tmem, adesc0, bdesc0, idesc, s > 0 ? 1u : 0u);
+                                tc_mma(d_tmem, adesc1, bdesc1, idesc, 1u);
+                                if (s == ns - 1) tc_commit(bar_acc + 8 * t);  // accumulator of tile t complete
                             }
-                            if (s == ns - 1) tc_commit(bar_acc + 8 * t);      // accumulator of tile t complete
                         }
-                        tc_commit(bar_empty + 8 * stage);                     // ring slot free once these MMAs retire
+                        if (leader) tc_commit(bar_empty + 8 * stage);         // ring slot free once these MMAs retire
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
                 }
@@ -526,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
     const float* tail = reinterpret_cast<const float*>(p.packed + kBiasOfs);
 
     if (warp == 0) {
-        if (lane == 0) {                                   // TMA producer: K=32 x N=256 slabs of W^T
+        {                                                  // TMA producer: K=32 x N=256 slabs of W^T
             uint32_t stage = 0, round = 0;
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int m = 0; m < kNumDgradLayers; ++m) {
@@ -534,15 +542,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                     const int ns = m == 0 ? 4 : 8;
                     for (int s = 0; s < ns; ++s) {
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-                        bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
+                        if (lane == 0) {
+                            mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
+                        }
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                   // MMA issuer
+        {                                                  // MMA issuer (warp-uniform loop, lane 0 issues)
+            const bool leader = lane == 0;
             uint32_t stage = 0, round = 0, use = 0;
             const uint32_t idesc = make_idesc(256);
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -557,13 +569,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                             tc_fence_after();
                             const uint32_t a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 4u * 2048u;
                             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks)
-                                tc_mma(d_tmem, make_desc(a_addr + ks * 2 * 2048, 2048, 128), make_desc(b_addr + ks * 2 * 4096, 4096, 128),
-                                       idesc, (s > 0 || ks > 0) ? 1u : 0u);
-                            if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                            const uint64_t adesc0 = make_desc(a_addr, 2048, 128), adesc1 = make_desc(a_addr + 2 * 2048, 2048, 128);
+                            const uint64_t bdesc0 = make_desc(b_addr, 4096, 128), bdesc1 = make_desc(b_addr + 2 * 4096, 4096, 128);
+                            if (leader) {
+                                tc_mma(d_tmem, adesc0, bdesc0, idesc, s > 0 ? 1u : 0u);
+                                tc_mma(d_tmem, adesc1, bdesc1, idesc, 1u);
+                                if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                            }
                         }
-                        tc_commit(bar_empty + 8 * stage);
+                        if (leader) tc_commit(bar_empty + 8 * stage);
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
                 }
@@ -733,7 +748,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
     for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) ++my_tiles;
 
     if (warp == 0) {
-        if (lane == 0) {       // producer: per tile, the dY image then the X image, each into the next ring slot
+        {                      // producer: per tile, the dY image then the X image, each into the next ring slot
             uint32_t slot = 0, round = 0;
             for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
                 for (int which = 0; which < 2; ++which) {
@@ -741,14 +756,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                                                     : p.stash + (size_t)tile * kStashTile + job.x_ofs;
                     const uint32_t bytes = which == 0 ? job.dy_bytes : job.x_bytes;
                     mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, bytes);
-                    bulk_g2s(sbase + slot * kWgBlock, src, bytes, bar_full + 8 * slot);
+                    if (lane == 0) {
+                        mbar_expect_tx(bar_full + 8 * slot, bytes);
+                        bulk_g2s(sbase + slot * kWgBlock, src, bytes, bar_full + 8 * slot);
+                    }
+                    __syncwarp();
                     if (++slot == kWgSlots) { slot = 0; ++round; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {       // MMA issuer
+        {                      // MMA issuer (warp-uniform loop, lane 0 issues)
+            const bool leader = lane == 0;
             uint32_t slot = 0, round = 0;
             const uint32_t idesc = make_idesc_mn(job.xcols);
             bool first = true;
@@ -763,15 +782,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                 const uint32_t a_base = sbase + s_dy * kWgBlock, b_base = sbase + s_x * kWgBlock;
                 for (int h = 0; h < job.halves; ++h) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
-                        tc_mma(tmem_base + (uint32_t)h * 256u, make_desc(a_base + h * 32768 + ks * 256, 128, 2048),
-                               make_desc(b_base + ks * 256, 128, 2048), idesc, (!first || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < 8; ++ks) {   // K = 16 points per MMA
+                        const uint64_t ad = make_desc(a_base + h * 32768 + ks * 256, 128, 2048);
+                        const uint64_t bd = make_desc(b_base + ks * 256, 128, 2048);
+                        if (leader) tc_mma(tmem_base + (uint32_t)h * 256u, ad, bd, idesc, (!first || ks > 0) ? 1u : 0u);
+                    }
                 }
                 first = false;
-                tc_commit(bar_empty + 8 * s_dy);
-                tc_commit(bar_empty + 8 * s_x);
+                if (leader) { tc_commit(bar_empty + 8 * s_dy); tc_commit(bar_empty + 8 * s_x); }
+                __syncwarp();
             }
-            tc_commit(bar_done);
+            if (leader) tc_commit(bar_done);
         }
     } else if (warp >= 4) {
         // ---- bias grads: column sums of the dY image (lanes over points -> conflict-free 16-byte reads) ----
