@@ -89,8 +89,7 @@ __device__ __forceinline__ uint64_t global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const uint64_t t0 = global_ns();
     while (!mbar_try_wait(bar, parity)) {
         if (global_ns() - t0 > 2000000000ull) {   // 2 s
@@ -99,6 +98,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// one lane of a converged warp (ptxas then knows a single thread issues and drops the per-lane waterfall)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// descriptor = constant high word (LBO, SBO, version) | 14-bit start address
+__device__ __forceinline__ uint64_t desc_hi(uint32_t lbo, uint32_t sbo) {
+    return ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t desc_at(uint64_t hi, uint32_t saddr) { return hi | (uint64_t)((saddr & 0x3FFFFu) >> 4); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     const int ns = layer_nslabs(l);
                     for (int s = 0; s < ns; ++s) {
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
-                        if (lane == 0) {
+                        if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
                             bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * bytes, bytes, bar_full + 8 * stage);
                         }
@@ -292,7 +305,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         // The whole warp executes the loop (warp-uniform values -> uniform registers, no per-lane waterfall around
         // the tcgen05 instructions); lane 0 issues.
         {
-            const bool leader = lane == 0;
             uint32_t stage = 0, round = 0, use = 0;   // use = how many layers both tiles went through (barrier parity)
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
@@ -309,22 +321,43 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                         else if (l == 9 && s == 8) { from_gx = true; a_off = 0; }
                         else { from_gx = false; a_off = (uint32_t)s * 4u * 2048u; }
                         const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (s == 0) { mbar_wait(bar_in + 8 * t, use & 1); }
-                            if (t == 0) { mbar_wait(bar_full + 8 * stage, round & 1); }
+                        const uint32_t a0 = sbase + (from_gx ? kSmemGx : kSmemAct) + a_off;                  // tile A
+                        const uint32_t a1 = a0 + (from_gx ? kGxBytes : kActBytes);                          // tile B
+                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(lbo_b, 128);
+                        const uint64_t bd0 = desc_at(bhi, b_addr), bd1 = desc_at(bhi, b_addr + 2 * lbo_b);
+                        const bool last = s == ns - 1;
+                        if (s == 0) {
+                            // layer start: tile A may begin while tile B's epilogue of the previous layer still runs
+                            mbar_wait(bar_in, use & 1);
+                            mbar_wait(bar_full + 8 * stage, round & 1);
                             tc_fence_after();
-                            const uint32_t a_addr = sbase + (from_gx ? (kSmemGx + t * kGxBytes) : (kSmemAct + t * kActBytes)) + a_off;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-                            const uint64_t adesc0 = make_desc(a_addr, 2048, 128), adesc1 = make_desc(a_addr + 2 * 2048, 2048, 128);
-                            const uint64_t bdesc0 = make_desc(b_addr, lbo_b, 128), bdesc1 = make_desc(b_addr + 2 * lbo_b, lbo_b, 128);
-                            if (leader) {
-                                tc_mma(d_tmem, adesc0, bdesc0, idesc, s > 0 ? 1u : 0u);
-                                tc_mma(d_tmem, adesc1, bdesc1, idesc, 1u);
-                                if (s == ns - 1) tc_commit(bar_acc + 8 * t);  // accumulator of tile t complete
+                            if (elect_one()) {
+                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 0u);
+                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc);
+                            }
+                            __syncwarp();
+                            mbar_wait(bar_in + 8, use & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 0u);
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc + 8);
+                                tc_commit(bar_empty + 8 * stage);
+                            }
+                        } else {
+                            mbar_wait(bar_full + 8 * stage, round & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 1u);
+                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc);                 // accumulator of tile A complete
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 1u);
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc + 8);             // accumulator of tile B complete
+                                tc_commit(bar_empty + 8 * stage);             // ring slot free once these MMAs retire
                             }
                         }
-                        if (leader) tc_commit(bar_empty + 8 * stage);         // ring slot free once these MMAs retire
                         __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
@@ -542,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                     const int ns = m == 0 ? 4 : 8;
                     for (int s = 0; s < ns; ++s) {
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
-                        if (lane == 0) {
+                        if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
                             bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
                         }
@@ -554,7 +587,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
         }
     } else if (warp == 1) {
         {                                                  // MMA issuer (warp-uniform loop, lane 0 issues)
-            const bool leader = lane == 0;
             uint32_t stage = 0, round = 0, use = 0;
             const uint32_t idesc = make_idesc(256);
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -562,22 +594,39 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                     const int ns = m == 0 ? 4 : 8;
                     for (int s = 0; s < ns; ++s) {
                         const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (s == 0) { mbar_wait(bar_in + 8 * t, use & 1); }
-                            if (t == 0) { mbar_wait(bar_full + 8 * stage, round & 1); }
+                        const uint32_t a0 = sbase + kSmemAct + (uint32_t)s * 4u * 2048u, a1 = a0 + kActBytes;
+                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
+                        const uint64_t bd0 = desc_at(bhi, b_addr), bd1 = desc_at(bhi, b_addr + 2 * 4096);
+                        const bool last = s == ns - 1;
+                        if (s == 0) {
+                            mbar_wait(bar_in, use & 1);
+                            mbar_wait(bar_full + 8 * stage, round & 1);
                             tc_fence_after();
-                            const uint32_t a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 4u * 2048u;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-                            const uint64_t adesc0 = make_desc(a_addr, 2048, 128), adesc1 = make_desc(a_addr + 2 * 2048, 2048, 128);
-                            const uint64_t bdesc0 = make_desc(b_addr, 4096, 128), bdesc1 = make_desc(b_addr + 2 * 4096, 4096, 128);
-                            if (leader) {
-                                tc_mma(d_tmem, adesc0, bdesc0, idesc, s > 0 ? 1u : 0u);
-                                tc_mma(d_tmem, adesc1, bdesc1, idesc, 1u);
-                                if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                            if (elect_one()) {
+                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 0u);
+                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
+                            }
+                            __syncwarp();
+                            mbar_wait(bar_in + 8, use & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 0u);
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
+                                tc_commit(bar_empty + 8 * stage);
+                            }
+                        } else {
+                            mbar_wait(bar_full + 8 * stage, round & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 1u);
+                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc);
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 1u);
+                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
+                                if (last) tc_commit(bar_acc + 8);
+                                tc_commit(bar_empty + 8 * stage);
                             }
                         }
-                        if (leader) tc_commit(bar_empty + 8 * stage);
                         __syncwarp();
                         if (++stage == kStages) { stage = 0; ++round; }
                     }
@@ -756,7 +805,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                                                     : p.stash + (size_t)tile * kStashTile + job.x_ofs;
                     const uint32_t bytes = which == 0 ? job.dy_bytes : job.x_bytes;
                     mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_expect_tx(bar_full + 8 * slot, bytes);
                         bulk_g2s(sbase + slot * kWgBlock, src, bytes, bar_full + 8 * slot);
                     }
@@ -767,9 +816,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
         }
     } else if (warp == 1) {
         {                      // MMA issuer (warp-uniform loop, lane 0 issues)
-            const bool leader = lane == 0;
             uint32_t slot = 0, round = 0;
             const uint32_t idesc = make_idesc_mn(job.xcols);
+            const uint64_t mnhi = desc_hi(128, 2048);
             bool first = true;
             for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
                 const uint32_t s_dy = slot, r_dy = round;
@@ -780,19 +829,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                 mbar_wait(bar_full + 8 * s_x, r_x & 1);
                 tc_fence_after();
                 const uint32_t a_base = sbase + s_dy * kWgBlock, b_base = sbase + s_x * kWgBlock;
-                for (int h = 0; h < job.halves; ++h) {
+                if (elect_one()) {
+                    for (int h = 0; h < job.halves; ++h) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {   // K = 16 points per MMA
-                        const uint64_t ad = make_desc(a_base + h * 32768 + ks * 256, 128, 2048);
-                        const uint64_t bd = make_desc(b_base + ks * 256, 128, 2048);
-                        if (leader) tc_mma(tmem_base + (uint32_t)h * 256u, ad, bd, idesc, (!first || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
+                            tc_mma(tmem_base + (uint32_t)h * 256u, desc_at(mnhi, a_base + h * 32768 + ks * 256),
+                                   desc_at(mnhi, b_base + ks * 256), idesc, (!first || ks > 0) ? 1u : 0u);
                     }
+                    tc_commit(bar_empty + 8 * s_dy);
+                    tc_commit(bar_empty + 8 * s_x);
                 }
                 first = false;
-                if (leader) { tc_commit(bar_empty + 8 * s_dy); tc_commit(bar_empty + 8 * s_x); }
                 __syncwarp();
             }
-            if (leader) tc_commit(bar_done);
+            if (elect_one()) tc_commit(bar_done);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---- bias grads: column sums of the dY image (lanes over points -> conflict-free 16-byte reads) ----
