@@ -32,7 +32,8 @@ constexpr int kSmemAct = 0;
 constexpr int kSmemGx = 2 * kActBytes;                      // 131072
 constexpr int kSmemRing = kSmemGx + 2 * kGxBytes;           // 163840
 constexpr int kSmemBar = kSmemRing + kStages * kStageBytes; // 229376
-constexpr int kSmemBytes = kSmemBar + 256;
+constexpr int kSmemBias = kSmemBar + 256;                   // 2 x 1 KB: per epilogue group, the current layer's bias
+constexpr int kSmemBytes = kSmemBias + 2048;
 constexpr int kThreads = 384;
 constexpr int kNumMmaLayers = 10;               // mlp.0..7, feature, color_fc
 constexpr uint32_t kTmemCols = 512;
@@ -146,6 +147,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// compiler-level dependency: uses of v[] may not be scheduled above this point (placed right after tcgen05.wait::ld)
+__device__ __forceinline__ void pin16(uint32_t (&v)[16]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                      "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
@@ -159,6 +175,12 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// {lo = relu(a), hi = relu(b)} as bf16x2 in one instruction
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -411,59 +433,94 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             stash_store(kStashGx, gx, kGxBytes);
             mbar_arrive(bar_in + 8 * t);
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
+            const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
+            const bool want_dbg = p.dbg != nullptr;
             for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
+                const int N = layer_N(l);
+                // While the MMAs of this layer run: fetch its bias (coalesced, one or two floats per thread) and the first
+                // lane-held slice of the head weights.  Nothing inside the column loop touches global memory.
+                const float b_lo = __ldg(tail + layer_bias_ofs(l) + r);
+                const float b_hi = N == 256 ? __ldg(tail + layer_bias_ofs(l) + 128 + r) : 0.f;
+                float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;      // l==7: w_sigma[32g+lane];  l==9: Wo[ch][32g+lane]
+                if (l == 7) hw0 = __ldg(tail + kWsigOfs + lane);
+                if (l == 9) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
-                stash_guard();
-                const int N = layer_N(l);
-                const float* bias = tail + layer_bias_ofs(l);
+                // group barrier 1: everyone is past the previous layer's reads of sbias; stash stores have read their smem
+                if (do_stash && r == 0) bulk_wait_read0();
+                named_bar_sync(1 + t, 128);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)r), "f"(b_lo) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 512u + 4u * (uint32_t)r), "f"(b_hi) : "memory");
+                named_bar_sync(1 + t, 128);                 // group barrier 2: bias visible
                 const bool relu = l != 8;
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_row + (uint32_t)c0, v);
-                    tc_wait_ld();
-                    float f[32];
+                const bool need_f32 = l == 7 || l == 9 || (want_dbg && l == p.dbg_layer);
+                const bool write_act = l != 9 || do_stash;  // next layer's A operand, in place (l == 9: c, only for the stash)
+                // column loop, 16 accumulator columns at a time, TMEM loads double-buffered one chunk ahead
+                auto process16 = [&](const uint32_t (&v)[16], int c0) {
+                    float f[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 bb;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                                     : "r"(sbias + 4u * (uint32_t)(c0 + j)));
                         f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
                         f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
                     }
-                    if (relu) {
+                    if (need_f32) {
+                        if (relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (l == 7) {          // sigma_out on the fp32 activations (mlps.py:265)
-                        const float* ws = tail + kWsigOfs + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws + j));
-                            sig = fmaf(f[j], w4.x, sig); sig = fmaf(f[j + 1], w4.y, sig);
-                            sig = fmaf(f[j + 2], w4.z, sig); sig = fmaf(f[j + 3], w4.w, sig);
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                         }
-                    }
-                    if (l == 9) {          // color_out on the fp32 color_fc activations (mlps.py:273)
+                        const int src0 = c0 & 16;              // position of this chunk inside the 32-wide lane-held slice
+                        if (l == 7) {                          // sigma_out on the fp32 activations (mlps.py:265)
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            const float* wo = tail + kWoOfs + ch * 128 + c0;
+                            for (int j = 0; j < 16; ++j) sig = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), sig);
+                        }
+                        if (l == 9) {                          // color_out on the fp32 color_fc activations (mlps.py:273)
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wo + j));
-                                rgb[ch] = fmaf(f[j], w4.x, rgb[ch]); rgb[ch] = fmaf(f[j + 1], w4.y, rgb[ch]);
-                                rgb[ch] = fmaf(f[j + 2], w4.z, rgb[ch]); rgb[ch] = fmaf(f[j + 3], w4.w, rgb[ch]);
+                            for (int j = 0; j < 16; ++j) {
+                                rgb[0] = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), rgb[0]);
+                                rgb[1] = fmaf(f[j], __shfl_sync(0xffffffffu, hw1, src0 + j), rgb[1]);
+                                rgb[2] = fmaf(f[j], __shfl_sync(0xffffffffu, hw2, src0 + j), rgb[2]);
                             }
                         }
-                    }
-                    if (p.dbg && l == p.dbg_layer && valid) {
+                        if (want_dbg && l == p.dbg_layer && valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) p.dbg[q * 256 + c0 + j] = f[j];
+                            for (int j = 0; j < 16; ++j) p.dbg[q * 256 + c0 + j] = f[j];
+                        }
                     }
-                    if (l != 9 || do_stash) {   // next layer's A operand, in place (l == 9: c, only for the stash)
+                    if (write_act) {
+                        uint32_t w[8];
+                        if (relu && !need_f32) {
 #pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8)
-                            st_chunk(act, (c0 >> 3) + j8, r, pack_bf16(f[8 * j8], f[8 * j8 + 1]), pack_bf16(f[8 * j8 + 2], f[8 * j8 + 3]),
-                                     pack_bf16(f[8 * j8 + 4], f[8 * j8 + 5]), pack_bf16(f[8 * j8 + 6], f[8 * j8 + 7]));
+                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16_relu(f[2 * j], f[2 * j + 1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+                        }
+                        st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+                        st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
                     }
+                };
+                uint32_t va[16], vb[16];
+                tc_ld16(tmem_row, va);
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    tc_wait_ld();
+                    pin16(va);
+                    tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+                    // next 32-wide slice of the head weights (used from the next iteration on)
+                    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+                    if (l == 7 && c0 + 32 < N) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
+                    if (l == 9 && c0 + 32 < N) {
+                        n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
+                        n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
+                    }
+                    process16(va, c0);
+                    tc_wait_ld();
+                    pin16(vb);
+                    if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
+                    process16(vb, c0 + 16);
+                    hw0 = n0; hw1 = n1; hw2 = n2;
                 }
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
                     if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4);
