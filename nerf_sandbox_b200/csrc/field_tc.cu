@@ -37,6 +37,10 @@ constexpr int kSmemBytes = kSmemBias + 2048;
 constexpr int kThreads = 384;
 constexpr int kNumMmaLayers = 10;               // mlp.0..7, feature, color_fc
 constexpr uint32_t kTmemCols = 512;
+#ifndef NSB_TC_PINGPONG
+#define NSB_TC_PINGPONG 1
+#endif
+constexpr bool kPingPong = NSB_TC_PINGPONG != 0;    // 1: tiles alternate per layer (weights streamed per tile); 0: interleaved per slab
 
 // bf16 image offsets (bytes) of the 10 MMA layers: [K/8][N][8] bf16 each
 __constant__ uint32_t c_layer_ofs[kNumMmaLayers] = {0,      32768,  163840, 294912, 425984,
@@ -310,7 +314,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     const uint32_t bytes = 32u * (uint32_t)layer_N(l) * 2u;
                     const uint8_t* src = p.packed + c_layer_ofs[l];
                     const int ns = layer_nslabs(l);
-                    for (int s = 0; s < ns; ++s) {
+                    // ping-pong: the layer's slabs are streamed once per tile (A, then B)
+                    for (int s2 = 0; s2 < (kPingPong ? 2 * ns : ns); ++s2) {
+                        const int s = s2 >= ns ? s2 - ns : s2;
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
@@ -334,6 +340,34 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     const uint32_t idesc = make_idesc(N);
                     const uint32_t lbo_b = (uint32_t)N * 16u;
                     const int ns = layer_nslabs(l);
+                    if (kPingPong) {
+                        // Tile A's whole layer, then tile B's: while one tile's epilogue drains TMEM (the 64 B/clk tcgen05.ld
+                        // path is as slow as the K=256 MMAs that fill it), the tensor core works on the other tile.
+                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(lbo_b, 128);
+                        for (int t = 0; t < 2; ++t) {
+                            mbar_wait(bar_in + 8 * t, use & 1);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+                            for (int s = 0; s < ns; ++s) {
+                                uint32_t a_addr;
+                                if (l == 0) a_addr = sbase + kSmemGx + t * kGxBytes + (uint32_t)s * 8192u;
+                                else if (l == 4 && s >= 8) a_addr = sbase + kSmemGx + t * kGxBytes + (uint32_t)(s - 8) * 8192u;
+                                else if (l == 9 && s == 8) a_addr = sbase + kSmemGx + t * kGxBytes;
+                                else a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 8192u;
+                                const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
+                                mbar_wait(bar_full + 8 * stage, round & 1);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    tc_mma(d_tmem, desc_at(ahi, a_addr), desc_at(bhi, b_addr), idesc, s > 0 ? 1u : 0u);
+                                    tc_mma(d_tmem, desc_at(ahi, a_addr + 2 * 2048), desc_at(bhi, b_addr + 2 * lbo_b), idesc, 1u);
+                                    if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                                    tc_commit(bar_empty + 8 * stage);
+                                }
+                                __syncwarp();
+                                if (++stage == kStages) { stage = 0; ++round; }
+                            }
+                        }
+                        continue;
+                    }
                     for (int s = 0; s < ns; ++s) {
                         // A-operand source of this K=32 slab
                         uint32_t a_off;   // byte offset inside the tile's act / gx buffer
@@ -630,7 +664,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                 for (int m = 0; m < kNumDgradLayers; ++m) {
                     const uint8_t* src = p.packed + dgrad_layer_ofs(m);
                     const int ns = m == 0 ? 4 : 8;
-                    for (int s = 0; s < ns; ++s) {
+                    for (int s2 = 0; s2 < (kPingPong ? 2 * ns : ns); ++s2) {
+                        const int s = s2 >= ns ? s2 - ns : s2;
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
@@ -649,6 +684,28 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                     const int ns = m == 0 ? 4 : 8;
+                    if (kPingPong) {
+                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
+                        for (int t = 0; t < 2; ++t) {
+                            mbar_wait(bar_in + 8 * t, use & 1);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+                            for (int s = 0; s < ns; ++s) {
+                                const uint32_t a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 8192u;
+                                const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
+                                mbar_wait(bar_full + 8 * stage, round & 1);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    tc_mma(d_tmem, desc_at(ahi, a_addr), desc_at(bhi, b_addr), idesc, s > 0 ? 1u : 0u);
+                                    tc_mma(d_tmem, desc_at(ahi, a_addr + 2 * 2048), desc_at(bhi, b_addr + 2 * 4096), idesc, 1u);
+                                    if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                                    tc_commit(bar_empty + 8 * stage);
+                                }
+                                __syncwarp();
+                                if (++stage == kStages) { stage = 0; ++round; }
+                            }
+                        }
+                        continue;
+                    }
                     for (int s = 0; s < ns; ++s) {
                         const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
                         const uint32_t a0 = sbase + kSmemAct + (uint32_t)s * 4u * 2048u, a1 = a0 + kActBytes;
