@@ -190,6 +190,76 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---- epilogue column loop, specialised per layer kind (branch-free inner loop) ---------------------------
+// KIND 0: bias + ReLU -> bf16 A operand (mlp.0..6)          KIND 1: same + sigma_out head on the fp32 values (mlp.7)
+// KIND 2: bias only (feature)                              KIND 3: bias + ReLU + color_out head (color_fc, N=128);
+//                                                                  writes c to smem only when WRITE (training stash)
+__device__ __forceinline__ void st_chunk(uint32_t base, int k8, int r, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <int KIND, bool WRITE>
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, uint32_t sbias, uint32_t act, int r, float& sig,
+                                            float (&rgb)[3], float hw0, float hw1, float hw2) {
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const float4 bb = lds_f4(sbias + 4u * (uint32_t)(c0 + j));
+        f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+        f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+    }
+    if (KIND == 1 || KIND == 3) {
+        const int src0 = c0 & 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            f[j] = fmaxf(f[j], 0.f);
+            if (KIND == 1) sig = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), sig);
+            if (KIND == 3) {
+                rgb[0] = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), rgb[0]);
+                rgb[1] = fmaf(f[j], __shfl_sync(0xffffffffu, hw1, src0 + j), rgb[1]);
+                rgb[2] = fmaf(f[j], __shfl_sync(0xffffffffu, hw2, src0 + j), rgb[2]);
+            }
+        }
+    }
+    if (WRITE) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = KIND == 0 ? pack_bf16_relu(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
+        st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+        st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+    }
+}
+template <int KIND, bool WRITE>
+__device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, uint32_t act, int r, int lane, const float* __restrict__ tail,
+                                            float& sig, float (&rgb)[3]) {
+    constexpr int N = KIND == 3 ? 128 : 256;
+    float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;          // lane-held 32-wide slice of the head weights
+    if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + lane);
+    if (KIND == 3) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
+    uint32_t va[16], vb[16];
+    tc_ld16(tmem_row, va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        tc_wait_ld();
+        pin16(va);
+        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+        if (KIND == 1 && c0 + 32 < N) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
+        if (KIND == 3 && c0 + 32 < N) {
+            n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
+            n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
+        }
+        epi_chunk16<KIND, WRITE>(va, c0, sbias, act, r, sig, rgb, hw0, hw1, hw2);
+        tc_wait_ld();
+        pin16(vb);
+        if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
+        epi_chunk16<KIND, WRITE>(vb, c0 + 16, sbias, act, r, sig, rgb, hw0, hw1, hw2);
+        hw0 = n0; hw1 = n1; hw2 = n2;
+    }
+}
+
 // ---- kernel parameters --------------------------------------------------------------------------------
 struct FwdParams {
     const float* rays_o; const float* rays_d; const float* z; const float* ray_norm; const float* viewdirs;   // FROM_ENC=false
@@ -536,6 +606,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                         st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
                     }
                 };
+                if (!(want_dbg && l == p.dbg_layer)) {
+                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                    else if (do_stash) epi_columns<3, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                } else {
                 uint32_t va[16], vb[16];
                 tc_ld16(tmem_row, va);
                 for (int c0 = 0; c0 < N; c0 += 32) {
@@ -555,6 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
                     process16(vb, c0 + 16);
                     hw0 = n0; hw1 = n1; hw2 = n2;
+                }
                 }
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
                     if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4);
