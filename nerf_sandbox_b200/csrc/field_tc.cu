@@ -710,6 +710,68 @@ __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterp
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// dgrad epilogue column loop.  KIND 0: plain (feature is linear)   1: + d_sigma * w_sigma, then ReLU mask   2: ReLU mask
+// The mask is the stashed bf16 activation image itself: a half-word is non-zero iff the activation was > 0.
+template <int KIND>
+__device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, const uint4& ma,
+                                              const uint4& mb) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+        if (KIND == 1) {
+            a = fmaf(dsig, __shfl_sync(0xffffffffu, hw0, (c0 & 16) + 2 * j), a);
+            b = fmaf(dsig, __shfl_sync(0xffffffffu, hw0, (c0 & 16) + 2 * j + 1), b);
+        }
+        w[j] = pack_bf16(a, b);
+    }
+    if (KIND != 0) {
+        w[0] &= __vcmpne2(ma.x, 0u); w[1] &= __vcmpne2(ma.y, 0u); w[2] &= __vcmpne2(ma.z, 0u); w[3] &= __vcmpne2(ma.w, 0u);
+        w[4] &= __vcmpne2(mb.x, 0u); w[5] &= __vcmpne2(mb.y, 0u); w[6] &= __vcmpne2(mb.z, 0u); w[7] &= __vcmpne2(mb.w, 0u);
+    }
+    st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+    st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+}
+template <int KIND>
+__device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, int r, int lane, const float* __restrict__ tail,
+                                              const uint8_t* __restrict__ mask_row, float dsig) {
+    float hw0 = KIND == 1 ? __ldg(tail + kWsigOfs + lane) : 0.f;
+    uint4 cur[4], nxt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cur[j] = make_uint4(0, 0, 0, 0); nxt[j] = make_uint4(0, 0, 0, 0); }
+    if (KIND != 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = ldg16(mask_row + (size_t)j * 2048);
+    }
+    uint32_t va[16], vb[16];
+    tc_ld16(tmem_row, va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        tc_wait_ld();
+        pin16(va);
+        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+        float n0 = 0.f;
+        if (c0 + 32 < 256) {
+            if (KIND != 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nxt[j] = ldg16(mask_row + (size_t)(((c0 + 32) >> 3) + j) * 2048);
+            }
+            if (KIND == 1) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
+        }
+        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, cur[0], cur[1]);
+        tc_wait_ld();
+        pin16(vb);
+        if (c0 + 32 < 256) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
+        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, cur[2], cur[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        hw0 = n0;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -846,65 +908,51 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             };
             guard();
             // ---- prologue: d_raw -> dY_9 = (d_rgb . Wo) * (c > 0)   (color_out dgrad + color_fc ReLU mask) ----
-            float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-            for (int c8 = 0; c8 < 16; ++c8) {
-                const uint4 cm = ldg16(st_tile + kStashC + (size_t)c8 * 2048 + (size_t)r * 16);
-                const uint32_t cw[4] = {cm.x, cm.y, cm.z, cm.w};
-                float o[8];
+            const float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r == 0 && tile_ok) l2_prefetch(st_tile + kStashH + 7 * 65536, 65536);      // h8: mask of the m=1 epilogue
+            {
+                const uint8_t* crow = st_tile + kStashC + (size_t)r * 16;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint4 cm[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = c8 * 8 + j;
-                    const float g = d.x * __ldg(tail + kWoOfs + col) + d.y * __ldg(tail + kWoOfs + 128 + col) + d.z * __ldg(tail + kWoOfs + 256 + col);
-                    const float cv = (j & 1) ? bf16hi(cw[j >> 1]) : bf16lo(cw[j >> 1]);
-                    o[j] = cv > 0.f ? g : 0.f;
+                    for (int j = 0; j < 8; ++j) cm[j] = ldg16(crow + (size_t)(half * 8 + j) * 2048);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {                     // 32 columns per lane-held slice of Wo
+                        const int col0 = half * 64 + g * 32;
+                        const float w0 = __ldg(tail + kWoOfs + col0 + lane), w1 = __ldg(tail + kWoOfs + 128 + col0 + lane),
+                                    w2 = __ldg(tail + kWoOfs + 256 + col0 + lane);
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j2 = 0; j2 < 4; ++j2) {
+                                const int s0 = c8 * 8 + 2 * j2;
+                                const float ga = d.x * __shfl_sync(0xffffffffu, w0, s0) + d.y * __shfl_sync(0xffffffffu, w1, s0) +
+                                                 d.z * __shfl_sync(0xffffffffu, w2, s0);
+                                const float gb = d.x * __shfl_sync(0xffffffffu, w0, s0 + 1) + d.y * __shfl_sync(0xffffffffu, w1, s0 + 1) +
+                                                 d.z * __shfl_sync(0xffffffffu, w2, s0 + 1);
+                                w[j2] = pack_bf16(ga, gb);
+                            }
+                            const uint4 mk = cm[g * 4 + c8];
+                            st_chunk(act, half * 8 + g * 4 + c8, r, w[0] & __vcmpne2(mk.x, 0u), w[1] & __vcmpne2(mk.y, 0u),
+                                     w[2] & __vcmpne2(mk.z, 0u), w[3] & __vcmpne2(mk.w, 0u));
+                        }
+                    }
                 }
-                st_chunk(act, c8, r, pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
             }
             store(dstash_ofs(9), 32768);
             mbar_arrive(bar_in + 8 * t);
             for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
+                // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (stash slot 8-m)
+                const uint8_t* mask_row = st_tile + kStashH + (size_t)(m >= 1 ? 8 - m : 0) * 65536 + (size_t)r * 16;
+                if (r == 0 && tile_ok && m <= 7) l2_prefetch(st_tile + kStashH + (size_t)(7 - m) * 65536, 65536);   // next layer's mask
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
                 guard();
-                // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (stash slot 8-m)
-                const uint8_t* mask = m >= 1 ? st_tile + kStashH + (size_t)(8 - m) * 65536 : nullptr;
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_row + (uint32_t)c0, v);
-                    uint4 mk[4];
-                    if (mask) {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) mk[j8] = ldg16(mask + (size_t)((c0 >> 3) + j8) * 2048 + (size_t)r * 16);
-                    }
-                    tc_wait_ld();
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (m == 1) {          // + d_sigma_raw * w_sigma  (sigma_out dgrad joins d(h8) here)
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + kWsigOfs + c0 + j));
-                            f[j] = fmaf(d.w, w4.x, f[j]); f[j + 1] = fmaf(d.w, w4.y, f[j + 1]);
-                            f[j + 2] = fmaf(d.w, w4.z, f[j + 2]); f[j + 3] = fmaf(d.w, w4.w, f[j + 3]);
-                        }
-                    }
-                    if (mask) {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            const uint32_t w[4] = {mk[j8].x, mk[j8].y, mk[j8].z, mk[j8].w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float hv = (j & 1) ? bf16hi(w[j >> 1]) : bf16lo(w[j >> 1]);
-                                if (!(hv > 0.f)) f[8 * j8 + j] = 0.f;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8)
-                        st_chunk(act, (c0 >> 3) + j8, r, pack_bf16(f[8 * j8], f[8 * j8 + 1]), pack_bf16(f[8 * j8 + 2], f[8 * j8 + 3]),
-                                 pack_bf16(f[8 * j8 + 4], f[8 * j8 + 5]), pack_bf16(f[8 * j8 + 6], f[8 * j8 + 7]));
-                }
+                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mask_row, d.w);
+                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mask_row, d.w);
+                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mask_row, d.w);
                 store(dstash_ofs(8 - m), kActBytes);
                 tc_fence_before();
                 if (m != kNumDgradLayers - 1) mbar_arrive(bar_in + 8 * t);
