@@ -120,8 +120,9 @@ int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_
 /* Packed weights of one NeRF: fp32 padded rows for the FFMA path and a bf16 image in tcgen05 operand
  * layout for the tensor path.  Sizes in bytes. */
 size_t nsb_packed_weights_bytes(void);
-/* params: flat fp32 [NSB_N_PARAMS] in state_dict order -> packed (call after every optimiser step). */
-int nsb_pack_weights(const float* params, void* packed, void* stream);
+/* params: flat fp32 [NSB_N_PARAMS] in state_dict order -> packed (call after every optimiser step).
+ * mode selects which section is refreshed: NSB_MODE_FP32, NSB_MODE_BF16, or -1 for both. */
+int nsb_pack_weights(const float* params, void* packed, int mode, void* stream);
 
 /* Workspace for one pass over Q = B*N points.  stash != 0 keeps what the backward needs. */
 size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash);

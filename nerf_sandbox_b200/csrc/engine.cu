@@ -72,10 +72,11 @@ extern "C" const char* nsb_last_cuda_error(void) { return g_cuda_err; }
 extern "C" int64_t nsb_launch_count(void) { return g_launches; }
 
 extern "C" size_t nsb_packed_weights_bytes(void) { return packed_layout().total; }
-extern "C" int nsb_pack_weights(const float* params, void* packed, void* stream) {
-    if (!params || !packed) return NSB_E_BADARG;
-    NSB_TRY(pack_fp32(params, packed, as_stream(stream)));
-    return tc_pack(params, reinterpret_cast<char*>(packed) + packed_layout().bf16_off, as_stream(stream));
+extern "C" int nsb_pack_weights(const float* params, void* packed, int mode, void* stream) {
+    if (!params || !packed || mode < -1 || mode > NSB_MODE_BF16) return NSB_E_BADARG;
+    if (mode != NSB_MODE_BF16) NSB_TRY(pack_fp32(params, packed, as_stream(stream)));
+    if (mode != NSB_MODE_FP32) NSB_TRY(tc_pack(params, reinterpret_cast<char*>(packed) + packed_layout().bf16_off, as_stream(stream)));
+    return NSB_OK;
 }
 
 extern "C" size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash) { return field_ws(Q, mode, stash); }

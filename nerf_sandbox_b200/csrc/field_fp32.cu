@@ -385,14 +385,18 @@ head_bwd_kernel(const float* __restrict__ d_raw, const float* __restrict__ C, co
 // ---------------------------------------------------------------------------------------------------
 // weight packing (fp32 section): flat state_dict order -> rows padded to Kpad, zero filled
 // ---------------------------------------------------------------------------------------------------
-__global__ void pack_fp32_kernel(const float* __restrict__ params, float* __restrict__ dstw, float* __restrict__ dstb,
-                                 int N, int K, int Kpad, int64_t w_off, int64_t b_off) {
-    const int total = N * Kpad;
+struct PackFp32Args { size_t w[12], b[12]; };
+__global__ void pack_fp32_kernel(const float* __restrict__ params, char* __restrict__ base, PackFp32Args a) {
+    const int l = blockIdx.y;
+    const LayerDesc d = layer_desc(l);
+    float* dstw = reinterpret_cast<float*>(base + a.w[l]);
+    float* dstb = reinterpret_cast<float*>(base + a.b[l]);
+    const int total = d.N * d.Kpad;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int n = idx / Kpad, k = idx % Kpad;
-        dstw[idx] = k < K ? params[w_off + (int64_t)n * K + k] : 0.f;
+        const int n = idx / d.Kpad, k = idx % d.Kpad;
+        dstw[idx] = k < d.K ? params[d.w_off + (int64_t)n * d.K + k] : 0.f;
     }
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) dstb[n] = params[b_off + n];
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x) dstb[n] = params[d.b_off + n];
 }
 
 PackedLayout packed_layout() {
@@ -411,15 +415,10 @@ PackedLayout packed_layout() {
 
 int pack_fp32(const float* params, void* packed, cudaStream_t st) {
     const PackedLayout L = packed_layout();
-    char* base = reinterpret_cast<char*>(packed);
-    for (int l = 0; l < 12; ++l) {
-        const LayerDesc d = layer_desc(l);
-        const int total = d.N * d.Kpad;
-        pack_fp32_kernel<<<(total + 255) / 256, 256, 0, st>>>(params, reinterpret_cast<float*>(base + L.f32_w[l]),
-                                                            reinterpret_cast<float*>(base + L.f32_b[l]), d.N, d.K, d.Kpad,
-                                                            d.w_off, d.b_off);
-        NSB_LAUNCH_CHECK("pack_fp32_kernel");
-    }
+    PackFp32Args a;
+    for (int l = 0; l < 12; ++l) { a.w[l] = L.f32_w[l]; a.b[l] = L.f32_b[l]; }
+    pack_fp32_kernel<<<dim3(32, 12), 256, 0, st>>>(params, reinterpret_cast<char*>(packed), a);
+    NSB_LAUNCH_CHECK("pack_fp32_kernel");
     return NSB_OK;
 }
 

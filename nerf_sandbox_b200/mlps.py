@@ -150,7 +150,7 @@ class NeRF(nn.Module):
             self._packed_version = -1
         version = sum(p._version for p in self.ordered_params())     # in-place updates (optimizer, load_state_dict)
         if force or self._packed_version != version:
-            _lib.check(L.nsb_pack_weights(_lib.ptr(flat), _lib.ptr(self._packed), _lib.stream()), "nsb_pack_weights")
+            _lib.check(L.nsb_pack_weights(_lib.ptr(flat), _lib.ptr(self._packed), self.mode, _lib.stream()), "nsb_pack_weights")
             self._packed_version = version
         return self._packed
 

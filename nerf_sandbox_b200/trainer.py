@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .dist import allreduce_grads
 from .encoders import get_vanilla_nerf_encoders
 from .mlps import NeRF
 
@@ -70,7 +71,8 @@ class VanillaTrainer:
             m.to(self.device)
         n = _lib.N_PARAMS
         z = lambda: torch.zeros(n, device=self.device, dtype=torch.float32)
-        self.grads_c, self.grads_f = z(), z()
+        self.grads_all = torch.zeros(2 * n, device=self.device, dtype=torch.float32)   # one buffer -> one all-reduce
+        self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self.m_c, self.v_c, self.m_f, self.v_f = z(), z(), z(), z()
         self.scalars = torch.zeros(4, device=self.device, dtype=torch.float32)
         self._ws = None
@@ -119,13 +121,8 @@ class VanillaTrainer:
     def step(self, batch, draws=None):
         """forward + backward (+ all-reduce) + Adam + re-pack.  Returns the device scalars tensor
         [loss, psnr, mse_c, mse_f] of this rank's shard (no host sync)."""
-        world = 1
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.pg)
         self._fwd_bwd(batch, draws, grad_scale=1.0)
-        if world > 1:                                        # one sum-allreduce per net on the flat fp32 buffers
-            torch.distributed.all_reduce(self.grads_c, group=self.pg)
-            torch.distributed.all_reduce(self.grads_f, group=self.pg)
+        world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
         self.adam_t += 1
         self.global_step += 1
         L = _lib.lib()
