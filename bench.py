@@ -69,7 +69,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -200,10 +200,10 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ("value") --------------------------------------------------------------
+    clk = ClockSampler(local) if rank == 0 else None      # samples through warm-up + both timed regions (all under load)
     for i in range(W_):
         tr.step(devb[i % pool_n])
     barrier()
-    clk = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -212,8 +212,7 @@ def main():
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - l0 + (2 * K if world > 1 else 0)
-    clocks = clk.stop() if clk else None
+    launches = _lib.launch_count() - l0 + (K if world > 1 else 0)      # + one NCCL all-reduce kernel per step
     loss_dev = float(tr.scalars[0])
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------------------
@@ -231,6 +230,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clocks = clk.stop() if clk else None
 
     # ---- roofline of the dominant kernel family (encoder+MLP fwd+bwd of the fine pass), timed alone ------
     L = _lib.lib()
