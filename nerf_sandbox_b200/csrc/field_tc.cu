@@ -195,6 +195,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // KIND 2: bias only (feature)                              KIND 3: bias + ReLU + color_out head (color_fc, N=128);
 //                                                                  writes c to smem only when WRITE (training stash)
 __device__ __forceinline__ void st_chunk(uint32_t base, int k8, int r, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
+__device__ __forceinline__ void st_chunk_g(uint8_t* grow, int k8, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -202,7 +203,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 template <int KIND, bool WRITE>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, uint32_t sbias, uint32_t act, int r, float& sig,
-                                            float (&rgb)[3], float hw0, float hw1, float hw2) {
+                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow) {
     float f[16];
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -223,17 +224,21 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, uin
             }
         }
     }
-    if (WRITE) {
+    if (WRITE || grow) {
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = KIND == 0 ? pack_bf16_relu(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
-        st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
-        st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+        if (WRITE) {
+            st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+            st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+        }
+        st_chunk_g(grow, (c0 >> 3), w[0], w[1], w[2], w[3]);
+        st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
     }
 }
 template <int KIND, bool WRITE>
 __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                            float& sig, float (&rgb)[3]) {
+                                            float& sig, float (&rgb)[3], uint8_t* grow) {
     constexpr int N = KIND == 3 ? 128 : 256;
     float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;          // lane-held 32-wide slice of the head weights
     if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + lane);
@@ -251,11 +256,11 @@ __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, u
             n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
             n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
         }
-        epi_chunk16<KIND, WRITE>(va, c0, sbias, act, r, sig, rgb, hw0, hw1, hw2);
+        epi_chunk16<KIND, WRITE>(va, c0, sbias, act, r, sig, rgb, hw0, hw1, hw2, grow);
         tc_wait_ld();
         pin16(vb);
         if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
-        epi_chunk16<KIND, WRITE>(vb, c0 + 16, sbias, act, r, sig, rgb, hw0, hw1, hw2);
+        epi_chunk16<KIND, WRITE>(vb, c0 + 16, sbias, act, r, sig, rgb, hw0, hw1, hw2, grow);
         hw0 = n0; hw1 = n1; hw2 = n2;
     }
 }
@@ -293,8 +298,14 @@ __device__ __forceinline__ void st_chunk(uint32_t base, int k8, int r, uint32_t 
                  : "memory");
 }
 
+// the same 16-byte row chunk straight to the (d)stash image in global memory: per warp 32 rows x 16 B = 512 contiguous
+// bytes per chunk -> fully coalesced 128-bit stores, no smem read-back, no barrier
+__device__ __forceinline__ void st_chunk_g(uint8_t* grow, int k8, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (grow) *reinterpret_cast<uint4*>(grow + (size_t)k8 * 2048) = make_uint4(a, b, c, d);
+}
+
 // gamma(x) of this thread's point -> gx buffer (K=64: [x(3) | sin(2^k x_d) k-major (30) | cos (30) | 0])
-__device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float py, float pz) {
+__device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float py, float pz, uint8_t* grow) {
     float e[64];
     e[0] = px; e[1] = py; e[2] = pz; e[63] = 0.f;
     float s[3], c[3];
@@ -309,12 +320,15 @@ __device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float p
         }
     }
 #pragma unroll
-    for (int k8 = 0; k8 < 8; ++k8)
-        st_chunk(gx, k8, r, pack_bf16(e[8 * k8], e[8 * k8 + 1]), pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
-                 pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]));
+    for (int k8 = 0; k8 < 8; ++k8) {
+        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
+    }
 }
 // gamma(d) -> first 4 K-chunks of the gx buffer (K=32: [v(3) | sin (12) | cos (12) | 0 x5])
-__device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float vy, float vz) {
+__device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float vy, float vz, uint8_t* grow) {
     float e[32];
 #pragma unroll
     for (int i = 27; i < 32; ++i) e[i] = 0.f;
@@ -331,17 +345,22 @@ __device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float v
         }
     }
 #pragma unroll
-    for (int k8 = 0; k8 < 4; ++k8)
-        st_chunk(gx, k8, r, pack_bf16(e[8 * k8], e[8 * k8 + 1]), pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
-                 pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]));
+    for (int k8 = 0; k8 < 4; ++k8) {
+        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
+    }
 }
 // materialised encodings (NeRF.forward boundary): copy a row of `n` floats, zero-padded to 8*chunks
-__device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __restrict__ src, int n, int chunks) {
+__device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __restrict__ src, int n, int chunks, uint8_t* grow) {
     for (int k8 = 0; k8 < chunks; ++k8) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (8 * k8 + j < n && src) ? src[8 * k8 + j] : 0.f;
-        st_chunk(gx, k8, r, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
     }
 }
 
@@ -505,21 +524,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             // training stash: bulk-store shared-memory images of the layer inputs (TMA engine, one elected thread)
             const bool do_stash = p.stash != nullptr;
             uint8_t* stash_tile = do_stash && tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
-            auto stash_guard = [&]() {       // earlier bulk stores must have finished READING smem before we overwrite it
-                if (do_stash) { if (r == 0) bulk_wait_read0(); named_bar_sync(1 + t, 128); }
-            };
-            auto stash_store = [&](size_t ofs, uint32_t src, uint32_t bytes) {
-                if (do_stash) {
-                    fence_async_smem();
-                    named_bar_sync(1 + t, 128);
-                    if (r == 0 && stash_tile) { bulk_s2g(stash_tile + ofs, src, bytes); bulk_commit(); }
-                }
-            };
-            stash_guard();
+            // row pointer into a stash block (or null): every 16-byte chunk written to smem is mirrored there
+            auto srow = [&](size_t ofs) -> uint8_t* { return stash_tile ? stash_tile + ofs + (size_t)r * 16 : nullptr; };
             // ---- layer-0 input: gamma(x) ----
             float vdir[3] = {0.f, 0.f, 1.f};
             if (FROM_ENC) {
-                copy_enc_row(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8);
+                copy_enc_row(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8, srow(kStashGx));
             } else {
                 const int64_t b = qc / p.N;
                 const float zz = valid ? p.z[qc] : 0.f;
@@ -527,14 +537,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 const float px = fmaf(p.rays_d[b * 3 + 0], zm, p.rays_o[b * 3 + 0]);
                 const float py = fmaf(p.rays_d[b * 3 + 1], zm, p.rays_o[b * 3 + 1]);
                 const float pz = fmaf(p.rays_d[b * 3 + 2], zm, p.rays_o[b * 3 + 2]);
-                encode_pos(gx, r, px, py, pz);
+                encode_pos(gx, r, px, py, pz, srow(kStashGx));
                 const float* vs = p.viewdirs ? p.viewdirs : p.rays_d;
                 const float vx = vs[b * 3 + 0], vy = vs[b * 3 + 1], vz = vs[b * 3 + 2];
                 const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
                 vdir[0] = vx * inv; vdir[1] = vy * inv; vdir[2] = vz * inv;
             }
             fence_async_smem();
-            stash_store(kStashGx, gx, kGxBytes);
             mbar_arrive(bar_in + 8 * t);
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
             const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
@@ -550,15 +559,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 if (l == 9) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
-                // group barrier 1: everyone is past the previous layer's reads of sbias; stash stores have read their smem
-                if (do_stash && r == 0) bulk_wait_read0();
+                // group barrier 1: everyone is past the previous layer's reads of sbias
                 named_bar_sync(1 + t, 128);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)r), "f"(b_lo) : "memory");
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 512u + 4u * (uint32_t)r), "f"(b_hi) : "memory");
                 named_bar_sync(1 + t, 128);                 // group barrier 2: bias visible
                 const bool relu = l != 8;
                 const bool need_f32 = l == 7 || l == 9 || (want_dbg && l == p.dbg_layer);
-                const bool write_act = l != 9 || do_stash;  // next layer's A operand, in place (l == 9: c, only for the stash)
+                const bool write_act = l != 9;              // next layer's A operand, in place
+                uint8_t* grow = l <= 7 ? srow(kStashH + (size_t)l * 65536) : (l == 8 ? srow(kStashFeat) : srow(kStashC));
                 // column loop, 16 accumulator columns at a time, TMEM loads double-buffered one chunk ahead
                 auto process16 = [&](const uint32_t (&v)[16], int c0) {
                     float f[16];
@@ -607,11 +616,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     }
                 };
                 if (!(want_dbg && l == p.dbg_layer)) {
-                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
-                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
-                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
-                    else if (do_stash) epi_columns<3, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
-                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb);
+                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
                 } else {
                 uint32_t va[16], vb[16];
                 tc_ld16(tmem_row, va);
@@ -635,12 +643,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 }
                 }
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
-                    if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4);
-                    else encode_dir(gx, r, vdir[0], vdir[1], vdir[2]);
+                    if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
+                    else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
                 }
-                if (l <= 7) stash_store(kStashH + (size_t)l * 65536, act, kActBytes);
-                else if (l == 8) { stash_store(kStashFeat, act, kActBytes); stash_store(kStashGd, gx, 8192); }
-                else stash_store(kStashC, act, 32768);
                 if (l != 9) {
                     tc_fence_before();
                     fence_async_smem();
@@ -653,7 +658,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             }
             tc_fence_before();   // the next pair's first MMA overwrites this accumulator: order our tcgen05.ld before it
         }
-        if (p.stash && r == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -717,7 +721,7 @@ __device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
 // The mask is the stashed bf16 activation image itself: a half-word is non-zero iff the activation was > 0.
 template <int KIND>
 __device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, const uint4& ma,
-                                              const uint4& mb) {
+                                              const uint4& mb, uint8_t* grow) {
     uint32_t w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -734,10 +738,12 @@ __device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, u
     }
     st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
     st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+    st_chunk_g(grow, (c0 >> 3), w[0], w[1], w[2], w[3]);
+    st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
 }
 template <int KIND>
 __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                              const uint8_t* __restrict__ mask_row, float dsig) {
+                                              const uint8_t* __restrict__ mask_row, float dsig, uint8_t* grow) {
     float hw0 = KIND == 1 ? __ldg(tail + kWsigOfs + lane) : 0.f;
     uint4 cur[4], nxt[4];
 #pragma unroll
@@ -761,11 +767,11 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
             }
             if (KIND == 1) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
         }
-        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, cur[0], cur[1]);
+        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, cur[0], cur[1], grow);
         tc_wait_ld();
         pin16(vb);
         if (c0 + 32 < 256) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
-        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, cur[2], cur[3]);
+        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, cur[2], cur[3], grow);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
         hw0 = n0;
@@ -900,13 +906,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             const bool valid = tile_ok && q < p.Q;
             const uint8_t* st_tile = p.stash + (size_t)(tile_ok ? tile : 0) * kStashTile;
             uint8_t* ds_tile = tile_ok ? p.dstash + (size_t)tile * kDstashTile : nullptr;
-            auto guard = [&]() { if (r == 0) bulk_wait_read0(); named_bar_sync(1 + t, 128); };
-            auto store = [&](size_t ofs, uint32_t bytes) {
-                fence_async_smem();
-                named_bar_sync(1 + t, 128);
-                if (r == 0 && ds_tile) { bulk_s2g(ds_tile + ofs, act, bytes); bulk_commit(); }
-            };
-            guard();
+            auto drow = [&](size_t ofs) -> uint8_t* { return ds_tile ? ds_tile + ofs + (size_t)r * 16 : nullptr; };
             // ---- prologue: d_raw -> dY_9 = (d_rgb . Wo) * (c > 0)   (color_out dgrad + color_fc ReLU mask) ----
             const float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (r == 0 && tile_ok) l2_prefetch(st_tile + kStashH + 7 * 65536, 65536);      // h8: mask of the m=1 epilogue
@@ -935,13 +935,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                                 w[j2] = pack_bf16(ga, gb);
                             }
                             const uint4 mk = cm[g * 4 + c8];
-                            st_chunk(act, half * 8 + g * 4 + c8, r, w[0] & __vcmpne2(mk.x, 0u), w[1] & __vcmpne2(mk.y, 0u),
-                                     w[2] & __vcmpne2(mk.z, 0u), w[3] & __vcmpne2(mk.w, 0u));
+                            w[0] &= __vcmpne2(mk.x, 0u); w[1] &= __vcmpne2(mk.y, 0u); w[2] &= __vcmpne2(mk.z, 0u); w[3] &= __vcmpne2(mk.w, 0u);
+                            st_chunk(act, half * 8 + g * 4 + c8, r, w[0], w[1], w[2], w[3]);
+                            st_chunk_g(drow(dstash_ofs(9)), half * 8 + g * 4 + c8, w[0], w[1], w[2], w[3]);
                         }
                     }
                 }
             }
-            store(dstash_ofs(9), 32768);
+            fence_async_smem();
             mbar_arrive(bar_in + 8 * t);
             for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                 // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (stash slot 8-m)
@@ -949,16 +950,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                 if (r == 0 && tile_ok && m <= 7) l2_prefetch(st_tile + kStashH + (size_t)(7 - m) * 65536, 65536);   // next layer's mask
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
-                guard();
-                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mask_row, d.w);
-                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mask_row, d.w);
-                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mask_row, d.w);
-                store(dstash_ofs(8 - m), kActBytes);
+                uint8_t* grow = drow(dstash_ofs(8 - m));
+                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
+                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
+                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
                 tc_fence_before();
+                fence_async_smem();
                 if (m != kNumDgradLayers - 1) mbar_arrive(bar_in + 8 * t);
             }
         }
-        if (r == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
