@@ -216,16 +216,19 @@ def main():
     loss_dev = float(tr.scalars[0])
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------------------
-    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+    # one pinned host buffer per batch, [o | d | norm | viewdir | rgb] field-major, so a step is ONE H2D copy
+    keys = ("rays_o_marching", "rays_d_marching_unit", "rays_d_marching_norm", "rays_d_world_unit", "rgb")
+    hpack = [torch.cat([b[k].reshape(-1) for k in keys]).pin_memory() for b in host]
+    dpack = torch.empty_like(hpack[0], device=dev)
+    offs = np.cumsum([0] + [host[0][k].numel() for k in keys])
+    stage = {k: dpack[offs[i]:offs[i + 1]].view(host[0][k].shape) for i, k in enumerate(keys)}
     for i in range(3):
-        for k in stage:
-            stage[k].copy_(host[i % pool_n][k], non_blocking=True)
+        dpack.copy_(hpack[i % pool_n], non_blocking=True)
         tr.step(stage); tr.scalars.cpu()
     barrier()
     e0.record()
     for i in range(K):
-        for k in stage:
-            stage[k].copy_(host[i % pool_n][k], non_blocking=True)
+        dpack.copy_(hpack[i % pool_n], non_blocking=True)
         loss_host = tr.step(stage).cpu()
     e1.record()
     barrier()

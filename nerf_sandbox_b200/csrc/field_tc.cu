@@ -202,14 +202,13 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return v;
 }
 template <int KIND, bool WRITE>
-__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, uint32_t sbias, uint32_t act, int r, float& sig,
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, const float4 (&bias)[4], uint32_t act, int r, float& sig,
                                             float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow) {
     float f[16];
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-        const float4 bb = lds_f4(sbias + 4u * (uint32_t)(c0 + j));
-        f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
-        f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+    for (int j = 0; j < 4; ++j) {
+        f[4 * j] = __uint_as_float(v[4 * j]) + bias[j].x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bias[j].y;
+        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bias[j].z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bias[j].w;
     }
     if (KIND == 1 || KIND == 3) {
         const int src0 = c0 & 16;
@@ -247,20 +246,24 @@ __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, u
     tc_ld16(tmem_row, va);
 #pragma unroll 1
     for (int c0 = 0; c0 < N; c0 += 32) {
-        tc_wait_ld();
-        pin16(va);
-        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+        // bias of these 32 columns: issued BEFORE the TMEM wait so the shared-memory latency hides behind it
+        float4 ba[4], bb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ba[j] = lds_f4(sbias + 4u * (uint32_t)(c0 + 4 * j)); bb[j] = lds_f4(sbias + 4u * (uint32_t)(c0 + 16 + 4 * j)); }
         float n0 = 0.f, n1 = 0.f, n2 = 0.f;
         if (KIND == 1 && c0 + 32 < N) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
         if (KIND == 3 && c0 + 32 < N) {
             n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
             n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
         }
-        epi_chunk16<KIND, WRITE>(va, c0, sbias, act, r, sig, rgb, hw0, hw1, hw2, grow);
+        tc_wait_ld();
+        pin16(va);
+        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow);
         tc_wait_ld();
         pin16(vb);
         if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
-        epi_chunk16<KIND, WRITE>(vb, c0 + 16, sbias, act, r, sig, rgb, hw0, hw1, hw2, grow);
+        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow);
         hw0 = n0; hw1 = n1; hw2 = n2;
     }
 }
