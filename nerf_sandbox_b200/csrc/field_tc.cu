@@ -106,6 +106,12 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
+// wait and add the waited cycles to `acc` (profiling aid; acc may be ignored by the optimiser when cyc == null)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 // one lane of a converged warp (ptxas then knows a single thread issues and drops the per-lane waterfall)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -276,6 +282,7 @@ struct FwdParams {
     float* raw;                   // [Q,4]
     uint8_t* stash;               // training: per tile, images of the layer inputs (see StashLayout); else null
     float* dbg; int dbg_layer;    // debug: post-activation fp32 of one layer, [Q,256]
+    unsigned long long* cyc;      // debug: per-role wait/busy cycle counters of CTA 0 (16 x u64), or null
     int64_t Q; int N;             // points, samples per ray
     int64_t num_tiles;
 };
@@ -401,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         // (whole warp runs the uniform control flow; one lane issues -- keeps operands in uniform registers)
         {
             uint32_t stage = 0, round = 0;
+            long long w_empty = 0; const long long t_begin = clock64();
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const uint32_t bytes = 32u * (uint32_t)layer_N(l) * 2u;
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     // ping-pong: the layer's slabs are streamed once per tile (A, then B)
                     for (int s2 = 0; s2 < (kPingPong ? 2 * ns : ns); ++s2) {
                         const int s = s2 >= ns ? s2 - ns : s2;
-                        mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
+                        mbar_wait_t(bar_empty + 8 * stage, (round & 1) ^ 1, w_empty);
                         if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
                             bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * bytes, bytes, bar_full + 8 * stage);
@@ -419,97 +427,55 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     }
                 }
             }
+            if (p.cyc && blockIdx.x == 0 && lane == 0) { p.cyc[0] = (unsigned long long)w_empty; p.cyc[1] = (unsigned long long)(clock64() - t_begin); }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ========================================
-        // The whole warp executes the loop (warp-uniform values -> uniform registers, no per-lane waterfall around
-        // the tcgen05 instructions); lane 0 issues.
-        {
-            uint32_t stage = 0, round = 0, use = 0;   // use = how many layers both tiles went through (barrier parity)
+        // ONE elected thread runs the whole issue loop (elect.sync tells ptxas a single lane is live, so tcgen05 operands go
+        // to uniform registers without per-lane waterfalls and there is no per-slab warp re-convergence).
+        // Schedule: tile A's whole layer, then tile B's -- while one tile's epilogue drains TMEM the tensor core works on
+        // the other tile; the layer's weight slabs are streamed once per tile.
+        if (elect_one()) {
+            uint32_t stage = 0, round = 0, use = 0;   // use = layers completed (parity of in_ready / acc_full)
+            long long w_in = 0, w_full = 0; const long long t_begin = clock64();
+            const uint64_t ahi = desc_hi(2048, 128);
+            const uint32_t ring_lo = (sbase + kSmemRing) >> 4;
+            // issue `n` K=32 slabs whose A operand starts at a_lo (descriptor address units of 16 B) into accumulator d_tmem
+            auto issue = [&](uint32_t a_lo, int n, bool first_overwrites, uint32_t d_tmem, uint64_t bhi, uint32_t b_step, uint32_t idesc,
+                             uint32_t acc_bar) {
+                for (int s = 0; s < n; ++s, a_lo += 512u) {
+                    if (p.cyc) mbar_wait_t(bar_full + 8 * stage, round & 1, w_full); else mbar_wait(bar_full + 8 * stage, round & 1);
+                    tc_fence_after();
+                    const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
+                    tc_mma(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, (first_overwrites && s == 0) ? 0u : 1u);
+                    tc_mma(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + b_step), idesc, 1u);
+                    if (acc_bar && s == n - 1) tc_commit(acc_bar);
+                    tc_commit(bar_empty + 8 * stage);
+                    if (++stage == kStages) { stage = 0; ++round; }
+                }
+            };
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
                     const int N = layer_N(l);
                     const uint32_t idesc = make_idesc(N);
                     const uint32_t lbo_b = (uint32_t)N * 16u;
-                    const int ns = layer_nslabs(l);
-                    if (kPingPong) {
-                        // Tile A's whole layer, then tile B's: while one tile's epilogue drains TMEM (the 64 B/clk tcgen05.ld
-                        // path is as slow as the K=256 MMAs that fill it), the tensor core works on the other tile.
-                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(lbo_b, 128);
-                        for (int t = 0; t < 2; ++t) {
-                            mbar_wait(bar_in + 8 * t, use & 1);
-                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-                            for (int s = 0; s < ns; ++s) {
-                                uint32_t a_addr;
-                                if (l == 0) a_addr = sbase + kSmemGx + t * kGxBytes + (uint32_t)s * 8192u;
-                                else if (l == 4 && s >= 8) a_addr = sbase + kSmemGx + t * kGxBytes + (uint32_t)(s - 8) * 8192u;
-                                else if (l == 9 && s == 8) a_addr = sbase + kSmemGx + t * kGxBytes;
-                                else a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 8192u;
-                                const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-                                mbar_wait(bar_full + 8 * stage, round & 1);
-                                tc_fence_after();
-                                if (elect_one()) {
-                                    tc_mma(d_tmem, desc_at(ahi, a_addr), desc_at(bhi, b_addr), idesc, s > 0 ? 1u : 0u);
-                                    tc_mma(d_tmem, desc_at(ahi, a_addr + 2 * 2048), desc_at(bhi, b_addr + 2 * lbo_b), idesc, 1u);
-                                    if (s == ns - 1) tc_commit(bar_acc + 8 * t);
-                                    tc_commit(bar_empty + 8 * stage);
-                                }
-                                __syncwarp();
-                                if (++stage == kStages) { stage = 0; ++round; }
-                            }
-                        }
-                        continue;
-                    }
-                    for (int s = 0; s < ns; ++s) {
-                        // A-operand source of this K=32 slab
-                        uint32_t a_off;   // byte offset inside the tile's act / gx buffer
-                        bool from_gx;
-                        if (l == 0) { from_gx = true; a_off = (uint32_t)s * 4u * 2048u; }
-                        else if (l == 4 && s >= 8) { from_gx = true; a_off = (uint32_t)(s - 8) * 4u * 2048u; }
-                        else if (l == 9 && s == 8) { from_gx = true; a_off = 0; }
-                        else { from_gx = false; a_off = (uint32_t)s * 4u * 2048u; }
-                        const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-                        const uint32_t a0 = sbase + (from_gx ? kSmemGx : kSmemAct) + a_off;                  // tile A
-                        const uint32_t a1 = a0 + (from_gx ? kGxBytes : kActBytes);                          // tile B
-                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(lbo_b, 128);
-                        const uint64_t bd0 = desc_at(bhi, b_addr), bd1 = desc_at(bhi, b_addr + 2 * lbo_b);
-                        const bool last = s == ns - 1;
-                        if (s == 0) {
-                            // layer start: tile A may begin while tile B's epilogue of the previous layer still runs
-                            mbar_wait(bar_in, use & 1);
-                            mbar_wait(bar_full + 8 * stage, round & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 0u);
-                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc);
-                            }
-                            __syncwarp();
-                            mbar_wait(bar_in + 8, use & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 0u);
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc + 8);
-                                tc_commit(bar_empty + 8 * stage);
-                            }
-                        } else {
-                            mbar_wait(bar_full + 8 * stage, round & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 1u);
-                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc);                 // accumulator of tile A complete
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 1u);
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc + 8);             // accumulator of tile B complete
-                                tc_commit(bar_empty + 8 * stage);             // ring slot free once these MMAs retire
-                            }
-                        }
-                        __syncwarp();
-                        if (++stage == kStages) { stage = 0; ++round; }
+                    const uint64_t bhi = desc_hi(lbo_b, 128);
+                    const uint32_t b_step = (2u * lbo_b) >> 4;
+                    // A-operand segments of the layer: n_act slabs from the activation buffer, then n_gx from the gamma buffer
+                    const int n_act = l == 0 ? 0 : 8;
+                    const int n_gx = l == 0 ? 2 : (l == 4 ? 2 : (l == 9 ? 1 : 0));
+                    for (int t = 0; t < 2; ++t) {
+                        if (p.cyc) mbar_wait_t(bar_in + 8 * t, use & 1, w_in); else mbar_wait(bar_in + 8 * t, use & 1);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+                        const uint32_t act_lo = (sbase + kSmemAct + t * kActBytes) >> 4, gx_lo = (sbase + kSmemGx + t * kGxBytes) >> 4;
+                        const uint32_t acc_bar = bar_acc + 8 * t;
+                        if (n_act) issue(act_lo, n_act, true, d_tmem, bhi, b_step, idesc, n_gx ? 0u : acc_bar);
+                        if (n_gx) issue(gx_lo, n_gx, n_act == 0, d_tmem, bhi, b_step, idesc, acc_bar);
                     }
                 }
+            }
+            if (p.cyc && blockIdx.x == 0) {
+                p.cyc[2] = (unsigned long long)w_in; p.cyc[3] = (unsigned long long)w_full; p.cyc[4] = (unsigned long long)(clock64() - t_begin);
             }
         }
     } else if (warp >= 4) {
@@ -519,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         const uint32_t act = sbase + kSmemAct + t * kActBytes, gx = sbase + kSmemGx + t * kGxBytes;
         const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t use = 0;
+        long long w_acc = 0, w_bar = 0, t_cols = 0; const long long t_begin = clock64();
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int64_t tile = pair * 2 + t;
             const int64_t q = tile * TILE_M + r;
@@ -560,13 +527,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;      // l==7: w_sigma[32g+lane];  l==9: Wo[ch][32g+lane]
                 if (l == 7) hw0 = __ldg(tail + kWsigOfs + lane);
                 if (l == 9) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
-                mbar_wait(bar_acc + 8 * t, use & 1);
+                mbar_wait_t(bar_acc + 8 * t, use & 1, w_acc);
                 tc_fence_after();
                 // group barrier 1: everyone is past the previous layer's reads of sbias
+                const long long tb0 = clock64();
                 named_bar_sync(1 + t, 128);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)r), "f"(b_lo) : "memory");
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 512u + 4u * (uint32_t)r), "f"(b_hi) : "memory");
                 named_bar_sync(1 + t, 128);                 // group barrier 2: bias visible
+                const long long tc0 = clock64();
+                w_bar += tc0 - tb0;
                 const bool relu = l != 8;
                 const bool need_f32 = l == 7 || l == 9 || (want_dbg && l == p.dbg_layer);
                 const bool write_act = l != 9;              // next layer's A operand, in place
@@ -645,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     hw0 = n0; hw1 = n1; hw2 = n2;
                 }
                 }
+                t_cols += clock64() - tc0;
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
                     if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
                     else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
@@ -660,6 +631,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                                                                    rgb[2] + tail[kBoOfs + 2], sig + tail[kBsigOfs]);
             }
             tc_fence_before();   // the next pair's first MMA overwrites this accumulator: order our tcgen05.ld before it
+        }
+        if (p.cyc && blockIdx.x == 0 && (r == 0)) {
+            p.cyc[5 + 4 * t] = (unsigned long long)w_acc; p.cyc[6 + 4 * t] = (unsigned long long)w_bar;
+            p.cyc[7 + 4 * t] = (unsigned long long)t_cols; p.cyc[8 + 4 * t] = (unsigned long long)(clock64() - t_begin);
         }
     }
     tc_fence_before();
@@ -1388,6 +1363,7 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 int tc_debug_layer(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,
                    const void* packed, float* raw, float* dbg, int layer, int64_t B, int N, cudaStream_t st) {
     tc::FwdParams p{};
+    if (layer < 0) { p.cyc = reinterpret_cast<unsigned long long*>(dbg); dbg = nullptr; }   // layer -1: cycle counters instead
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.ray_norm = ray_norm; p.viewdirs = viewdirs;
     p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw; p.dbg = dbg; p.dbg_layer = layer;
     p.Q = B * (int64_t)N; p.N = N;
