@@ -802,71 +802,28 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             }
         }
     } else if (warp == 1) {
-        {                                                  // MMA issuer (warp-uniform loop, lane 0 issues)
+        if (elect_one()) {                                 // MMA issuer: one elected thread, ping-pong over the two tiles
             uint32_t stage = 0, round = 0, use = 0;
             const uint32_t idesc = make_idesc(256);
+            const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
+            const uint32_t ring_lo = (sbase + kSmemRing) >> 4;
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                     const int ns = m == 0 ? 4 : 8;
-                    if (kPingPong) {
-                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
-                        for (int t = 0; t < 2; ++t) {
-                            mbar_wait(bar_in + 8 * t, use & 1);
-                            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-                            for (int s = 0; s < ns; ++s) {
-                                const uint32_t a_addr = sbase + kSmemAct + t * kActBytes + (uint32_t)s * 8192u;
-                                const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-                                mbar_wait(bar_full + 8 * stage, round & 1);
-                                tc_fence_after();
-                                if (elect_one()) {
-                                    tc_mma(d_tmem, desc_at(ahi, a_addr), desc_at(bhi, b_addr), idesc, s > 0 ? 1u : 0u);
-                                    tc_mma(d_tmem, desc_at(ahi, a_addr + 2 * 2048), desc_at(bhi, b_addr + 2 * 4096), idesc, 1u);
-                                    if (s == ns - 1) tc_commit(bar_acc + 8 * t);
-                                    tc_commit(bar_empty + 8 * stage);
-                                }
-                                __syncwarp();
-                                if (++stage == kStages) { stage = 0; ++round; }
-                            }
-                        }
-                        continue;
-                    }
-                    for (int s = 0; s < ns; ++s) {
-                        const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
-                        const uint32_t a0 = sbase + kSmemAct + (uint32_t)s * 4u * 2048u, a1 = a0 + kActBytes;
-                        const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
-                        const uint64_t bd0 = desc_at(bhi, b_addr), bd1 = desc_at(bhi, b_addr + 2 * 4096);
-                        const bool last = s == ns - 1;
-                        if (s == 0) {
-                            mbar_wait(bar_in, use & 1);
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(bar_in + 8 * t, use & 1);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+                        uint32_t a_lo = (sbase + kSmemAct + t * kActBytes) >> 4;
+                        for (int s = 0; s < ns; ++s, a_lo += 512u) {
                             mbar_wait(bar_full + 8 * stage, round & 1);
                             tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 0u);
-                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
-                            }
-                            __syncwarp();
-                            mbar_wait(bar_in + 8, use & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 0u);
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
-                                tc_commit(bar_empty + 8 * stage);
-                            }
-                        } else {
-                            mbar_wait(bar_full + 8 * stage, round & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                tc_mma(tmem_base, desc_at(ahi, a0), bd0, idesc, 1u);
-                                tc_mma(tmem_base, desc_at(ahi, a0 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc);
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1), bd0, idesc, 1u);
-                                tc_mma(tmem_base + 256u, desc_at(ahi, a1 + 2 * 2048), bd1, idesc, 1u);
-                                if (last) tc_commit(bar_acc + 8);
-                                tc_commit(bar_empty + 8 * stage);
-                            }
+                            const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
+                            tc_mma(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, s > 0 ? 1u : 0u);
+                            tc_mma(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + 512u), idesc, 1u);
+                            if (s == ns - 1) tc_commit(bar_acc + 8 * t);
+                            tc_commit(bar_empty + 8 * stage);
+                            if (++stage == kStages) { stage = 0; ++round; }
                         }
-                        __syncwarp();
-                        if (++stage == kStages) { stage = 0; ++round; }
                     }
                 }
             }
@@ -1033,7 +990,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        {                      // MMA issuer (warp-uniform loop, lane 0 issues)
+        if (elect_one()) {     // MMA issuer: one elected thread
             uint32_t slot = 0, round = 0;
             const uint32_t idesc = make_idesc_mn(job.xcols);
             const uint64_t mnhi = desc_hi(128, 2048);
@@ -1046,22 +1003,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                 mbar_wait(bar_full + 8 * s_dy, r_dy & 1);
                 mbar_wait(bar_full + 8 * s_x, r_x & 1);
                 tc_fence_after();
-                const uint32_t a_base = sbase + s_dy * kWgBlock, b_base = sbase + s_x * kWgBlock;
-                if (elect_one()) {
-                    for (int h = 0; h < job.halves; ++h) {
+                const uint32_t a_lo = (sbase + s_dy * kWgBlock) >> 4, b_lo = (sbase + s_x * kWgBlock) >> 4;
+                for (int h = 0; h < job.halves; ++h) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
-                            tc_mma(tmem_base + (uint32_t)h * 256u, desc_at(mnhi, a_base + h * 32768 + ks * 256),
-                                   desc_at(mnhi, b_base + ks * 256), idesc, (!first || ks > 0) ? 1u : 0u);
-                    }
-                    tc_commit(bar_empty + 8 * s_dy);
-                    tc_commit(bar_empty + 8 * s_x);
+                    for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
+                        tc_mma(tmem_base + (uint32_t)h * 256u, mnhi | (uint64_t)(a_lo + h * 2048 + ks * 16), mnhi | (uint64_t)(b_lo + ks * 16), idesc,
+                               (!first || ks > 0) ? 1u : 0u);
                 }
                 first = false;
-                __syncwarp();
+                tc_commit(bar_empty + 8 * s_dy);
+                tc_commit(bar_empty + 8 * s_x);
             }
-            if (elect_one()) tc_commit(bar_done);
-            __syncwarp();
+            tc_commit(bar_done);
         }
     } else if (warp >= 4) {
         // ---- bias grads: column sums of the dY image (lanes over points -> conflict-free 16-byte reads) ----
