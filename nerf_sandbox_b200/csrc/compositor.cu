@@ -16,7 +16,8 @@ struct Sample { float r, g, b, sigma; };
 template <bool RAW>
 __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                                               const float* __restrict__ noise, float noise_std, bool add_noise,
-                                              uint64_t seed, uint64_t offset, int64_t q, float* pre_out) {
+                                              uint64_t seed, uint64_t offset, int64_t q, float* pre_out,
+                                              const float* pre_in = nullptr) {
     Sample s;
     if (RAW) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(rgb_or_raw) + q);
@@ -24,7 +25,8 @@ __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_r
         s.g = 1.0f / (1.0f + expf(-v.y));
         s.b = 1.0f / (1.0f + expf(-v.z));
         float pre = v.w;
-        if (add_noise) pre += (noise ? noise[q] : philox_normal(seed, offset, (uint64_t)q)) * noise_std;   // :239-241
+        if (pre_in) pre = *pre_in;                            // reverse pass: noisy pre-activation kept from pass 1
+        else if (add_noise) pre += (noise ? noise[q] : hash_normal(seed, offset, (uint64_t)q)) * noise_std;   // :239-241
         if (pre_out) *pre_out = pre;
         s.sigma = fmaxf(pre, 0.0f);                           // :246 relu
     } else {
@@ -119,8 +121,9 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t offset) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* s_alpha = smem + (size_t)warp * 2 * N;
+    float* s_alpha = smem + (size_t)warp * 3 * N;
     float* s_T = s_alpha + N;
+    float* s_pre = s_T + N;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
     const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
     for (int64_t b = blockIdx.x * (int64_t)kCompWarps + warp; b < B; b += (int64_t)gridDim.x * kCompWarps) {
@@ -136,7 +139,9 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             Sample s = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 zi = zrow[i];
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, nullptr);
+                float pre1 = 0.f;
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre1);
+                if (RAW) s_pre[i] = pre1;
                 const float sdt = fminf(fmaxf(s.sigma * delta_at(zrow, i, N, inf_last, rn, has_rn), 0.0f), 60.0f);
                 alpha = 1.0f - expf(-sdt);
                 f = (1.0f - alpha) + eps;
@@ -181,7 +186,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             Sample s = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 alpha = s_alpha[i]; T = s_T[i];
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre, RAW ? &s_pre[i] : nullptr);
                 delta = delta_at(zrow, i, N, inf_last, rn, has_rn);
                 const float wraw = T * alpha;
                 const bool fin = isfinite(wraw);
@@ -238,7 +243,7 @@ static int launch_bwd(const float* a, const float* sigma, const float* noise, fl
                       const float* rn, const float* g_comp, const float* g_w, const float* g_a, const float* g_d,
                       float* d0, float* d1, int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t off,
                       void* stream) {
-    const size_t smem = (size_t)kCompWarps * 2 * N * sizeof(float);
+    const size_t smem = (size_t)kCompWarps * 3 * N * sizeof(float);
     if (smem > 200 * 1024) return NSB_E_BADARG;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(composite_bwd_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -66,6 +66,16 @@ __device__ inline float philox_normal(uint64_t seed, uint64_t stream_id, uint64_
     return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
+// N(0,1) for the sigma regulariser (render_utils.py:240): splitmix64 finaliser as a counter hash + fast Box-Muller.
+// Far cheaper than a Philox-10 block per sample; statistical quality is ample for additive training noise.
+__device__ inline float hash_normal(uint64_t seed, uint64_t stream_id, uint64_t idx) {
+    uint64_t x = (idx + 0x9E3779B97F4A7C15ull * (stream_id + 1)) ^ seed;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    const float u1 = ((float)((uint32_t)(x >> 40)) + 1.0f) * (1.0f / 16777216.0f);   // (0,1]
+    const float u2 = (float)((uint32_t)x >> 8) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853071795865f * u2);
+}
+
 // ---- warp helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -19,17 +19,26 @@ __device__ __forceinline__ float coarse_z_at(int i, int Nc, float near_, float f
 __global__ void stratified_kernel(float* __restrict__ z, const float* __restrict__ U, int64_t B, int Nc,
                                   float near_, float far_, int jitter, uint64_t seed, uint64_t offset) {
     const int64_t total = B * (int64_t)Nc;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % Nc);
-        const float zi = coarse_z_at(i, Nc, near_, far_);
-        if (!jitter) { z[idx] = zi; continue; }
-        const float zl = i > 0 ? coarse_z_at(i - 1, Nc, near_, far_) : zi;
-        const float zr = i < Nc - 1 ? coarse_z_at(i + 1, Nc, near_, far_) : zi;
-        const float lower = i > 0 ? 0.5f * (zi + zl) : zi;     // :904-905  (mids = 0.5*(z[1:]+z[:-1]))
-        const float upper = i < Nc - 1 ? 0.5f * (zr + zi) : zi; // :906
-        const float u = U ? U[idx] : philox_uniform(seed, offset, (uint64_t)idx);
-        z[idx] = lower + (upper - lower) * u;                  // :907 (the sort at :908 is the identity)
+    // four consecutive samples per thread: one Philox4x32 block feeds all four uniforms
+    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; base < total;
+         base += (int64_t)gridDim.x * blockDim.x * 4) {
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (jitter && !U) rnd = philox4(seed, offset, (uint64_t)(base >> 2));
+        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t idx = base + e;
+            if (idx >= total) break;
+            const int i = (int)(idx % Nc);
+            const float zi = coarse_z_at(i, Nc, near_, far_);
+            if (!jitter) { z[idx] = zi; continue; }
+            const float zl = i > 0 ? coarse_z_at(i - 1, Nc, near_, far_) : zi;
+            const float zr = i < Nc - 1 ? coarse_z_at(i + 1, Nc, near_, far_) : zi;
+            const float lower = i > 0 ? 0.5f * (zi + zl) : zi;     // :904-905  (mids = 0.5*(z[1:]+z[:-1]))
+            const float upper = i < Nc - 1 ? 0.5f * (zr + zi) : zi; // :906
+            const float u = U ? U[idx] : u01(rw[e]);
+            z[idx] = lower + (upper - lower) * u;                  // :907 (the sort at :908 is the identity)
+        }
     }
 }
 
@@ -145,6 +154,17 @@ __device__ __forceinline__ void warp_bitonic_sort(float* a, int len, int lane) {
     }
 }
 
+// first index with a[idx] >= v  /  first index with a[idx] > v, on a sorted shared-memory array
+__device__ __forceinline__ int lower_bound_f(const float* a, int n, float v) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// The merge of sort(cat(zc, zf)) (trainer.py:981) is done by rank: zc is sorted (stratified), zf is sorted because the
+// inverse CDF is monotone in u -- directly for the deterministic linspace u, after a bitonic sort of the Nf samples for
+// random u.  out[i + #{zf < zc[i]}] = zc[i];  out[j + #{zc <= zf[j]}] = zf[j]  (coarse first on ties; values-only, so the
+// result is bit-identical to any sort).
 __global__ void resample_merge_kernel(const float* __restrict__ zc, const float* __restrict__ w_c,
                                       const float* __restrict__ u_in, float* __restrict__ z_all,
                                       float* __restrict__ z_fine, int64_t B, int Nc, int Nf, int sort_len,
@@ -152,15 +172,16 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = Nc - 1;
-    const int per_warp = 3 * Nc + sort_len;                     // zc | edges | cdf | sort buffer
+    const int Nt = Nc + Nf;
+    const int per_warp = 3 * Nc + sort_len + Nt;                // zc | edges | cdf | fine (padded) | merged row
     float* zrow = smem + (size_t)warp * per_warp;
     float* edges = zrow + Nc;
     float* cdf = edges + Nc;
-    float* sortbuf = cdf + Nc;
-    const int Nt = Nc + Nf;
+    float* fine = cdf + Nc;
+    float* merged = fine + sort_len;
     for (int64_t b = blockIdx.x * (int64_t)kWarpsPerBlock + warp; b < B; b += (int64_t)gridDim.x * kWarpsPerBlock) {
         const float* wrow = w_c + b * Nc;
-        for (int j = lane; j < Nc; j += 32) { const float v = zc[b * Nc + j]; zrow[j] = v; sortbuf[j] = v; }
+        for (int j = lane; j < Nc; j += 32) zrow[j] = zc[b * Nc + j];
         __syncwarp();
         auto mid = [&](int j) { return 0.5f * (zrow[j + 1] + zrow[j]); };                      // :926
         build_edges_from_mids(edges, M, lane, mid);
@@ -173,13 +194,20 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
             else u = u_in ? u_in[b * Nf + s] : philox_uniform(seed, offset, (uint64_t)(b * Nf + s));
             int ind;
             const float zf = invert(cdf, edges, M, u, &ind);
-            sortbuf[Nc + s] = zf;
+            fine[s] = zf;
             if (z_fine) z_fine[b * Nf + s] = zf;
         }
-        for (int j = Nt + lane; j < sort_len; j += 32) sortbuf[j] = __int_as_float(0x7f800000);   // +inf pad
+        if (!deterministic) {
+            for (int j = Nf + lane; j < sort_len; j += 32) fine[j] = __int_as_float(0x7f800000);   // +inf pad
+            __syncwarp();
+            warp_bitonic_sort(fine, sort_len, lane);
+        } else {
+            __syncwarp();
+        }
+        for (int i = lane; i < Nc; i += 32) { const float v = zrow[i]; merged[i + lower_bound_f(fine, Nf, v)] = v; }
+        for (int j = lane; j < Nf; j += 32) { const float v = fine[j]; merged[j + upper_bound(zrow, Nc, v)] = v; }
         __syncwarp();
-        warp_bitonic_sort(sortbuf, sort_len, lane);                                              // :981
-        for (int j = lane; j < Nt; j += 32) z_all[b * Nt + j] = sortbuf[j];
+        for (int j = lane; j < Nt; j += 32) z_all[b * Nt + j] = merged[j];
         __syncwarp();
     }
 }
@@ -199,7 +227,8 @@ extern "C" int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, flo
     if (B == 0) return NSB_OK;
     if (!z || B < 0 || Nc < 1) return NSB_E_BADARG;
     const int64_t total = B * Nc;
-    const int grid = (int)(cdiv(total, 256) < (int64_t)num_sms() * 8 ? cdiv(total, 256) : (int64_t)num_sms() * 8);
+    const int64_t want = cdiv(total, 256 * 4);
+    const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
     stratified_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset);
     NSB_LAUNCH_CHECK("stratified_kernel");
     return NSB_OK;
@@ -226,8 +255,8 @@ extern "C" int nsb_resample_merge(const float* zc, const float* w_c, const float
     if (B == 0) return NSB_OK;
     if (!zc || !w_c || !z_all || Nc < 2 || Nf < 1 || B < 0) return NSB_E_BADARG;
     int sort_len = 32;
-    while (sort_len < Nc + Nf) sort_len <<= 1;
-    const size_t smem = (size_t)kWarpsPerBlock * (3 * Nc + sort_len) * sizeof(float);
+    while (sort_len < Nf) sort_len <<= 1;
+    const size_t smem = (size_t)kWarpsPerBlock * (3 * Nc + sort_len + Nc + Nf) * sizeof(float);
     if (smem > 200 * 1024) return NSB_E_BADARG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     resample_merge_kernel<<<grid_for_rays(B), kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
