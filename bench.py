@@ -267,7 +267,13 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     ach_tf = Q * FLOP_TRAIN_PER_POINT / (ms_field * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+    traffic = None
+    try:      # DRAM bytes of this launch set from the committed ncu --set full captures (bf16 mode only)
+        if args.mode == "bf16":
+            traffic = int(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["field_fwd_bwd_fine_bytes"])
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                 "kernel": f"field fwd+bwd ({args.mode}) on the fine pass, {Q} points, {ms_field:.3f} ms/launch-set",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"}
 
