@@ -176,6 +176,21 @@ int nsb_render_rays(const float* rays_o, const float* rays_d, const float* ray_n
                     size_t ws_bytes, int64_t B, int Nc, int Nf, float near_, float far_, uint32_t flags, int mode,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ray generation (the producer of the path's inputs)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* get_camera_rays, utils/ray_utils.py:10-136.  K_host[9] (3x3 row-major) and c2w_host[3 x c2w_cols]
+ * (c2w_cols must be 4; rows of a (3,4) or (4,4) pose) are HOST pointers.  convention: 0 opengl/blender/nerf,
+ * 1 opencv/colmap, 2 pytorch3d (:69-77).  pixels_xy[n_pixels,2] [opt, device] selects pixels (x,y), otherwise
+ * the full H*W row-major grid.  Outputs (device): o_world[n,3], d_world_unit[n,3], d_world_norm[n],
+ * o_march[n,3], d_march_unit[n,3], d_march_norm[n] -- the reference's 6-tuple; as_ndc applies the NDC
+ * warp of :92-126 to the marching rays. */
+int nsb_camera_rays(int H, int W, const float* K_host, const float* c2w_host, int c2w_cols, int convention,
+                    int pixel_center, int as_ndc, float near_plane, const float* pixels_xy, int64_t n_pixels,
+                    float* o_world, float* d_world_unit, float* d_world_norm, float* o_march, float* d_march_unit,
+                    float* d_march_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

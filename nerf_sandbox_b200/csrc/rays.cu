@@ -1,0 +1,77 @@
+// Camera-ray generation + NDC warp: utils/ray_utils.py:10-136.
+// One thread per pixel, everything in registers, six coalesced outputs.  Compiled -fmad=false so each
+// mul/add/div rounds like the reference's separate ATen ops.
+#include "nsb_common.cuh"
+
+namespace nsb {
+
+struct RayCam {
+    float fx, fy, cx, cy;
+    float R[9];      // row-major c2w[:3,:3]
+    float t[3];      // c2w[:3,3]
+    float sy_cam, sz_cam;   // camera-frame signs of (y, z): opengl (-1,-1), opencv (+1,+1), pytorch3d (-1,+1)  (:69-77)
+};
+
+__global__ void camera_rays_kernel(RayCam c, int H, int W, const float* __restrict__ pixels_xy, int64_t n, int pixel_center,
+                                   int as_ndc, float near_plane, float* __restrict__ o_world, float* __restrict__ d_world_unit,
+                                   float* __restrict__ d_world_norm, float* __restrict__ o_march, float* __restrict__ d_march_unit,
+                                   float* __restrict__ d_march_norm) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x, y;
+        if (pixels_xy) { x = pixels_xy[2 * i]; y = pixels_xy[2 * i + 1]; }        // :56-60
+        else { x = (float)(i % W); y = (float)(i / W); }                           // :45-54 (row-major meshgrid)
+        if (pixel_center) { x += 0.5f; y += 0.5f; }
+        const float xc = (x - c.cx) / c.fx, yc = (y - c.cy) / c.fy;                // :66-67
+        const float dc[3] = {xc, c.sy_cam * yc, c.sz_cam};
+        float d[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) d[r] = dc[0] * c.R[3 * r] + dc[1] * c.R[3 * r + 1] + dc[2] * c.R[3 * r + 2];   // dirs @ R^T :80
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);          // :81
+        const float inv = nrm + 1e-9f;
+        const float du[3] = {d[0] / inv, d[1] / inv, d[2] / inv};                  // :82
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { o_world[3 * i + r] = c.t[r]; d_world_unit[3 * i + r] = du[r]; }
+        d_world_norm[i] = nrm;
+        if (!as_ndc) {                                                             // :86-90
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { o_march[3 * i + r] = c.t[r]; d_march_unit[3 * i + r] = du[r]; }
+            d_march_norm[i] = nrm;
+        } else {                                                                   // :92-126
+            const float sx = 2.0f * c.fx / (float)W, sy = 2.0f * c.fx / (float)H;  // scalar focal = fx (:100-102)
+            const float tn = -(near_plane + c.t[2]) / (d[2] + 1e-9f);              // :108
+            const float ow[3] = {c.t[0] + tn * d[0], c.t[1] + tn * d[1], c.t[2] + tn * d[2]};
+            const float oz = ow[2] + 1e-9f, dz = d[2] + 1e-9f;
+            const float o0 = -sx * (ow[0] / oz), o1 = -sy * (ow[1] / oz), o2 = 1.0f + 2.0f * near_plane / oz;   // :112-114
+            const float d0 = -sx * (d[0] / dz - ow[0] / oz), d1 = -sy * (d[1] / dz - ow[1] / oz), d2 = -2.0f * near_plane / oz;
+            const float nn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);                   // :125
+            const float dn = fmaxf(nn, 1e-12f);                                    // F.normalize :126
+            o_march[3 * i] = o0; o_march[3 * i + 1] = o1; o_march[3 * i + 2] = o2;
+            d_march_unit[3 * i] = d0 / dn; d_march_unit[3 * i + 1] = d1 / dn; d_march_unit[3 * i + 2] = d2 / dn;
+            d_march_norm[i] = nn;
+        }
+    }
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_camera_rays(int H, int W, const float* K_host, const float* c2w_host, int c2w_cols, int convention,
+                               int pixel_center, int as_ndc, float near_plane, const float* pixels_xy, int64_t n_pixels,
+                               float* o_world, float* d_world_unit, float* d_world_norm, float* o_march, float* d_march_unit,
+                               float* d_march_norm, void* stream) {
+    if (!K_host || !c2w_host || (c2w_cols != 4) || H < 1 || W < 1 || convention < 0 || convention > 2) return NSB_E_BADARG;
+    const int64_t n = pixels_xy ? n_pixels : (int64_t)H * W;
+    if (n == 0) return NSB_OK;
+    if (!o_world || !d_world_unit || !d_world_norm || !o_march || !d_march_unit || !d_march_norm) return NSB_E_BADARG;
+    RayCam c;
+    c.fx = K_host[0]; c.fy = K_host[4]; c.cx = K_host[2]; c.cy = K_host[5];
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) c.R[3 * r + k] = c2w_host[4 * r + k]; c.t[r] = c2w_host[4 * r + 3]; }
+    c.sy_cam = convention == 1 ? 1.0f : -1.0f;
+    c.sz_cam = convention == 0 ? -1.0f : 1.0f;
+    const int64_t want = cdiv(n, 256), cap = (int64_t)num_sms() * 16;
+    camera_rays_kernel<<<(int)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
+        c, H, W, pixels_xy, n, pixel_center, as_ndc, near_plane, o_world, d_world_unit, d_world_norm, o_march, d_march_unit, d_march_norm);
+    NSB_LAUNCH_CHECK("camera_rays_kernel");
+    return NSB_OK;
+}

@@ -10,17 +10,22 @@ import importlib
 import sys
 import types
 
-from . import encoders, mlps, render, sampling
+from . import encoders, mlps, rays, render, sampling
 
 _BINDINGS = {
     "nerf_sandbox.source.train.trainer": {
         "PositionalEncoder": encoders.PositionalEncoder, "get_vanilla_nerf_encoders": encoders.get_vanilla_nerf_encoders,
         "NeRF": mlps.NeRF, "log_nerf_arch": mlps.log_nerf_arch, "volume_render_rays": render.volume_render_rays,
-        "nerf_forward_pass": render.nerf_forward_pass, "sample_pdf": sampling.sample_pdf},
+        "nerf_forward_pass": render.nerf_forward_pass, "sample_pdf": sampling.sample_pdf,
+        "get_camera_rays": rays.get_camera_rays},
     "nerf_sandbox.source.utils.render_utils": {
+        "get_camera_rays": rays.get_camera_rays, "render_pose": rays.render_pose,
         "sample_pdf": sampling.sample_pdf, "volume_render_rays": render.volume_render_rays,
         "nerf_forward_pass": render.nerf_forward_pass, "render_image_chunked": render.render_image_chunked},
-    "nerf_sandbox.source.utils.validation_renderer": {"render_image_chunked": render.render_image_chunked},
+    "nerf_sandbox.source.utils.validation_renderer": {"render_image_chunked": render.render_image_chunked,
+                                                      "render_pose": rays.render_pose, "get_camera_rays": rays.get_camera_rays},
+    "nerf_sandbox.source.data.samplers": {"get_camera_rays": rays.get_camera_rays},
+    "nerf_sandbox.source.utils.ray_utils": {"get_camera_rays": rays.get_camera_rays},
     "nerf_sandbox.source.models.encoders": {
         "PositionalEncoder": encoders.PositionalEncoder, "get_vanilla_nerf_encoders": encoders.get_vanilla_nerf_encoders},
     "nerf_sandbox.source.models.mlps": {"NeRF": mlps.NeRF, "log_nerf_arch": mlps.log_nerf_arch},

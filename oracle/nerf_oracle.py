@@ -516,3 +516,45 @@ def synthetic_rays(rng: np.random.Generator, B: int, radius: float = 4.0311):
     tgt = rng.uniform(0.0, 1.0, size=(B, 3)).astype(F32)
     return dict(rays_o_marching=o, rays_d_marching_unit=d, rays_d_marching_norm=norms,
                 rays_d_world_unit=d.copy(), rgb=tgt)
+
+
+# --------------------------------------------------------------------------
+# Ray generation + NDC warp -- utils/ray_utils.py:10-136
+# --------------------------------------------------------------------------
+def camera_rays(H, W, K, c2w, *, convention="opengl", pixel_center=False, as_ndc=False, near_plane=1.0, pixels_xy=None):
+    K, c2w = _f(K), _f(c2w)
+    R, t = c2w[:3, :3], c2w[:3, 3]
+    if pixels_xy is None:                                                    # :44-54
+        ys, xs = np.meshgrid(np.arange(H, dtype=F32), np.arange(W, dtype=F32), indexing="ij")
+        x, y = xs.reshape(-1), ys.reshape(-1)
+    else:                                                                    # :55-60
+        px = _f(pixels_xy).reshape(-1, 2)
+        x, y = px[:, 0], px[:, 1]
+    if pixel_center:
+        x, y = x + F32(0.5), y + F32(0.5)
+    xc, yc = (x - K[0, 2]) / K[0, 0], (y - K[1, 2]) / K[1, 1]                # :63-67
+    conv = (convention or "opengl").lower()
+    one = np.ones_like(xc)
+    if conv in ("opengl", "blender", "nerf"):
+        dc = np.stack([xc, -yc, -one], -1)
+    elif conv in ("opencv", "colmap"):
+        dc = np.stack([xc, yc, one], -1)
+    elif conv in ("pytorch3d", "p3d"):
+        dc = np.stack([xc, -yc, one], -1)
+    else:
+        raise ValueError(f"Unknown convention '{convention}'")
+    d = (dc @ R.T).astype(F32)                                               # :80
+    nrm = np.sqrt((d * d).sum(-1, keepdims=True, dtype=F32))                 # :81
+    du = (d / (nrm + F32(1e-9))).astype(F32)                                 # :82
+    o = np.broadcast_to(t, d.shape).astype(F32)
+    if not as_ndc:                                                           # :86-90
+        return o, du, nrm, o, du, nrm
+    sx, sy = F32(2.0) * K[0, 0] / F32(W), F32(2.0) * K[0, 0] / F32(H)        # :100-102
+    tn = -(F32(near_plane) + o[:, 2]) / (d[:, 2] + F32(1e-9))                # :108
+    ow = o + tn[:, None] * d
+    oz, dz = ow[:, 2] + F32(1e-9), d[:, 2] + F32(1e-9)
+    o0, o1, o2 = -sx * (ow[:, 0] / oz), -sy * (ow[:, 1] / oz), F32(1) + F32(2) * F32(near_plane) / oz      # :112-114
+    d0 = -sx * (d[:, 0] / dz - ow[:, 0] / oz); d1 = -sy * (d[:, 1] / dz - ow[:, 1] / oz); d2 = -F32(2) * F32(near_plane) / oz
+    om, dm = np.stack([o0, o1, o2], -1).astype(F32), np.stack([d0, d1, d2], -1).astype(F32)
+    nn = np.sqrt((dm * dm).sum(-1, keepdims=True, dtype=F32))               # :125
+    return o, du, nrm, om, (dm / np.maximum(nn, F32(1e-12))).astype(F32), nn  # :126

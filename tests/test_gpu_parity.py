@@ -321,3 +321,33 @@ def test_reference_style_step_through_module_boundary_fp32(nsb):
     for tag, net in (("c", tr.nerf_c), ("f", tr.nerf_f)):
         norms = np.array([float(q.grad.norm()) for q in net.parameters()])
         close(norms, g[f"grad_norms_{tag}"], 5e-3 if tag == "f" else 1e-3, 1e-7)
+
+
+def test_camera_rays_and_render_pose(nsb):
+    g = golden("rays")
+    for name in g["names"]:
+        name = str(name)
+        px = g.get(f"{name}_px")
+        out = nsb.get_camera_rays(int(g[f"{name}_H"]), int(g[f"{name}_W"]), g[f"{name}_K"], g[f"{name}_c2w"], device=DEV,
+                                  convention=str(g[f"{name}_conv"]), pixel_center=bool(g[f"{name}_pc"]), as_ndc=bool(g[f"{name}_ndc"]),
+                                  near_plane=float(g[f"{name}_near"]), pixels_xy=px)
+        assert len(out) == 6
+        for i, a in enumerate(out):
+            ref = g[f"{name}_out{i}"]
+            assert tuple(a.shape) == ref.shape
+            close(N(a), ref, 2e-6, 2e-6)
+    with pytest.raises(ValueError):
+        nsb.get_camera_rays(4, 4, np.eye(3, dtype=np.float32), np.eye(4, dtype=np.float32), device=DEV, convention="nope")
+    with pytest.raises(ValueError):
+        nsb.get_camera_rays(4, 4, np.eye(2, dtype=np.float32), np.eye(4, dtype=np.float32), device=DEV)
+    # render_pose == render_image_chunked on the generated rays (world and NDC marching)
+    nc_, _ = load_nerf(31, 1.0); nf_, _ = load_nerf(32, 1.0)
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    K, c2w = g["blender_K"], g["blender_c2w"]
+    r = nsb.render_pose(c2w, 12, 10, K, 2.0, 6.0, pe.to(DEV), de.to(DEV), nc_, nf_, DEV, nc_eval=64, nf_eval=128, eval_chunk=50)
+    w = nsb.get_camera_rays(12, 10, K, c2w, device=DEV, pixel_center=True)
+    ref = O.render_rays_eval({k: N(v) for k, v in nc_.state_dict().items()}, {k: N(v) for k, v in nf_.state_dict().items()},
+                             N(w[0]), N(w[1]), N(w[2]), N(w[1]), near=2.0, far=6.0, nc=64, nf=128)
+    close(N(r["rgb"]).reshape(-1, 3), ref["rgb"]); close(N(r["depth"]).reshape(-1, 1), ref["depth"], 1e-4, 1e-4)
+    r2 = nsb.render_pose(g["llff_ndc_c2w"], 12, 16, g["llff_ndc_K"], 1.0, 6.0, pe, de, nc_, nf_, DEV, use_ndc=True)
+    assert r2["rgb"].shape == (12, 16, 3) and torch.isfinite(r2["rgb"]).all() and torch.isfinite(r2["depth"]).all()

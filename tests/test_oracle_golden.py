@@ -143,3 +143,19 @@ def test_eval_tile_matches_reference(tag, ilb, nf):
     close(r["rgb"].reshape(H, W, 3), g[f"{tag}_rgb"], 1e-4, 1e-5)
     close(r["acc"].reshape(H, W, 1), g[f"{tag}_acc"], 1e-4, 1e-5)
     close(r["depth"].reshape(H, W, 1), g[f"{tag}_depth"], 1e-4, 1e-4)
+
+
+def _ray_cases():
+    g = golden("rays")
+    for name in g["names"]:
+        name = str(name)
+        kw = dict(convention=str(g[f"{name}_conv"]), pixel_center=bool(g[f"{name}_pc"]), as_ndc=bool(g[f"{name}_ndc"]),
+                  near_plane=float(g[f"{name}_near"]), pixels_xy=g.get(f"{name}_px"))
+        yield name, g, (int(g[f"{name}_H"]), int(g[f"{name}_W"]), g[f"{name}_K"], g[f"{name}_c2w"]), kw
+
+
+def test_camera_rays_match_reference():
+    for name, g, args, kw in _ray_cases():
+        out = O.camera_rays(*args, **kw)
+        for i, a in enumerate(out):
+            close(a, g[f"{name}_out{i}"], 2e-6, 2e-6)          # author's own bar: origin/norm p95 <= 1e-6 (compare_nerf_repos.py:896-991)
