@@ -191,6 +191,19 @@ int nsb_camera_rays(int H, int W, const float* K_host, const float* c2w_host, in
                     float* o_world, float* d_world_unit, float* d_world_norm, float* o_march, float* d_march_unit,
                     float* d_march_norm, void* stream);
 
+/* Device-side pixel/ray batch sampler: RandomPixelRaySampler.__iter__,
+ * data/samplers.py:134-290, with the images resident in HBM and no host round trip.  images[F,H,W,C] (C = 3 or 4,
+ * values in [0,1]); Ks[F,4] = (fx,fy,cx,cy) and c2ws[F,12] (row-major 3x4) are DEVICE arrays.  fid >= 0: all rays
+ * from that frame (single-frame / vanilla mode); fid < 0: frame drawn per ray (mixed mode).  Pixels are uniform in
+ * [w0,w1) x [h0,h1) (the precrop window, :119-127); RGBA is composited on white when white_bkgd (:129-132); rays
+ * use pixel_center=True (:181-188).  Outputs: rgb[B,3], pixels_xy[B,2] [opt], fids_out[B] [opt] and the 6-tuple
+ * of nsb_camera_rays.  Draws come from Philox(seed, step). */
+int nsb_sample_pixel_batch(const float* images, int F, int H, int W, int C, const float* Ks, const float* c2ws, int fid,
+                           int h0, int h1, int w0, int w1, int white_bkgd, int convention, int as_ndc, float near_plane,
+                           int64_t B, uint64_t seed, uint64_t step, float* rgb, float* pixels_xy, int* fids_out,
+                           float* o_world, float* d_world_unit, float* d_world_norm, float* o_march, float* d_march_unit,
+                           float* d_march_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ from .mlps import NeRF, log_nerf_arch
 from .sampling import sample_pdf
 from .render import volume_render_rays, nerf_forward_pass, render_image_chunked, render_rays
 from .rays import get_camera_rays, render_pose
+from .samplers import RandomPixelRaySampler
 from .trainer import VanillaTrainer
 
 __all__ = ["PositionalEncoder", "get_vanilla_nerf_encoders", "NeRF", "log_nerf_arch", "sample_pdf", "volume_render_rays",
-           "nerf_forward_pass", "render_image_chunked", "render_rays", "get_camera_rays", "render_pose", "VanillaTrainer"]
+           "nerf_forward_pass", "render_image_chunked", "render_rays", "get_camera_rays", "render_pose", "RandomPixelRaySampler", "VanillaTrainer"]

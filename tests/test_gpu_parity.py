@@ -351,3 +351,43 @@ def test_camera_rays_and_render_pose(nsb):
     close(N(r["rgb"]).reshape(-1, 3), ref["rgb"]); close(N(r["depth"]).reshape(-1, 1), ref["depth"], 1e-4, 1e-4)
     r2 = nsb.render_pose(g["llff_ndc_c2w"], 12, 16, g["llff_ndc_K"], 1.0, 6.0, pe, de, nc_, nf_, DEV, use_ndc=True)
     assert r2["rgb"].shape == (12, 16, 3) and torch.isfinite(r2["rgb"]).all() and torch.isfinite(r2["depth"]).all()
+
+
+def test_device_pixel_sampler_matches_reference_semantics(nsb):
+    """RandomPixelRaySampler (data/samplers.py:134-290) on device: given the pixels it drew, rgb (white composite) and
+    rays must equal the reference's computation; draws respect the precrop window and cover it uniformly."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(3)
+    H, W, F = 40, 50, 3
+    g = golden("rays")
+    frames = []
+    for f in range(F):
+        img = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+        K = np.array([[60.0, 0, W / 2], [0, 61.0, H / 2], [0, 0, 1]], dtype=np.float32)
+        c2w = g["blender_c2w"].copy(); c2w[:3, 3] += f
+        frames.append(SimpleNamespace(image=img, K=K, c2w=c2w))
+    scene = SimpleNamespace(frames=frames, white_bkgd=True)
+    for single, ndc in ((True, False), (False, True)):
+        smp = nsb.RandomPixelRaySampler(scene, rays_per_batch=4096, device=DEV, sample_from_single_frame=single,
+                                        precrop_iters=1, precrop_frac=0.5, as_ndc=ndc, near_plane=1.0, seed=5)
+        b = smp.next_batch(with_pixels=True)
+        px, fid = N(b["pixels_xy"]).astype(int), N(b["frame_ids"]).astype(int)
+        assert px[:, 0].min() >= W // 4 and px[:, 0].max() < 3 * W // 4 + 1 and px[:, 1].min() >= H // 4 and px[:, 1].max() < 3 * H // 4 + 1
+        assert (len(np.unique(fid)) == 1) == single
+        assert len(np.unique(px[:, 0])) >= (W // 2) - 1          # covers the crop window
+        for f in np.unique(fid):
+            m = fid == f
+            pix = frames[f].image[px[m, 1], px[m, 0]]
+            np.testing.assert_allclose(N(b["rgb"])[m], pix[:, :3] * pix[:, 3:4] + (1 - pix[:, 3:4]), rtol=0, atol=1e-6)
+            ref = O.camera_rays(H, W, frames[f].K, frames[f].c2w, pixel_center=True, as_ndc=ndc, near_plane=1.0,
+                                pixels_xy=px[m].astype(np.float32))
+            for key, r in zip(("rays_o_world", "rays_d_world_unit", "rays_d_world_norm", "rays_o_marching", "rays_d_marching_unit",
+                               "rays_d_marching_norm"), ref):
+                close(N(b[key])[m], r, 2e-6, 2e-6)
+        b2 = smp.next_batch(with_pixels=True)                     # precrop over: full frame
+        assert N(b2["pixels_xy"])[:, 0].max() > 3 * W // 4 and not torch.equal(b2["pixels_xy"], b["pixels_xy"])
+    # feeds the trainer directly (device-resident loop, no host sync)
+    tr = nsb.VanillaTrainer(DEV, mode="fp32", sigma_bias=0.3)
+    smp = nsb.RandomPixelRaySampler(scene, rays_per_batch=256, device=DEV, sample_from_single_frame=True)
+    sc = tr.step(smp.next_batch())
+    assert torch.isfinite(sc).all()
