@@ -391,3 +391,30 @@ def test_device_pixel_sampler_matches_reference_semantics(nsb):
     smp = nsb.RandomPixelRaySampler(scene, rays_per_batch=256, device=DEV, sample_from_single_frame=True)
     sc = tr.step(smp.next_batch())
     assert torch.isfinite(sc).all()
+
+
+def test_llff_ndc_shape_train_step_fp32(nsb):
+    """BASELINE configs[3] shape (LLFF fern 504x378, NDC marching rays, z in [0,1], viewdirs = world dirs) against the oracle."""
+    rng = np.random.default_rng(17)
+    H, W, f = 378, 504, 407.6
+    K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    c2w = np.array([[1, 0, 0, 0.05], [0, 1, 0, -0.03], [0, 0, 1, 0.02]], dtype=np.float32)
+    px = np.stack([rng.integers(0, W, 40), rng.integers(0, H, 40)], -1).astype(np.float32)
+    r = O.camera_rays(H, W, K, c2w, pixel_center=True, as_ndc=True, near_plane=1.0, pixels_xy=px)
+    assert abs(float(np.median(r[5])) - 2.0) < 0.5                        # NDC rays span z in [0,1]: |d_ndc| ~ 2
+    B, nc, nf = 40, 64, 128
+    batch = dict(rays_o_marching=r[3], rays_d_marching_unit=r[4], rays_d_marching_norm=r[5], rays_d_world_unit=r[1],
+                 rgb=rng.uniform(0, 1, (B, 3)).astype(np.float32))
+    draws = dict(U=rng.uniform(0, 1, (B, nc)).astype(np.float32), u_fine=rng.uniform(0, 1, (B, nf)).astype(np.float32),
+                 noise_c=rng.standard_normal(B * nc).astype(np.float32), noise_f=rng.standard_normal(B * (nc + nf)).astype(np.float32))
+    tr = nsb.VanillaTrainer(DEV, nc=nc, nf=nf, near=0.0, far=1.0, mode="fp32", sigma_bias=2.0)
+    pc = {k: N(v) for k, v in tr.nerf_c.state_dict().items()}; pf = {k: N(v) for k, v in tr.nerf_f.state_dict().items()}
+    ref = O.train_step(pc, pf, batch, near=0.0, far=1.0, nc=nc, nf=nf, **draws)
+    out = tr._train_step({k: T(v) for k, v in batch.items()}, {k: T(v) for k, v in draws.items()})
+    assert abs(float(out["loss"].detach()) - float(ref["loss"])) <= 1e-4 * float(ref["loss"])
+    close(N(out["comp_f"]), ref["comp_f"]); close(N(out["comp_c"]), ref["comp_c"])
+    out["loss"].backward()
+    for tag, net in (("c", tr.nerf_c), ("f", tr.nerf_f)):
+        got = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
+        want = O.flatten_params(ref[f"grads_{tag}"])
+        assert np.linalg.norm(got - want) <= (2e-2 if tag == "f" else 2e-3) * np.linalg.norm(want)
