@@ -34,10 +34,7 @@ constexpr int kSmemRing = kSmemGx + 2 * kGxBytes;           // 163840
 constexpr int kSmemBar = kSmemRing + kStages * kStageBytes; // 229376
 constexpr int kSmemBias = kSmemBar + 256;                   // 2 x 1 KB: per epilogue group, the current layer's bias
 constexpr int kSmemBytes = kSmemBias + 2048;
-constexpr int kEpiWarpsPerTile = 8;               // two warps per TMEM lane quarter: each takes half of the columns
-constexpr int kEpiThreads = kEpiWarpsPerTile * 32; // 256 per tile
-constexpr int kThreads = 128 + 2 * kEpiThreads;    // 640 (forward)
-constexpr int kDgThreads = 384;                    // dgrad: 4 epilogue warps per tile
+constexpr int kThreads = 384;
 constexpr int kNumMmaLayers = 10;               // mlp.0..7, feature, color_fc
 constexpr uint32_t kTmemCols = 512;
 #ifndef NSB_TC_PINGPONG
@@ -212,7 +209,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 template <int KIND, bool WRITE>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, const float4 (&bias)[4], uint32_t act, int r, float& sig,
-                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow, float* dbg_row) {
+                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow) {
     float f[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -232,10 +229,6 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, con
             }
         }
     }
-    if (dbg_row) {                                         // test hook: fp32 post-activation of this layer
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dbg_row[c0 + j] = KIND == 0 ? fmaxf(f[j], 0.f) : f[j];
-    }
     if (WRITE || grow) {
         uint32_t w[8];
 #pragma unroll
@@ -248,38 +241,37 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, con
         st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
     }
 }
-// columns [c_begin, c_end) of this thread's accumulator row (c_begin, c_end multiples of 32)
 template <int KIND, bool WRITE>
-__device__ __forceinline__ void epi_columns(uint32_t tmem_row, int c_begin, int c_end, uint32_t sbias, uint32_t act, int r, int lane,
-                                            const float* __restrict__ tail, float& sig, float (&rgb)[3], uint8_t* grow, float* dbg_row) {
+__device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, uint32_t act, int r, int lane, const float* __restrict__ tail,
+                                            float& sig, float (&rgb)[3], uint8_t* grow) {
+    constexpr int N = KIND == 3 ? 128 : 256;
     float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;          // lane-held 32-wide slice of the head weights
-    if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + c_begin + lane);
-    if (KIND == 3) {
-        hw0 = __ldg(tail + kWoOfs + c_begin + lane); hw1 = __ldg(tail + kWoOfs + 128 + c_begin + lane);
-        hw2 = __ldg(tail + kWoOfs + 256 + c_begin + lane);
-    }
+    if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + lane);
+    if (KIND == 3) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
     uint32_t va[16], vb[16];
-    tc_ld16(tmem_row + (uint32_t)c_begin, va);
+    tc_ld16(tmem_row, va);
 #pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
         // bias of these 32 columns: issued BEFORE the TMEM wait so the shared-memory latency hides behind it
         float4 ba[4], bb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { ba[j] = lds_f4(sbias + 4u * (uint32_t)(c0 + 4 * j)); bb[j] = lds_f4(sbias + 4u * (uint32_t)(c0 + 16 + 4 * j)); }
         float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-        if (KIND == 1 && c0 + 32 < c_end) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
-        if (KIND == 3 && c0 + 32 < c_end) {
+        if (KIND == 1 && c0 + 32 < N) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
+        if (KIND == 3 && c0 + 32 < N) {
             n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
             n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
         }
+        // consumers pinned BEHIND the next TMEM load: the pin follows the tcgen05.ld in program order, so this chunk's
+        // math cannot be hoisted above the issue of the next load
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         pin16(va);
-        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow, dbg_row);
+        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow);
         tc_wait_ld();
-        tc_ld16(tmem_row + (uint32_t)(c0 + 32 < c_end ? c0 + 32 : c0), va);      // last iteration: harmless re-read
+        tc_ld16(tmem_row + (uint32_t)(c0 + 32 < N ? c0 + 32 : c0), va);      // last iteration: harmless re-read
         pin16(vb);
-        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow, dbg_row);
+        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow);
         hw0 = n0; hw1 = n1; hw2 = n2;
     }
 }
@@ -324,79 +316,63 @@ __device__ __forceinline__ void st_chunk_g(uint8_t* grow, int k8, uint32_t a, ui
     if (grow) *reinterpret_cast<uint4*>(grow + (size_t)k8 * 2048) = make_uint4(a, b, c, d);
 }
 
-// one bf16 element of row r at K index `idx` of a tile image in shared memory
-__device__ __forceinline__ void st_elem(uint32_t base, int idx, int r, float v) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + (uint32_t)(idx >> 3) * 2048u + (uint32_t)r * 16u + (uint32_t)(idx & 7) * 2u),
-                 "h"(*reinterpret_cast<const unsigned short*>(&h))
-                 : "memory");
-}
-// gamma(x) of this thread's point -> gx buffer (K=64: [x(3) | sin(2^k x_d) k-major (30) | cos (30) | 0]).  The two threads
-// of a row split the ten frequency levels (half 0: k=0..4 and the raw x; half 1: k=5..9 and the zero pad): one accurate
-// sincosf per coordinate, then the double-angle recurrence.
-__device__ __forceinline__ void encode_pos_half(uint32_t gx, int r, int half, float px, float py, float pz) {
+// gamma(x) of this thread's point -> gx buffer (K=64: [x(3) | sin(2^k x_d) k-major (30) | cos (30) | 0])
+__device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float py, float pz, uint8_t* grow) {
+    float e[64];
+    e[0] = px; e[1] = py; e[2] = pz; e[63] = 0.f;
     float s[3], c[3];
     sincosf(px, &s[0], &c[0]); sincosf(py, &s[1], &c[1]); sincosf(pz, &s[2], &c[2]);
-    if (half == 0) { st_elem(gx, 0, r, px); st_elem(gx, 1, r, py); st_elem(gx, 2, r, pz); }
-    else {
-        st_elem(gx, 63, r, 0.f);
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { const float s2 = 2.0f * s[d] * c[d], c2 = fmaf(-2.0f * s[d], s[d], 1.0f); s[d] = s2; c[d] = c2; }
-    }
-    const int k0 = half * 5;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 10; ++k) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            st_elem(gx, 3 + 3 * (k0 + k) + d, r, s[d]); st_elem(gx, 33 + 3 * (k0 + k) + d, r, c[d]);
+            e[3 + 3 * k + d] = s[d]; e[33 + 3 * k + d] = c[d];
             const float s2 = 2.0f * s[d] * c[d], c2 = fmaf(-2.0f * s[d], s[d], 1.0f);   // angle doubling
             s[d] = s2; c[d] = c2;
         }
     }
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
+    }
 }
-// gamma(d) -> first 4 K-chunks of the gx buffer (K=32: [v(3) | sin (12) | cos (12) | 0 x5]); half 0: v and k=0,1; half 1: k=2,3, pad
-__device__ __forceinline__ void encode_dir_half(uint32_t gx, int r, int half, float vx, float vy, float vz) {
+// gamma(d) -> first 4 K-chunks of the gx buffer (K=32: [v(3) | sin (12) | cos (12) | 0 x5])
+__device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float vy, float vz, uint8_t* grow) {
+    float e[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) e[i] = 0.f;
+    e[0] = vx; e[1] = vy; e[2] = vz;
     float s[3], c[3];
     sincosf(vx, &s[0], &c[0]); sincosf(vy, &s[1], &c[1]); sincosf(vz, &s[2], &c[2]);
-    if (half == 0) { st_elem(gx, 0, r, vx); st_elem(gx, 1, r, vy); st_elem(gx, 2, r, vz); }
-    else {
 #pragma unroll
-        for (int i = 27; i < 32; ++i) st_elem(gx, i, r, 0.f);
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { const float s2 = 2.0f * s[d] * c[d], c2 = fmaf(-2.0f * s[d], s[d], 1.0f); s[d] = s2; c[d] = c2; }
-    }
-    const int k0 = half * 2;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            st_elem(gx, 3 + 3 * (k0 + k) + d, r, s[d]); st_elem(gx, 15 + 3 * (k0 + k) + d, r, c[d]);
+            e[3 + 3 * k + d] = s[d]; e[15 + 3 * k + d] = c[d];
             const float s2 = 2.0f * s[d] * c[d], c2 = fmaf(-2.0f * s[d], s[d], 1.0f);
             s[d] = s2; c[d] = c2;
         }
     }
+#pragma unroll
+    for (int k8 = 0; k8 < 4; ++k8) {
+        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
+    }
 }
-// materialised encodings (NeRF.forward boundary): chunks [k8_begin, k8_end) of a row of `n` floats, zero padded
-__device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __restrict__ src, int n, int k8_begin, int k8_end) {
-    for (int k8 = k8_begin; k8 < k8_end; ++k8) {
+// materialised encodings (NeRF.forward boundary): copy a row of `n` floats, zero-padded to 8*chunks
+__device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __restrict__ src, int n, int chunks, uint8_t* grow) {
+    for (int k8 = 0; k8 < chunks; ++k8) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (8 * k8 + j < n && src) ? src[8 * k8 + j] : 0.f;
-        st_chunk(gx, k8, r, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    }
-}
-// mirror chunks [k8_begin, k8_end) of row r from a shared-memory image to the stash (after the group has finished writing)
-__device__ __forceinline__ void mirror_chunks(uint32_t img, int r, int k8_begin, int k8_end, uint8_t* grow) {
-    if (!grow) return;
-    for (int k8 = k8_begin; k8 < k8_end; ++k8) {
-        uint4 v;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "r"(img + (uint32_t)k8 * 2048u + (uint32_t)r * 16u));
-        *reinterpret_cast<uint4*>(grow + (size_t)k8 * 2048) = v;
+        const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+        st_chunk(gx, k8, r, w0, w1, w2, w3);
+        st_chunk_g(grow, k8, w0, w1, w2, w3);
     }
 }
 
@@ -412,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, kEpiThreads); mbar_init(bar_acc + 8 * t, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {   // TMEM allocation (whole SM: 2 tiles x 256 fp32 columns)
@@ -506,17 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         }
     } else if (warp >= 4) {
         // ===================================== epilogue groups ===================================
-        // 8 warps per tile: warp (quarter, half) owns TMEM lanes 32*quarter.. (its warp index mod 4 == quarter, as tcgen05.ld
-        // requires) and columns [half*N/2, (half+1)*N/2) -- two resident warps per scheduler per tile hide each other's
-        // TMEM / shared-memory latencies.
-        const int t = (warp - 4) / kEpiWarpsPerTile;   // tile of the pair: 0 = A, 1 = B
-        const int wg = (warp - 4) % kEpiWarpsPerTile;
-        const int quarter = wg & 3, half = wg >> 2;
-        const int r = quarter * 32 + lane;             // accumulator row == TMEM lane == point within the tile
-        const int bar_id = 1 + t;
+        const int t = (warp - 4) >> 2;                 // tile of the pair: 0 = A, 1 = B
+        const int r = (int)threadIdx.x - 128 - t * 128; // accumulator row == TMEM lane == point within the tile
         const uint32_t act = sbase + kSmemAct + t * kActBytes, gx = sbase + kSmemGx + t * kGxBytes;
-        const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
+        const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t use = 0;
         long long w_acc = 0, w_bar = 0, t_cols = 0; const long long t_begin = clock64();
         for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -524,13 +493,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             const int64_t q = tile * TILE_M + r;
             const bool valid = tile < p.num_tiles && q < p.Q;
             const int64_t qc = valid ? q : 0;
-            // training stash: every 16-byte chunk written to smem is mirrored to the tile's stash image (coalesced stores)
-            uint8_t* stash_tile = p.stash != nullptr && tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
+            // training stash: bulk-store shared-memory images of the layer inputs (TMA engine, one elected thread)
+            const bool do_stash = p.stash != nullptr;
+            uint8_t* stash_tile = do_stash && tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
+            // row pointer into a stash block (or null): every 16-byte chunk written to smem is mirrored there
             auto srow = [&](size_t ofs) -> uint8_t* { return stash_tile ? stash_tile + ofs + (size_t)r * 16 : nullptr; };
             // ---- layer-0 input: gamma(x) ----
             float vdir[3] = {0.f, 0.f, 1.f};
             if (FROM_ENC) {
-                copy_enc_row(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 4 * half, 4 * half + 4);
+                copy_enc_row(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8, srow(kStashGx));
             } else {
                 const int64_t b = qc / p.N;
                 const float zz = valid ? p.z[qc] : 0.f;
@@ -538,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 const float px = fmaf(p.rays_d[b * 3 + 0], zm, p.rays_o[b * 3 + 0]);
                 const float py = fmaf(p.rays_d[b * 3 + 1], zm, p.rays_o[b * 3 + 1]);
                 const float pz = fmaf(p.rays_d[b * 3 + 2], zm, p.rays_o[b * 3 + 2]);
-                encode_pos_half(gx, r, half, px, py, pz);
+                encode_pos(gx, r, px, py, pz, srow(kStashGx));
                 const float* vs = p.viewdirs ? p.viewdirs : p.rays_d;
                 const float vx = vs[b * 3 + 0], vy = vs[b * 3 + 1], vz = vs[b * 3 + 2];
                 const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
@@ -546,61 +517,124 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             }
             fence_async_smem();
             mbar_arrive(bar_in + 8 * t);
-            if (stash_tile) {                              // gamma(x) image -> stash (needs both halves' elements)
-                named_bar_sync(bar_id, kEpiThreads);
-                mirror_chunks(gx, r, 4 * half, 4 * half + 4, srow(kStashGx));
-            }
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
+            const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
+            const bool want_dbg = p.dbg != nullptr;
             for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
                 const int N = layer_N(l);
-                // While the MMAs of this layer run: fetch one bias value per thread (coalesced).  Nothing inside the column loop
-                // touches global memory except the lane-held head-weight slices.
-                const int bi = half * 128 + r;
-                const float b_val = bi < N ? __ldg(tail + layer_bias_ofs(l) + bi) : 0.f;
-                if (p.cyc) mbar_wait_t(bar_acc + 8 * t, use & 1, w_acc); else mbar_wait(bar_acc + 8 * t, use & 1);
+                // While the MMAs of this layer run: fetch its bias (coalesced, one or two floats per thread) and the first
+                // lane-held slice of the head weights.  Nothing inside the column loop touches global memory.
+                const float b_lo = __ldg(tail + layer_bias_ofs(l) + r);
+                const float b_hi = N == 256 ? __ldg(tail + layer_bias_ofs(l) + 128 + r) : 0.f;
+                float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;      // l==7: w_sigma[32g+lane];  l==9: Wo[ch][32g+lane]
+                if (l == 7) hw0 = __ldg(tail + kWsigOfs + lane);
+                if (l == 9) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
+                mbar_wait_t(bar_acc + 8 * t, use & 1, w_acc);
                 tc_fence_after();
                 // group barrier 1: everyone is past the previous layer's reads of sbias
                 const long long tb0 = clock64();
-                named_bar_sync(bar_id, kEpiThreads);
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)bi), "f"(b_val) : "memory");
-                named_bar_sync(bar_id, kEpiThreads);       // group barrier 2: bias visible
+                named_bar_sync(1 + t, 128);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)r), "f"(b_lo) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 512u + 4u * (uint32_t)r), "f"(b_hi) : "memory");
+                named_bar_sync(1 + t, 128);                 // group barrier 2: bias visible
                 const long long tc0 = clock64();
                 w_bar += tc0 - tb0;
-                const int c_begin = half * (N >> 1), c_end = c_begin + (N >> 1);
+                const bool relu = l != 8;
+                const bool need_f32 = l == 7 || l == 9 || (want_dbg && l == p.dbg_layer);
+                const bool write_act = l != 9;              // next layer's A operand, in place
                 uint8_t* grow = l <= 7 ? srow(kStashH + (size_t)l * 65536) : (l == 8 ? srow(kStashFeat) : srow(kStashC));
-                float* dbg_row = (p.dbg && l == p.dbg_layer && valid) ? p.dbg + q * 256 : nullptr;
-                if (l <= 6) epi_columns<0, true>(tmem_row, c_begin, c_end, sbias, act, r, lane, tail, sig, rgb, grow, dbg_row);
-                else if (l == 7) epi_columns<1, true>(tmem_row, c_begin, c_end, sbias, act, r, lane, tail, sig, rgb, grow, dbg_row);
-                else if (l == 8) epi_columns<2, true>(tmem_row, c_begin, c_end, sbias, act, r, lane, tail, sig, rgb, grow, dbg_row);
-                else epi_columns<3, false>(tmem_row, c_begin, c_end, sbias, act, r, lane, tail, sig, rgb, grow, dbg_row);
+                // column loop, 16 accumulator columns at a time, TMEM loads double-buffered one chunk ahead
+                auto process16 = [&](const uint32_t (&v)[16], int c0) {
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 bb;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                                     : "r"(sbias + 4u * (uint32_t)(c0 + j)));
+                        f[j] = __uint_as_float(v[j]) + bb.x; f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+                        f[j + 2] = __uint_as_float(v[j + 2]) + bb.z; f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+                    }
+                    if (need_f32) {
+                        if (relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        const int src0 = c0 & 16;              // position of this chunk inside the 32-wide lane-held slice
+                        if (l == 7) {                          // sigma_out on the fp32 activations (mlps.py:265)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) sig = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), sig);
+                        }
+                        if (l == 9) {                          // color_out on the fp32 color_fc activations (mlps.py:273)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                rgb[0] = fmaf(f[j], __shfl_sync(0xffffffffu, hw0, src0 + j), rgb[0]);
+                                rgb[1] = fmaf(f[j], __shfl_sync(0xffffffffu, hw1, src0 + j), rgb[1]);
+                                rgb[2] = fmaf(f[j], __shfl_sync(0xffffffffu, hw2, src0 + j), rgb[2]);
+                            }
+                        }
+                        if (want_dbg && l == p.dbg_layer && valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) p.dbg[q * 256 + c0 + j] = f[j];
+                        }
+                    }
+                    if (write_act) {
+                        uint32_t w[8];
+                        if (relu && !need_f32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16_relu(f[2 * j], f[2 * j + 1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+                        }
+                        st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+                        st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+                    }
+                };
+                if (!(want_dbg && l == p.dbg_layer)) {
+                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                } else {
+                uint32_t va[16], vb[16];
+                tc_ld16(tmem_row, va);
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    tc_wait_ld();
+                    pin16(va);
+                    tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+                    // next 32-wide slice of the head weights (used from the next iteration on)
+                    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+                    if (l == 7 && c0 + 32 < N) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
+                    if (l == 9 && c0 + 32 < N) {
+                        n0 = __ldg(tail + kWoOfs + c0 + 32 + lane); n1 = __ldg(tail + kWoOfs + 128 + c0 + 32 + lane);
+                        n2 = __ldg(tail + kWoOfs + 256 + c0 + 32 + lane);
+                    }
+                    process16(va, c0);
+                    tc_wait_ld();
+                    pin16(vb);
+                    if (c0 + 32 < N) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
+                    process16(vb, c0 + 16);
+                    hw0 = n0; hw1 = n1; hw2 = n2;
+                }
+                }
                 t_cols += clock64() - tc0;
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
-                    if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 2 * half, 2 * half + 2);
-                    else encode_dir_half(gx, r, half, vdir[0], vdir[1], vdir[2]);
+                    if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
+                    else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
                 }
                 if (l != 9) {
                     tc_fence_before();
                     fence_async_smem();
                     mbar_arrive(bar_in + 8 * t);
                 }
-                if (l == 8 && stash_tile) {                // gamma(d) image -> stash
-                    named_bar_sync(bar_id, kEpiThreads);
-                    mirror_chunks(gx, r, 2 * half, 2 * half + 2, srow(kStashGd));
-                }
             }
-            // combine the two column halves of the head dot products through the (now idle) activation buffer
-            if (half == 1)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(act + (uint32_t)r * 16u), "f"(rgb[0]), "f"(rgb[1]), "f"(rgb[2]), "f"(sig)
-                             : "memory");
-            named_bar_sync(bar_id, kEpiThreads);
-            if (half == 0 && valid) {
-                const float4 o = lds_f4(act + (uint32_t)r * 16u);
-                reinterpret_cast<float4*>(p.raw)[q] = make_float4(rgb[0] + o.x + tail[kBoOfs], rgb[1] + o.y + tail[kBoOfs + 1],
-                                                                   rgb[2] + o.z + tail[kBoOfs + 2], sig + o.w + tail[kBsigOfs]);
+            if (valid) {
+                reinterpret_cast<float4*>(p.raw)[q] = make_float4(rgb[0] + tail[kBoOfs], rgb[1] + tail[kBoOfs + 1],
+                                                                   rgb[2] + tail[kBoOfs + 2], sig + tail[kBsigOfs]);
             }
             tc_fence_before();   // the next pair's first MMA overwrites this accumulator: order our tcgen05.ld before it
         }
-        if (p.cyc && blockIdx.x == 0 && r == 0 && half == 0) {
+        if (p.cyc && blockIdx.x == 0 && (r == 0)) {
             p.cyc[5 + 4 * t] = (unsigned long long)w_acc; p.cyc[6 + 4 * t] = (unsigned long long)w_bar;
             p.cyc[7 + 4 * t] = (unsigned long long)t_cols; p.cyc[8 + 4 * t] = (unsigned long long)(clock64() - t_begin);
         }
@@ -703,8 +737,8 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 32) {
         tc_wait_ld();
-        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         pin16(va);
+        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         float n0 = 0.f;
         if (c0 + 32 < 256) {
             if (KIND != 0) {
@@ -715,8 +749,8 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
         }
         dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, cur[0], cur[1], grow);
         tc_wait_ld();
-        tc_ld16(tmem_row + (uint32_t)(c0 + 32 < 256 ? c0 + 32 : c0), va);    // last iteration: harmless re-read
         pin16(vb);
+        if (c0 + 32 < 256) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
         dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, cur[2], cur[3], grow);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
@@ -724,7 +758,7 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
     }
 }
 
-__global__ void __launch_bounds__(kDgThreads, 1) field_dgrad_kernel(const DgradParams p) {
+__global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1230,7 +1264,7 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     tc::DgradParams dp{};
     dp.d_raw = d_raw; dp.packed = reinterpret_cast<const uint8_t*>(packed); dp.stash = ws_stash(ws); dp.dstash = ws_dstash(ws, Q);
     dp.Q = Q; dp.num_tiles = tiles;
-    tc::field_dgrad_kernel<<<(int)(pairs < num_sms() ? pairs : num_sms()), tc::kDgThreads, tc::kSmemBytes, st>>>(dp);
+    tc::field_dgrad_kernel<<<(int)(pairs < num_sms() ? pairs : num_sms()), tc::kThreads, tc::kSmemBytes, st>>>(dp);
     NSB_LAUNCH_CHECK("field_dgrad_kernel");
 
     tc::WgradParams wp{};
