@@ -196,6 +196,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// 16 ReLU'd bf16 outputs held as 8 packed words -> 16 mask bits: bit j (even column 2j) and bit 16+j (odd column 2j+1).
+// __vsetne2 gives 0x0001 per non-zero half-word; one multiply-add per word shifts it into place.
+__device__ __forceinline__ uint32_t relu_bits16(const uint32_t (&w)[8]) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __vsetne2(w[j], 0u) << j;
+    return s;
+}
+// the 0xFFFF-per-half AND mask of packed word j of a 16-column chunk, from its bit field (already shifted to bit 0)
+__device__ __forceinline__ uint32_t relu_mask_word(uint32_t bits16, int j) { return ((bits16 >> j) & 0x00010001u) * 0xFFFFu; }
+
 // ---- epilogue column loop, specialised per layer kind (branch-free inner loop) ---------------------------
 // KIND 0: bias + ReLU -> bf16 A operand (mlp.0..6)          KIND 1: same + sigma_out head on the fp32 values (mlp.7)
 // KIND 2: bias only (feature)                              KIND 3: bias + ReLU + color_out head (color_fc, N=128);
@@ -209,7 +220,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 template <int KIND, bool WRITE>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, const float4 (&bias)[4], uint32_t act, int r, float& sig,
-                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow) {
+                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow, uint32_t& mbits) {
     float f[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -239,11 +250,12 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, con
         }
         st_chunk_g(grow, (c0 >> 3), w[0], w[1], w[2], w[3]);
         st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
+        if (grow && KIND != 2) mbits = relu_bits16(w);       // training: ReLU mask bits of these 16 outputs
     }
 }
 template <int KIND, bool WRITE>
 __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                            float& sig, float (&rgb)[3], uint8_t* grow) {
+                                            float& sig, float (&rgb)[3], uint8_t* grow, uint32_t* gmask) {
     constexpr int N = KIND == 3 ? 128 : 256;
     float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;          // lane-held 32-wide slice of the head weights
     if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + lane);
@@ -267,11 +279,13 @@ __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, u
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         pin16(va);
-        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow);
+        uint32_t m0 = 0, m1 = 0;
+        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow, m0);
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)(c0 + 32 < N ? c0 + 32 : c0), va);      // last iteration: harmless re-read
         pin16(vb);
-        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow);
+        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow, m1);
+        if (gmask) gmask[c0 >> 5] = m0 | (m1 << 8);          // one mask word per 32 columns
         hw0 = n0; hw1 = n1; hw2 = n2;
     }
 }
@@ -293,7 +307,10 @@ struct FwdParams {
 //   gx (K=64) 16384 | h1..h8 (inputs of mlp.1..7 and of feature/sigma; K=256) 8 x 65536 | feat (K=256) 65536 |
 //   gd (K=32) 8192 | c (color_fc output, K=128) 32768
 constexpr size_t kStashGx = 0, kStashH = 16384, kStashFeat = kStashH + 8 * 65536, kStashGd = kStashFeat + 65536,
-                 kStashC = kStashGd + 8192, kStashTile = kStashC + 32768;   // 647,168 B / tile = 5056 B / point
+                 kStashC = kStashGd + 8192,
+                 // ReLU masks, one bit per element: slot s (0..7 = h1..h8, 8 = c), row r, 8 words (32 B per row and slot).
+                 // Word w covers columns [32w, 32w+32): bit (8*(c/16%2) + (c%16)/2) + 16*(c%2)  -- see relu_bits16().
+                 kStashMask = kStashC + 32768, kStashTile = kStashMask + 9 * 128 * 32;   // 684,032 B / tile = 5344 B / point
 // Gradient stash of one tile, written by the dgrad chain and read by wgrad (same image layout):
 //   dY_9 (d pre-activation of color_fc, K=128) 32768 | dY_8 (d feature out) | dY_7 .. dY_0 (d pre-act of mlp.7..0), 65536 each
 constexpr size_t kDstashTile = 32768 + 9 * 65536;                           // 622,592 B / tile = 4864 B / point
@@ -591,10 +608,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     }
                 };
                 if (!(want_dbg && l == p.dbg_layer)) {
-                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
-                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
-                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
-                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow);
+                    // mask slot: layers 0..7 produce h1..h8 (slots 0..7), color_fc produces c (slot 8); feature has no ReLU
+                    uint32_t* gmask = (stash_tile && l != 8)
+                                          ? reinterpret_cast<uint32_t*>(stash_tile + kStashMask + (size_t)(l == 9 ? 8 : l) * 4096 + (size_t)r * 32)
+                                          : nullptr;
+                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
+                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
+                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
+                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
                 } else {
                 uint32_t va[16], vb[16];
                 tc_ld16(tmem_row, va);
@@ -698,10 +719,11 @@ __device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 // dgrad epilogue column loop.  KIND 0: plain (feature is linear)   1: + d_sigma * w_sigma, then ReLU mask   2: ReLU mask
-// The mask is the stashed bf16 activation image itself: a half-word is non-zero iff the activation was > 0.
+// The mask comes as 8 bit words per row (one per 32 columns) written by the forward epilogue -- loaded once per layer,
+// so nothing inside the column loop waits on global memory.
 template <int KIND>
-__device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, const uint4& ma,
-                                              const uint4& mb, uint8_t* grow) {
+__device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, uint32_t bits16,
+                                              uint8_t* grow) {
     uint32_t w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -711,10 +733,7 @@ __device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, u
             b = fmaf(dsig, __shfl_sync(0xffffffffu, hw0, (c0 & 16) + 2 * j + 1), b);
         }
         w[j] = pack_bf16(a, b);
-    }
-    if (KIND != 0) {
-        w[0] &= __vcmpne2(ma.x, 0u); w[1] &= __vcmpne2(ma.y, 0u); w[2] &= __vcmpne2(ma.z, 0u); w[3] &= __vcmpne2(ma.w, 0u);
-        w[4] &= __vcmpne2(mb.x, 0u); w[5] &= __vcmpne2(mb.y, 0u); w[6] &= __vcmpne2(mb.z, 0u); w[7] &= __vcmpne2(mb.w, 0u);
+        if (KIND != 0) w[j] &= relu_mask_word(bits16, j);
     }
     st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
     st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
@@ -723,37 +742,24 @@ __device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, u
 }
 template <int KIND>
 __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                              const uint8_t* __restrict__ mask_row, float dsig, uint8_t* grow) {
+                                              const uint4& mlo, const uint4& mhi, float dsig, uint8_t* grow) {
     float hw0 = KIND == 1 ? __ldg(tail + kWsigOfs + lane) : 0.f;
-    uint4 cur[4], nxt[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { cur[j] = make_uint4(0, 0, 0, 0); nxt[j] = make_uint4(0, 0, 0, 0); }
-    if (KIND != 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = ldg16(mask_row + (size_t)j * 2048);
-    }
+    const uint32_t mw[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
     uint32_t va[16], vb[16];
     tc_ld16(tmem_row, va);
-#pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-        tc_wait_ld();
-        pin16(va);
-        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                 // fully unrolled: mask words are indexed statically
+        const int c0 = 32 * i;
         float n0 = 0.f;
-        if (c0 + 32 < 256) {
-            if (KIND != 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) nxt[j] = ldg16(mask_row + (size_t)(((c0 + 32) >> 3) + j) * 2048);
-            }
-            if (KIND == 1) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
-        }
-        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, cur[0], cur[1], grow);
+        if (KIND == 1 && i < 7) n0 = __ldg(tail + kWsigOfs + c0 + 32 + lane);
         tc_wait_ld();
+        tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
+        pin16(va);
+        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, mw[i], grow);
+        tc_wait_ld();
+        tc_ld16(tmem_row + (uint32_t)(i < 7 ? c0 + 32 : c0), va);    // last iteration: harmless re-read
         pin16(vb);
-        if (c0 + 32 < 256) tc_ld16(tmem_row + (uint32_t)c0 + 32u, va);
-        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, cur[2], cur[3], grow);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, mw[i] >> 8, grow);
         hw0 = n0;
     }
 }
@@ -846,51 +852,47 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             auto drow = [&](size_t ofs) -> uint8_t* { return ds_tile ? ds_tile + ofs + (size_t)r * 16 : nullptr; };
             // ---- prologue: d_raw -> dY_9 = (d_rgb . Wo) * (c > 0)   (color_out dgrad + color_fc ReLU mask) ----
             const float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r == 0 && tile_ok) l2_prefetch(st_tile + kStashH + 7 * 65536, 65536);      // h8: mask of the m=1 epilogue
             {
-                const uint8_t* crow = st_tile + kStashC + (size_t)r * 16;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint4 cm[8];
+                const uint8_t* mrow = st_tile + kStashMask + (size_t)r * 32;
+                const uint4 cbits = ldg16(mrow + 8 * 4096);                    // c mask (slot 8): 128 columns = 4 words
+                const uint32_t cw[4] = {cbits.x, cbits.y, cbits.z, cbits.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) cm[j] = ldg16(crow + (size_t)(half * 8 + j) * 2048);
+                for (int g = 0; g < 4; ++g) {                                  // 32 columns per lane-held slice of Wo
+                    const float w0 = __ldg(tail + kWoOfs + 32 * g + lane), w1 = __ldg(tail + kWoOfs + 128 + 32 * g + lane),
+                                w2 = __ldg(tail + kWoOfs + 256 + 32 * g + lane);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {                     // 32 columns per lane-held slice of Wo
-                        const int col0 = half * 64 + g * 32;
-                        const float w0 = __ldg(tail + kWoOfs + col0 + lane), w1 = __ldg(tail + kWoOfs + 128 + col0 + lane),
-                                    w2 = __ldg(tail + kWoOfs + 256 + col0 + lane);
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const uint32_t bits16 = cw[g] >> (8 * (c8 >> 1));          // chunk (c8/2) of this 32-column word
+                        uint32_t w[4];
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j2 = 0; j2 < 4; ++j2) {
-                                const int s0 = c8 * 8 + 2 * j2;
-                                const float ga = d.x * __shfl_sync(0xffffffffu, w0, s0) + d.y * __shfl_sync(0xffffffffu, w1, s0) +
-                                                 d.z * __shfl_sync(0xffffffffu, w2, s0);
-                                const float gb = d.x * __shfl_sync(0xffffffffu, w0, s0 + 1) + d.y * __shfl_sync(0xffffffffu, w1, s0 + 1) +
-                                                 d.z * __shfl_sync(0xffffffffu, w2, s0 + 1);
-                                w[j2] = pack_bf16(ga, gb);
-                            }
-                            const uint4 mk = cm[g * 4 + c8];
-                            w[0] &= __vcmpne2(mk.x, 0u); w[1] &= __vcmpne2(mk.y, 0u); w[2] &= __vcmpne2(mk.z, 0u); w[3] &= __vcmpne2(mk.w, 0u);
-                            st_chunk(act, half * 8 + g * 4 + c8, r, w[0], w[1], w[2], w[3]);
-                            st_chunk_g(drow(dstash_ofs(9)), half * 8 + g * 4 + c8, w[0], w[1], w[2], w[3]);
+                        for (int j2 = 0; j2 < 4; ++j2) {
+                            const int s0 = c8 * 8 + 2 * j2;
+                            const float ga = d.x * __shfl_sync(0xffffffffu, w0, s0) + d.y * __shfl_sync(0xffffffffu, w1, s0) +
+                                             d.z * __shfl_sync(0xffffffffu, w2, s0);
+                            const float gb = d.x * __shfl_sync(0xffffffffu, w0, s0 + 1) + d.y * __shfl_sync(0xffffffffu, w1, s0 + 1) +
+                                             d.z * __shfl_sync(0xffffffffu, w2, s0 + 1);
+                            w[j2] = pack_bf16(ga, gb) & relu_mask_word(bits16, 4 * (c8 & 1) + j2);
                         }
+                        st_chunk(act, g * 4 + c8, r, w[0], w[1], w[2], w[3]);
+                        st_chunk_g(drow(dstash_ofs(9)), g * 4 + c8, w[0], w[1], w[2], w[3]);
                     }
                 }
             }
             fence_async_smem();
             mbar_arrive(bar_in + 8 * t);
             for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
-                // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (stash slot 8-m)
-                const uint8_t* mask_row = st_tile + kStashH + (size_t)(m >= 1 ? 8 - m : 0) * 65536 + (size_t)r * 16;
-                if (r == 0 && tile_ok && m <= 7) l2_prefetch(st_tile + kStashH + (size_t)(7 - m) * 65536, 65536);   // next layer's mask
+                // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (mask slot 8-m)
+                uint4 mlo = make_uint4(0, 0, 0, 0), mhi = mlo;
+                if (m >= 1) {
+                    const uint8_t* mrow = st_tile + kStashMask + (size_t)(8 - m) * 4096 + (size_t)r * 32;
+                    mlo = ldg16(mrow); mhi = ldg16(mrow + 16);
+                }
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
                 uint8_t* grow = drow(dstash_ofs(8 - m));
-                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
-                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
-                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mask_row, d.w, grow);
+                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
+                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
+                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
                 tc_fence_before();
                 fence_async_smem();
                 if (m != kNumDgradLayers - 1) mbar_arrive(bar_in + 8 * t);
