@@ -908,40 +908,74 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
 }
 
 // =======================================================================================================
-// Backward, part 2: wgrad.  gW[n, k] = sum_points dY[pt, n] * X[pt, k]: both operands are the stashed tile
-// images used as MN-major tcgen05 operands (contraction over the 128 points of a tile), accumulators stay in
-// TMEM across all tiles a CTA owns and are flushed once with fp32 atomics.  CTAs are split over "jobs"
-// (layer x operand block) in proportion to their cost.  Bias grads = column sums of the dY image in smem.
+// Backward, part 2: wgrad (+ bias and head parameter grads).  gW[n, k] = sum_points dY[pt, n] * X[pt, k]: both operands
+// are stashed tile images used as MN-major tcgen05 operands (contraction over the 128 points of a tile); fp32
+// accumulators stay in TMEM across all tiles a CTA owns and are flushed once with atomics.  CTAs are split over "jobs"
+// (layer x operand block) in proportion to the bytes they stream -- the kernel is HBM-bound, so the tile images arrive
+// as 32 KB column-half pieces through a 6-slot TMA ring (always two or more pieces in flight per SM) and each MMA group
+// (dY half x X half) starts as soon as its two pieces have landed.  The four otherwise idle warps walk the same pieces in
+// shared memory for the CUDA-core reductions: bias grads (column sums of dY) and the sigma_out / color_out weight grads
+// (d_raw-weighted column sums of the h8 / c images).
 // =======================================================================================================
+struct WgPiece { uint32_t ofs; uint32_t bytes; int from_stash; int dy_half; int head; };   // dy_half: -1 (X piece) | 0 | 1
+struct WgGroup { int a_piece, b_piece, tmem_col, n; };          // A = dY piece (M = 128 features), B = X piece (N = n columns)
+enum { HEAD_NONE = 0, HEAD_SIGMA = 1, HEAD_RGB = 2 };
 struct WgradJob {
-    uint32_t dy_ofs;      // byte offset of the dY block inside a dstash tile
-    uint32_t dy_bytes;    // 32768 (128 cols) or 65536
-    uint32_t x_ofs;       // byte offset of the X block inside a stash tile
-    uint32_t x_bytes;
-    int halves;           // M halves (dY cols / 128)
-    int xcols;            // N of the MMA (64 / 256 / 32)
-    int64_t w_dst;        // float offset of gW[0, col0] in the flat grads
-    int ldw;              // row stride of gW (K_true)
-    int ncols_valid;      // columns actually present (<= xcols)
-    int64_t b_dst;        // float offset of the bias grad, or -1
+    int n_pieces; WgPiece pieces[4];
+    int n_groups; WgGroup groups[4];
+    int release_after[4];  // piece i may be released after group release_after[i] (-1: no MMA uses it)
+    int halves, xcols;     // flush geometry: M halves x N columns
+    int64_t w_dst;         // float offset of gW[0, col0] in the flat grads
+    int ldw;               // row stride of gW (K_true)
+    int ncols_valid;       // columns actually present (<= xcols)
+    int64_t b_dst;         // float offset of the bias grad, or -1
+    int64_t head_w_dst, head_b_dst;   // HEAD_SIGMA: g w_sigma[256], g b_sigma;  HEAD_RGB: g Wo[3][128], g bo[3]
     int cta_begin, cta_count;
+    uint32_t bytes_per_tile;
 };
 constexpr int kMaxJobs = 16;
 struct WgradParams {
-    const uint8_t* stash; const uint8_t* dstash; float* grads;
-    int64_t num_tiles; int num_jobs;
+    const uint8_t* stash; const uint8_t* dstash; const float* d_raw; float* grads;
+    int64_t num_tiles, Q; int num_jobs;
     WgradJob jobs[kMaxJobs];
 };
-constexpr int kWgBlock = 65536;                       // ring slot (one tile image)
-constexpr int kWgSlots = 3;
-constexpr int kWgSmemBar = kWgSlots * kWgBlock;       // 196608
+constexpr int kWgPiece = 32768;                       // ring slot: one column half of a tile image
+constexpr int kWgSlots = 6;
+constexpr int kWgSmemBar = kWgSlots * kWgPiece;       // 196608
 constexpr int kWgSmemBytes = kWgSmemBar + 256;
-constexpr int kWgThreads = 256;                       // warp 0 producer, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 bias/flush
+constexpr int kWgThreads = 256;                       // warp 0 producer, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 reductions/flush
 
 // MN-major, no-swizzle descriptor for a tile image used with the POINT index as K: SBO = stride between 8-wide
 // column groups (2048 B), LBO = stride between 8-point groups (128 B).
 __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// Column sums of one piece (chunks w4, w4+4, ... of 8 columns; this lane's rows lane, lane+32, ...):
+// KIND 0: plain sum into a0;  1: weighted by d_raw.w into a0;  2: weighted by d_raw.{x,y,z} into a0, a1, a2.
+template <int KIND>
+__device__ __forceinline__ void wg_colsum(const uint8_t* img, int nchunks, int w4, int lane, const float4 (&dr)[4], float (&a0)[4][8],
+                                          float (&a1)[4][8], float (&a2)[4][8]) {
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int c8 = w4 + 4 * ii;
+        if (c8 < nchunks) {
+#pragma unroll
+            for (int rg = 0; rg < 4; ++rg) {
+                const uint4 v = *reinterpret_cast<const uint4*>(img + (size_t)c8 * 2048 + (size_t)(rg * 32 + lane) * 16);
+                const float x[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (KIND == 0) a0[ii][j] += x[j];
+                    else if (KIND == 1) a0[ii][j] = fmaf(dr[rg].w, x[j], a0[ii][j]);
+                    else {
+                        a0[ii][j] = fmaf(dr[rg].x, x[j], a0[ii][j]); a1[ii][j] = fmaf(dr[rg].y, x[j], a1[ii][j]);
+                        a2[ii][j] = fmaf(dr[rg].z, x[j], a2[ii][j]);
+                    }
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -950,14 +984,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + kWgSmemBar, bar_empty = bar_full + 8 * kWgSlots, bar_done = bar_empty + 8 * kWgSlots;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgSmemBar + 8 * (2 * kWgSlots + 2));
-    // which job does this CTA belong to?
     int ji = 0;
     for (int j = 0; j < p.num_jobs; ++j)
         if ((int)blockIdx.x >= p.jobs[j].cta_begin && (int)blockIdx.x < p.jobs[j].cta_begin + p.jobs[j].cta_count) ji = j;
     const WgradJob& job = p.jobs[ji];
     const int part = (int)blockIdx.x - job.cta_begin;
-    const bool want_bias = job.b_dst >= 0;
     if (threadIdx.x == 0) {
+        // every slot release = one tcgen05.commit (or a plain arrive when no MMA reads the piece) + 4 reduction warps
         for (int s = 0; s < kWgSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + 4); }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -976,116 +1009,159 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
     for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) ++my_tiles;
 
     if (warp == 0) {
-        {                      // producer: per tile, the dY image then the X image, each into the next ring slot
-            uint32_t slot = 0, round = 0;
-            for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
-                for (int which = 0; which < 2; ++which) {
-                    const uint8_t* src = which == 0 ? p.dstash + (size_t)tile * kDstashTile + job.dy_ofs
-                                                    : p.stash + (size_t)tile * kStashTile + job.x_ofs;
-                    const uint32_t bytes = which == 0 ? job.dy_bytes : job.x_bytes;
-                    mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * slot, bytes);
-                        bulk_g2s(sbase + slot * kWgBlock, src, bytes, bar_full + 8 * slot);
-                    }
-                    __syncwarp();
-                    if (++slot == kWgSlots) { slot = 0; ++round; }
+        // producer: the tile's pieces in consumption order, each into the next ring slot
+        uint32_t slot = 0, round = 0;
+        for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
+            for (int i = 0; i < job.n_pieces; ++i) {
+                const WgPiece& pc = job.pieces[i];
+                const uint8_t* src = pc.from_stash ? p.stash + (size_t)tile * kStashTile + pc.ofs : p.dstash + (size_t)tile * kDstashTile + pc.ofs;
+                mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_full + 8 * slot, pc.bytes);
+                    bulk_g2s(sbase + slot * kWgPiece, src, pc.bytes, bar_full + 8 * slot);
                 }
+                __syncwarp();
+                if (++slot == kWgSlots) { slot = 0; ++round; }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {     // MMA issuer: one elected thread
             uint32_t slot = 0, round = 0;
-            const uint32_t idesc = make_idesc_mn(job.xcols);
             const uint64_t mnhi = desc_hi(128, 2048);
             bool first = true;
             for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
-                const uint32_t s_dy = slot, r_dy = round;
-                if (++slot == kWgSlots) { slot = 0; ++round; }
-                const uint32_t s_x = slot, r_x = round;
-                if (++slot == kWgSlots) { slot = 0; ++round; }
-                mbar_wait(bar_full + 8 * s_dy, r_dy & 1);
-                mbar_wait(bar_full + 8 * s_x, r_x & 1);
-                tc_fence_after();
-                const uint32_t a_lo = (sbase + s_dy * kWgBlock) >> 4, b_lo = (sbase + s_x * kWgBlock) >> 4;
-                for (int h = 0; h < job.halves; ++h) {
+                uint32_t pslot[4], pround[4];
+                for (int i = 0; i < job.n_pieces; ++i) { pslot[i] = slot; pround[i] = round; if (++slot == kWgSlots) { slot = 0; ++round; } }
+                uint32_t ready = 0;                    // bit i: piece i's full barrier has been observed
+                for (int g = 0; g < job.n_groups; ++g) {
+                    const WgGroup& gr = job.groups[g];
+                    if (!(ready >> gr.a_piece & 1)) { mbar_wait(bar_full + 8 * pslot[gr.a_piece], pround[gr.a_piece] & 1); ready |= 1u << gr.a_piece; }
+                    if (!(ready >> gr.b_piece & 1)) { mbar_wait(bar_full + 8 * pslot[gr.b_piece], pround[gr.b_piece] & 1); ready |= 1u << gr.b_piece; }
+                    tc_fence_after();
+                    const uint32_t a_lo = (sbase + pslot[gr.a_piece] * kWgPiece) >> 4, b_lo = (sbase + pslot[gr.b_piece] * kWgPiece) >> 4;
+                    const uint32_t idesc = make_idesc_mn(gr.n);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)     // K = 16 points per MMA
-                        tc_mma(tmem_base + (uint32_t)h * 256u, mnhi | (uint64_t)(a_lo + h * 2048 + ks * 16), mnhi | (uint64_t)(b_lo + ks * 16), idesc,
+                        tc_mma(tmem_base + (uint32_t)gr.tmem_col, mnhi | (uint64_t)(a_lo + ks * 16), mnhi | (uint64_t)(b_lo + ks * 16), idesc,
                                (!first || ks > 0) ? 1u : 0u);
+                    for (int i = 0; i < job.n_pieces; ++i)
+                        if (job.release_after[i] == g) tc_commit(bar_empty + 8 * pslot[i]);
                 }
+                for (int i = 0; i < job.n_pieces; ++i)      // pieces no MMA reads (head-only jobs): plain arrive
+                    if (job.release_after[i] < 0) { mbar_wait(bar_full + 8 * pslot[i], pround[i] & 1); mbar_arrive(bar_empty + 8 * pslot[i]); }
                 first = false;
-                tc_commit(bar_empty + 8 * s_dy);
-                tc_commit(bar_empty + 8 * s_x);
             }
             tc_commit(bar_done);
         }
     } else if (warp >= 4) {
-        // ---- bias grads: column sums of the dY image (lanes over points -> conflict-free 16-byte reads) ----
+        // ---- CUDA-core reductions over the pieces in shared memory (lanes over points -> conflict-free 16-byte reads) ----
         const int w4 = warp - 4;
-        float bsum[8][8];
+        float bsum[2][4][8];            // bias grads: [dY half][chunk w4+4i][8 columns]
+        float hacc[3][4][8];            // HEAD_SIGMA: [X half][chunk][8];  HEAD_RGB: [channel][chunk][8] (c = one 128-column piece)
+        float dsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bsum[i][j] = 0.f;
-        const int nchunks = job.halves * 16;            // 8-column groups in dY
+            for (int j = 0; j < 8; ++j) { bsum[0][i][j] = bsum[1][i][j] = 0.f; hacc[0][i][j] = hacc[1][i][j] = hacc[2][i][j] = 0.f; }
+        const bool want_bias = job.b_dst >= 0;
+        int job_head = HEAD_NONE;
+        for (int i = 0; i < job.n_pieces; ++i) if (job.pieces[i].head) job_head = job.pieces[i].head;
+        auto load_dr = [&](int64_t tile, float4 (&dr)[4]) {
+#pragma unroll
+            for (int rg = 0; rg < 4; ++rg) {
+                const int64_t q = tile * TILE_M + rg * 32 + lane;
+                dr[rg] = (tile < p.num_tiles && q < p.Q) ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
         {
             uint32_t slot = 0, round = 0;
+            float4 dr[4], dr_next[4];          // d_raw of this lane's four rows, prefetched one tile ahead (head jobs only)
+            if (job_head) load_dr(part, dr_next);
             for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
-                const uint32_t s_dy = slot, r_dy = round;
-                if (++slot == kWgSlots) { slot = 0; ++round; }
-                const uint32_t s_x = slot, r_x = round;
-                if (++slot == kWgSlots) { slot = 0; ++round; }
-                // pace on the ring even when there is no bias to sum: an early arrive would complete the wrong phase
-                mbar_wait(bar_full + 8 * s_dy, r_dy & 1);
-                mbar_wait(bar_full + 8 * s_x, r_x & 1);
-                if (want_bias) {
-                    const uint8_t* img = smem + s_dy * kWgBlock;
+                if (job_head) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c8 = w4 + 4 * i;
-                        if (c8 < nchunks) {
+                    for (int rg = 0; rg < 4; ++rg) dr[rg] = dr_next[rg];
+                    load_dr(tile + job.cta_count, dr_next);
+                    if (w4 == 0) {
 #pragma unroll
-                            for (int rg = 0; rg < 4; ++rg) {
-                                const uint4 v = *reinterpret_cast<const uint4*>(img + (size_t)c8 * 2048 + (size_t)(rg * 32 + lane) * 16);
-                                bsum[i][0] += bf16lo(v.x); bsum[i][1] += bf16hi(v.x); bsum[i][2] += bf16lo(v.y); bsum[i][3] += bf16hi(v.y);
-                                bsum[i][4] += bf16lo(v.z); bsum[i][5] += bf16hi(v.z); bsum[i][6] += bf16lo(v.w); bsum[i][7] += bf16hi(v.w);
-                            }
-                        }
+                        for (int rg = 0; rg < 4; ++rg) { dsum[0] += dr[rg].x; dsum[1] += dr[rg].y; dsum[2] += dr[rg].z; dsum[3] += dr[rg].w; }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(bar_empty + 8 * s_dy); mbar_arrive(bar_empty + 8 * s_x); }
-            }
-        }
-        if (want_bias && my_tiles > 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c8 = w4 + 4 * i;
-                if (c8 < nchunks) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float sum = warp_sum(bsum[i][j]);
-                        if (lane == 0) atomicAdd(p.grads + job.b_dst + c8 * 8 + j, sum);
+                int xhalf = 0;
+                for (int i = 0; i < job.n_pieces; ++i) {
+                    const WgPiece& pc = job.pieces[i];
+                    mbar_wait(bar_full + 8 * slot, round & 1);      // also paces the arrivals on the ring
+                    const uint8_t* img = smem + slot * kWgPiece;
+                    const int nchunks = (int)(pc.bytes >> 11);      // 8-column groups in this piece
+                    if (pc.dy_half == 0 && want_bias) wg_colsum<0>(img, nchunks, w4, lane, dr, bsum[0], bsum[0], bsum[0]);
+                    else if (pc.dy_half == 1 && want_bias) wg_colsum<0>(img, nchunks, w4, lane, dr, bsum[1], bsum[1], bsum[1]);
+                    if (pc.head == HEAD_SIGMA) {
+                        if (xhalf == 0) wg_colsum<1>(img, nchunks, w4, lane, dr, hacc[0], hacc[0], hacc[0]);
+                        else wg_colsum<1>(img, nchunks, w4, lane, dr, hacc[1], hacc[1], hacc[1]);
+                        ++xhalf;
+                    } else if (pc.head == HEAD_RGB) {
+                        wg_colsum<2>(img, nchunks, w4, lane, dr, hacc[0], hacc[1], hacc[2]);
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+                    if (++slot == kWgSlots) { slot = 0; ++round; }
                 }
             }
         }
-        // ---- flush: TMEM accumulators -> fp32 atomics on the flat gradient ----
         if (my_tiles > 0) {
-            mbar_wait(bar_done, 0);
-            tc_fence_after();
-            for (int h = 0; h < job.halves; ++h) {
-                const int n = h * 128 + w4 * 32 + lane;                 // output feature (row of gW)
-                const uint32_t trow = tmem_base + (uint32_t)h * 256u + ((uint32_t)(w4 * 32) << 16);
-                for (int c0 = 0; c0 < job.xcols; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(trow + (uint32_t)c0, v);
-                    tc_wait_ld();
-                    float* dst = p.grads + job.w_dst + (int64_t)n * job.ldw + c0;
+            if (want_bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < job.ncols_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float sum = warp_sum(bsum[a][ii][j]);
+                            if (lane == 0 && a < job.halves) atomicAdd(p.grads + job.b_dst + a * 128 + (w4 + 4 * ii) * 8 + j, sum);
+                        }
+            }
+            if (job_head == HEAD_SIGMA) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float sum = warp_sum(hacc[a][ii][j]);
+                            if (lane == 0) atomicAdd(p.grads + job.head_w_dst + a * 128 + (w4 + 4 * ii) * 8 + j, sum);
+                        }
+                if (w4 == 0) { const float sd = warp_sum(dsum[3]); if (lane == 0) atomicAdd(p.grads + job.head_b_dst, sd); }
+            } else if (job_head == HEAD_RGB) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float sum = warp_sum(hacc[ch][ii][j]);
+                            if (lane == 0) atomicAdd(p.grads + job.head_w_dst + ch * 128 + (w4 + 4 * ii) * 8 + j, sum);
+                        }
+                if (w4 == 0) {
+                    const float a0 = warp_sum(dsum[0]), a1 = warp_sum(dsum[1]), a2 = warp_sum(dsum[2]);
+                    if (lane == 0) { atomicAdd(p.grads + job.head_b_dst, a0); atomicAdd(p.grads + job.head_b_dst + 1, a1); atomicAdd(p.grads + job.head_b_dst + 2, a2); }
+                }
+            }
+            // ---- flush: TMEM accumulators -> fp32 atomics on the flat gradient ----
+            if (job.n_groups > 0) {
+                mbar_wait(bar_done, 0);
+                tc_fence_after();
+                for (int h = 0; h < job.halves; ++h) {
+                    const int n = h * 128 + w4 * 32 + lane;                 // output feature (row of gW)
+                    const uint32_t trow = tmem_base + (uint32_t)h * 256u + ((uint32_t)(w4 * 32) << 16);
+                    for (int c0 = 0; c0 < job.xcols; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld32(trow + (uint32_t)c0, v);
+                        tc_wait_ld();
+                        float* dst = p.grads + job.w_dst + (int64_t)n * job.ldw + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < job.ncols_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    }
                 }
             }
         }
@@ -1095,78 +1171,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
-// =======================================================================================================
-// Backward, part 3: head parameter grads on CUDA cores (fp32 accumulate):
-//   g w_sigma[j] = sum d_sigma * h8[., j];  g b_sigma;  g Wo[ch, j] = sum d_rgb[ch] * c[., j];  g bo
-// Warps own 8-column groups of the stashed h8 / c images; lanes run over points (coalesced 16-byte loads).
-// =======================================================================================================
-__global__ void __launch_bounds__(256) field_head_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict__ stash,
-                                                              float* __restrict__ g_wsig, float* __restrict__ g_bsig,
-                                                              float* __restrict__ g_wo, float* __restrict__ g_bo, int64_t Q,
-                                                              int64_t num_tiles) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float hs[4][8], cs[2][3][8], bs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hs[i][j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cs[i][ch][j] = 0.f;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const uint8_t* st = stash + (size_t)tile * kStashTile;
-#pragma unroll
-        for (int rg = 0; rg < 4; ++rg) {
-            const int r = rg * 32 + lane;
-            const int64_t q = tile * TILE_M + r;
-            const float4 d = q < Q ? __ldg(reinterpret_cast<const float4*>(d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (warp == 0) { bs[0] += d.x; bs[1] += d.y; bs[2] += d.z; bs[3] += d.w; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {          // h8 chunks warp, warp+8, warp+16, warp+24
-                const uint4 v = ldg16(st + kStashH + 7 * 65536 + (size_t)(warp + 8 * i) * 2048 + (size_t)r * 16);
-                hs[i][0] = fmaf(d.w, bf16lo(v.x), hs[i][0]); hs[i][1] = fmaf(d.w, bf16hi(v.x), hs[i][1]);
-                hs[i][2] = fmaf(d.w, bf16lo(v.y), hs[i][2]); hs[i][3] = fmaf(d.w, bf16hi(v.y), hs[i][3]);
-                hs[i][4] = fmaf(d.w, bf16lo(v.z), hs[i][4]); hs[i][5] = fmaf(d.w, bf16hi(v.z), hs[i][5]);
-                hs[i][6] = fmaf(d.w, bf16lo(v.w), hs[i][6]); hs[i][7] = fmaf(d.w, bf16hi(v.w), hs[i][7]);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {          // c chunks warp, warp+8
-                const uint4 v = ldg16(st + kStashC + (size_t)(warp + 8 * i) * 2048 + (size_t)r * 16);
-                const float c[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    cs[i][0][j] = fmaf(d.x, c[j], cs[i][0][j]); cs[i][1][j] = fmaf(d.y, c[j], cs[i][1][j]);
-                    cs[i][2][j] = fmaf(d.z, c[j], cs[i][2][j]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float v = warp_sum(hs[i][j]);
-            if (lane == 0) atomicAdd(g_wsig + (warp + 8 * i) * 8 + j, v);
-        }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float v = warp_sum(cs[i][ch][j]);
-                if (lane == 0) atomicAdd(g_wo + ch * 128 + (warp + 8 * i) * 8 + j, v);
-            }
-    if (warp == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bs[j] = warp_sum(bs[j]);
-        if (lane == 0) { atomicAdd(g_bo, bs[0]); atomicAdd(g_bo + 1, bs[1]); atomicAdd(g_bo + 2, bs[2]); atomicAdd(g_bsig, bs[3]); }
     }
 }
 
@@ -1270,31 +1274,62 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     NSB_LAUNCH_CHECK("field_dgrad_kernel");
 
     tc::WgradParams wp{};
-    wp.stash = ws_stash(ws); wp.dstash = ws_dstash(ws, Q); wp.grads = grads; wp.num_tiles = tiles;
+    wp.stash = ws_stash(ws); wp.dstash = ws_dstash(ws, Q); wp.d_raw = d_raw; wp.grads = grads; wp.num_tiles = tiles; wp.Q = Q;
     int nj = 0;
-    auto add = [&](int k, size_t x_ofs, uint32_t x_bytes, int xcols, int pl, int col0, int valid, bool bias) {
+    // one job = gW block (dY_k columns) x (X block); pieces are 32 KB column halves in consumption order
+    auto add = [&](int k, size_t x_ofs, int xcols, int pl, int col0, int valid, bool bias, int head) {
         const LayerDesc d = layer_desc(pl);
         tc::WgradJob& j = wp.jobs[nj++];
-        j.dy_ofs = (uint32_t)tc::dstash_ofs(k); j.dy_bytes = k == 9 ? 32768u : 65536u; j.halves = k == 9 ? 1 : 2;
-        j.x_ofs = (uint32_t)x_ofs; j.x_bytes = x_bytes; j.xcols = xcols;
+        j = tc::WgradJob{};
+        const int halves = k == 9 ? 1 : 2;
+        const uint32_t dy = (uint32_t)tc::dstash_ofs(k);
+        const uint32_t xb = (uint32_t)xcols * 256u;                 // bytes of the X block (xcols/8 chunks x 2048)
+        auto piece = [&](uint32_t ofs, uint32_t bytes, int from_stash, int dy_half, int hd) {
+            j.pieces[j.n_pieces] = tc::WgPiece{ofs, bytes, from_stash, dy_half, hd}; j.release_after[j.n_pieces] = -1; return j.n_pieces++;
+        };
+        auto group = [&](int a, int b, int col, int n) {
+            j.groups[j.n_groups] = tc::WgGroup{a, b, col, n}; j.release_after[a] = j.n_groups; j.release_after[b] = j.n_groups; ++j.n_groups;
+        };
+        const int a0 = piece(dy, 32768, 0, 0, 0);
+        if (xcols == 256) {
+            const int b0 = piece((uint32_t)x_ofs, 32768, 1, -1, head), b1 = piece((uint32_t)x_ofs + 32768, 32768, 1, -1, head);
+            group(a0, b0, 0, 128); group(a0, b1, 128, 128);
+            if (halves == 2) { const int a1 = piece(dy + 32768, 32768, 0, 1, 0); group(a1, b0, 256, 128); group(a1, b1, 384, 128); }
+        } else {
+            const int b0 = piece((uint32_t)x_ofs, xb, 1, -1, head);
+            group(a0, b0, 0, xcols);
+            if (halves == 2) { const int a1 = piece(dy + 32768, 32768, 0, 1, 0); group(a1, b0, 256, xcols); }
+        }
+        j.halves = halves; j.xcols = xcols;
         j.w_dst = d.w_off + col0; j.ldw = d.K; j.ncols_valid = valid; j.b_dst = bias ? d.b_off : -1;
+        if (head == tc::HEAD_SIGMA) { const LayerDesc ds = layer_desc(9); j.head_w_dst = ds.w_off; j.head_b_dst = ds.b_off; }
+        j.bytes_per_tile = 0;
+        for (int i = 0; i < j.n_pieces; ++i) j.bytes_per_tile += j.pieces[i].bytes;
     };
-    add(0, tc::kStashGx, 16384, 64, 0, 0, 63, true);
+    add(0, tc::kStashGx, 64, 0, 0, 63, true, 0);
     for (int l = 1; l <= 7; ++l) {
-        add(l, tc::kStashH + (size_t)(l - 1) * 65536, 65536, 256, l, 0, 256, true);
-        if (l == 4) add(4, tc::kStashGx, 16384, 64, 4, 256, 63, false);
+        add(l, tc::kStashH + (size_t)(l - 1) * 65536, 256, l, 0, 256, true, 0);
+        if (l == 4) add(4, tc::kStashGx, 64, 4, 256, 63, false, 0);
     }
-    add(8, tc::kStashH + 7 * 65536, 65536, 256, 8, 0, 256, true);           // feature
-    add(9, tc::kStashFeat, 65536, 256, 10, 0, 256, true);                   // color_fc [feat | .]
-    add(9, tc::kStashGd, 8192, 32, 10, 256, 27, false);                     // color_fc [. | gamma(d)]
+    add(8, tc::kStashH + 7 * 65536, 256, 8, 0, 256, true, tc::HEAD_SIGMA);      // feature; its X = h8 also feeds g w_sigma
+    add(9, tc::kStashFeat, 256, 10, 0, 256, true, 0);                           // color_fc [feat | .]
+    add(9, tc::kStashGd, 32, 10, 256, 27, false, 0);                            // color_fc [. | gamma(d)]
+    {   // color_out: g Wo = d_rgb^T c, g bo -- CUDA-core job over the c image, no MMA
+        tc::WgradJob& j = wp.jobs[nj++];
+        j = tc::WgradJob{};
+        j.pieces[0] = tc::WgPiece{(uint32_t)tc::kStashC, 32768, 1, -1, tc::HEAD_RGB}; j.release_after[0] = -1; j.n_pieces = 1;
+        const LayerDesc dc = layer_desc(11);
+        j.head_w_dst = dc.w_off; j.head_b_dst = dc.b_off; j.b_dst = -1;
+        j.bytes_per_tile = 3 * (32768 + 2048);      // CUDA-core bound: measured best at ~3x its byte share
+    }
     wp.num_jobs = nj;
     // CTAs per job in proportion to the bytes a tile costs (the kernel is HBM-bound), at least one each
     const int total = num_sms();
     double sum = 0;
-    for (int i = 0; i < nj; ++i) sum += wp.jobs[i].dy_bytes + wp.jobs[i].x_bytes;
+    for (int i = 0; i < nj; ++i) sum += wp.jobs[i].bytes_per_tile;
     int used = 0;
     for (int i = 0; i < nj; ++i) {
-        int c = (int)((wp.jobs[i].dy_bytes + wp.jobs[i].x_bytes) / sum * total);
+        int c = (int)(wp.jobs[i].bytes_per_tile / sum * total);
         if (c < 1) c = 1;
         if ((int64_t)c > tiles) c = (int)tiles;
         wp.jobs[i].cta_count = c; used += c;
@@ -1307,12 +1342,6 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     for (int i = 0; i < nj; ++i) { wp.jobs[i].cta_begin = begin; begin += wp.jobs[i].cta_count; }
     tc::field_wgrad_kernel<<<begin, tc::kWgThreads, tc::kWgSmemBytes, st>>>(wp);
     NSB_LAUNCH_CHECK("field_wgrad_kernel");
-
-    const LayerDesc ds = layer_desc(9), dc = layer_desc(11);
-    const int hg = (int)(tiles < 2 * (int64_t)num_sms() ? tiles : 2 * (int64_t)num_sms());
-    tc::field_head_grad_kernel<<<hg, 256, 0, st>>>(d_raw, ws_stash(ws), grads + ds.w_off, grads + ds.b_off, grads + dc.w_off,
-                                                   grads + dc.b_off, Q, tiles);
-    NSB_LAUNCH_CHECK("field_head_grad_kernel");
     return NSB_OK;
 }
 
