@@ -218,9 +218,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-template <int KIND, bool WRITE>
+template <int KIND, bool MASK>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, const float4 (&bias)[4], uint32_t act, int r, float& sig,
-                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint8_t* grow, uint32_t& mbits) {
+                                            float (&rgb)[3], float hw0, float hw1, float hw2, uint32_t& mbits) {
     float f[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -240,26 +240,25 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, con
             }
         }
     }
-    if (WRITE || grow) {
+    if (KIND != 3 || MASK) {          // color_fc output goes to shared memory only for the training stash
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = KIND == 0 ? pack_bf16_relu(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
-        if (WRITE) {
-            st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
-            st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
-        }
-        st_chunk_g(grow, (c0 >> 3), w[0], w[1], w[2], w[3]);
-        st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
-        if (grow && KIND != 2) mbits = relu_bits16(w);       // training: ReLU mask bits of these 16 outputs
+        st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
+        st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
+        if (KIND != 2 && MASK) mbits = relu_bits16(w);            // training: ReLU mask bits of these 16 outputs
     }
 }
-template <int KIND, bool WRITE>
+// MASK = training: mask words kept in registers and written once after the loop to gmask (this row's 32 B of the layer's
+// mask slot; null for rows of a tile past the end)
+template <int KIND, bool MASK>
 __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                            float& sig, float (&rgb)[3], uint8_t* grow, uint32_t* gmask) {
+                                            float& sig, float (&rgb)[3], uint32_t* gmask) {
     constexpr int N = KIND == 3 ? 128 : 256;
     float hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;          // lane-held 32-wide slice of the head weights
     if (KIND == 1) hw0 = __ldg(tail + kWsigOfs + lane);
     if (KIND == 3) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
+    uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     uint32_t va[16], vb[16];
     tc_ld16(tmem_row, va);
 #pragma unroll 1
@@ -280,13 +279,21 @@ __device__ __forceinline__ void epi_columns(uint32_t tmem_row, uint32_t sbias, u
         tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         pin16(va);
         uint32_t m0 = 0, m1 = 0;
-        epi_chunk16<KIND, WRITE>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, grow, m0);
+        epi_chunk16<KIND, MASK>(va, c0, ba, act, r, sig, rgb, hw0, hw1, hw2, m0);
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)(c0 + 32 < N ? c0 + 32 : c0), va);      // last iteration: harmless re-read
         pin16(vb);
-        epi_chunk16<KIND, WRITE>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, grow, m1);
-        if (gmask) gmask[c0 >> 5] = m0 | (m1 << 8);          // one mask word per 32 columns
+        epi_chunk16<KIND, MASK>(vb, c0 + 16, bb, act, r, sig, rgb, hw0, hw1, hw2, m1);
+        if (MASK) {                                       // one mask word per 32 columns, kept in registers until the end
+            const uint32_t m = m0 | (m1 << 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mw[k] = (c0 >> 5) == k ? m : mw[k];
+        }
         hw0 = n0; hw1 = n1; hw2 = n2;
+    }
+    if (MASK && gmask) {
+        reinterpret_cast<uint4*>(gmask)[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        reinterpret_cast<uint4*>(gmask)[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
     }
 }
 
@@ -319,6 +326,34 @@ __host__ __device__ inline size_t dstash_ofs(int k) { return k == 9 ? 0 : 32768 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// ---- operand hand-off (epilogue group -> MMA issuer) and stash write-out --------------------------------
+// Two things must not be done by the 128 epilogue threads themselves:
+//  * the generic->async proxy fence that tcgen05.mma needs before it reads an A operand written with st.shared
+//    (ptxas emits MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC for it, and the MEMBAR waits for every memory operation the thread
+//    has in flight), and
+//  * the stash stores to global memory: any st.global inside the TMEM column loop -- even one 4-byte store per 32
+//    columns -- stretched the loop from ~2.9k to ~5.2k cycles per layer (measured with the per-role cycle counters),
+//    which made the training forward 1.6x slower than the same kernel without a stash.
+// So the epilogue threads only write shared memory and bar.arrive on a named barrier; a helper warp per tile (warps 2, 3:
+// no stores of their own) waits on that barrier, issues the proxy fence, arrives on the MMA issuer's mbarrier and lets the
+// TMA engine copy the finished tile image to the stash (cp.async.bulk shared -> global).  Once the engine has read the
+// tile the helper releases the group's "tile may be overwritten" barrier (named barrier 1+t, 128 + 32 threads).
+constexpr int kHandoffBar = 3;          // named barriers 3 (tile A) and 4 (tile B): 128 arrivals + the helper warp
+__device__ __forceinline__ void handoff_signal(int t) {
+    tc_fence_before();
+    named_bar_arrive(kHandoffBar + t, 160);
+}
+// helper side of one event: returns after the fence; lane 0 then arrives / stores
+__device__ __forceinline__ void handoff_wait(int t) {
+    named_bar_sync(kHandoffBar + t, 160);
+    tc_fence_after();
+    fence_async_smem();
+    tc_fence_before();
+}
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // write 8 consecutive K elements (one 16-byte core-matrix row) of row r at K-chunk `k8`
 __device__ __forceinline__ void st_chunk(uint32_t base, int k8, int r, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -393,7 +428,8 @@ __device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __
     }
 }
 
-template <bool FROM_ENC>
+// STASH = training: the kernel also writes the stash (p.stash) that the backward kernels read
+template <bool FROM_ENC, bool STASH>
 __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -405,7 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
+        // inference (no stash): the 128 epilogue threads fence and arrive themselves; training: the tile's helper warp does
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, STASH ? 1 : 128); mbar_init(bar_acc + 8 * t, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {   // TMEM allocation (whole SM: 2 tiles x 256 fp32 columns)
@@ -497,6 +534,33 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 p.cyc[2] = (unsigned long long)w_in; p.cyc[3] = (unsigned long long)w_full; p.cyc[4] = (unsigned long long)(clock64() - t_begin);
             }
         }
+    } else if (STASH && (warp == 2 || warp == 3)) {
+        // ============================ operand hand-off + stash write-out, one warp per tile ======================
+        // events per pair: e0 = layer-0 input encoded; e1..e9 = output of layer e-1 in the activation tile (next A operand;
+        // training: image of h_{e} / feat -> stash); training only: e10 = c (color_fc output) -> stash, feeds no MMA
+        const int t = warp - 2;
+        const uint32_t act = sbase + kSmemAct + t * kActBytes;
+        const int n_events = kNumMmaLayers + 1;
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + t;
+            uint8_t* stash_tile = tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
+            for (int e = 0; e < n_events; ++e) {
+                handoff_wait(t);
+                if (lane == 0) {
+                    if (e < kNumMmaLayers) mbar_arrive(bar_in + 8 * t);
+                    if (stash_tile && e >= 1) {
+                        const int l = e - 1;
+                        const size_t ofs = l <= 7 ? kStashH + (size_t)l * 65536 : (l == 8 ? kStashFeat : kStashC);
+                        bulk_s2g(stash_tile + ofs, act, l == 9 ? 32768u : 65536u);
+                        bulk_commit();
+                        bulk_wait_read0();          // the engine has read the tile: it may be overwritten
+                    }
+                }
+                __syncwarp();
+                if (e < kNumMmaLayers) named_bar_arrive(1 + t, 160);      // release for the epilogue of layer e
+            }
+        }
+        if (lane == 0) bulk_wait_all0();
     } else if (warp >= 4) {
         // ===================================== epilogue groups ===================================
         const int t = (warp - 4) >> 2;                 // tile of the pair: 0 = A, 1 = B
@@ -510,8 +574,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
             const int64_t q = tile * TILE_M + r;
             const bool valid = tile < p.num_tiles && q < p.Q;
             const int64_t qc = valid ? q : 0;
-            // training stash: bulk-store shared-memory images of the layer inputs (TMA engine, one elected thread)
-            const bool do_stash = p.stash != nullptr;
+            // training stash: gamma(x), gamma(d) and the mask words are stored from here; the activation tiles by the helper warp
+            constexpr bool do_stash = STASH;
             uint8_t* stash_tile = do_stash && tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
             // row pointer into a stash block (or null): every 16-byte chunk written to smem is mirrored there
             auto srow = [&](size_t ofs) -> uint8_t* { return stash_tile ? stash_tile + ofs + (size_t)r * 16 : nullptr; };
@@ -532,8 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
                 vdir[0] = vx * inv; vdir[1] = vy * inv; vdir[2] = vz * inv;
             }
-            fence_async_smem();
-            mbar_arrive(bar_in + 8 * t);
+            if (do_stash) handoff_signal(t); else { fence_async_smem(); mbar_arrive(bar_in + 8 * t); }
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
             const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
             const bool want_dbg = p.dbg != nullptr;
@@ -548,9 +611,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 if (l == 9) { hw0 = __ldg(tail + kWoOfs + lane); hw1 = __ldg(tail + kWoOfs + 128 + lane); hw2 = __ldg(tail + kWoOfs + 256 + lane); }
                 mbar_wait_t(bar_acc + 8 * t, use & 1, w_acc);
                 tc_fence_after();
-                // group barrier 1: everyone is past the previous layer's reads of sbias
+                // group barrier 1: everyone is past the previous layer's reads of sbias, and the helper warp has released the
+                // activation tile (its previous image has been read by the stash copy)
                 const long long tb0 = clock64();
-                named_bar_sync(1 + t, 128);
+                named_bar_sync(1 + t, do_stash ? 160 : 128);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * (uint32_t)r), "f"(b_lo) : "memory");
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 512u + 4u * (uint32_t)r), "f"(b_hi) : "memory");
                 named_bar_sync(1 + t, 128);                 // group barrier 2: bias visible
@@ -559,7 +623,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 const bool relu = l != 8;
                 const bool need_f32 = l == 7 || l == 9 || (want_dbg && l == p.dbg_layer);
                 const bool write_act = l != 9;              // next layer's A operand, in place
-                uint8_t* grow = l <= 7 ? srow(kStashH + (size_t)l * 65536) : (l == 8 ? srow(kStashFeat) : srow(kStashC));
                 // column loop, 16 accumulator columns at a time, TMEM loads double-buffered one chunk ahead
                 auto process16 = [&](const uint32_t (&v)[16], int c0) {
                     float f[16];
@@ -612,10 +675,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     uint32_t* gmask = (stash_tile && l != 8)
                                           ? reinterpret_cast<uint32_t*>(stash_tile + kStashMask + (size_t)(l == 9 ? 8 : l) * 4096 + (size_t)r * 32)
                                           : nullptr;
-                    if (l <= 6) epi_columns<0, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
-                    else if (l == 7) epi_columns<1, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
-                    else if (l == 8) epi_columns<2, true>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
-                    else epi_columns<3, false>(tmem_row, sbias, act, r, lane, tail, sig, rgb, grow, gmask);
+                    if (l <= 6) epi_columns<0, STASH>(tmem_row, sbias, act, r, lane, tail, sig, rgb, gmask);
+                    else if (l == 7) epi_columns<1, STASH>(tmem_row, sbias, act, r, lane, tail, sig, rgb, gmask);
+                    else if (l == 8) epi_columns<2, STASH>(tmem_row, sbias, act, r, lane, tail, sig, rgb, gmask);
+                    else epi_columns<3, STASH>(tmem_row, sbias, act, r, lane, tail, sig, rgb, gmask);
                 } else {
                 uint32_t va[16], vb[16];
                 tc_ld16(tmem_row, va);
@@ -643,11 +706,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
                     else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
                 }
-                if (l != 9) {
-                    tc_fence_before();
-                    fence_async_smem();
-                    mbar_arrive(bar_in + 8 * t);
-                }
+                if (do_stash) handoff_signal(t);                // l == 9: only the stash copy of c waits for it
+                else if (l != 9) { tc_fence_before(); fence_async_smem(); mbar_arrive(bar_in + 8 * t); }
             }
             if (valid) {
                 reinterpret_cast<float4*>(p.raw)[q] = make_float4(rgb[0] + tail[kBoOfs], rgb[1] + tail[kBoOfs + 1],
@@ -722,8 +782,7 @@ __device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
 // The mask comes as 8 bit words per row (one per 32 columns) written by the forward epilogue -- loaded once per layer,
 // so nothing inside the column loop waits on global memory.
 template <int KIND>
-__device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, uint32_t bits16,
-                                              uint8_t* grow) {
+__device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, uint32_t act, int r, float dsig, float hw0, uint32_t bits16) {
     uint32_t w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -737,12 +796,10 @@ __device__ __forceinline__ void dgrad_chunk16(const uint32_t (&v)[16], int c0, u
     }
     st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
     st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
-    st_chunk_g(grow, (c0 >> 3), w[0], w[1], w[2], w[3]);
-    st_chunk_g(grow, (c0 >> 3) + 1, w[4], w[5], w[6], w[7]);
 }
 template <int KIND>
 __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, int r, int lane, const float* __restrict__ tail,
-                                              const uint4& mlo, const uint4& mhi, float dsig, uint8_t* grow) {
+                                              const uint4& mlo, const uint4& mhi, float dsig) {
     float hw0 = KIND == 1 ? __ldg(tail + kWsigOfs + lane) : 0.f;
     const uint32_t mw[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
     uint32_t va[16], vb[16];
@@ -755,25 +812,30 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)c0 + 16u, vb);
         pin16(va);
-        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, mw[i], grow);
+        dgrad_chunk16<KIND>(va, c0, act, r, dsig, hw0, mw[i]);
         tc_wait_ld();
         tc_ld16(tmem_row + (uint32_t)(i < 7 ? c0 + 32 : c0), va);    // last iteration: harmless re-read
         pin16(vb);
-        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, mw[i] >> 8, grow);
+        dgrad_chunk16<KIND>(vb, c0 + 16, act, r, dsig, hw0, mw[i] >> 8);
         hw0 = n0;
     }
 }
 
+// the dgrad chain has no gamma(x)/gamma(d) operand, so its weight ring takes that space too: 6 stages instead of 4
+constexpr int kDgStages = 6;
+constexpr int kDgSmemRing = kSmemGx;
+static_assert(kDgSmemRing + kDgStages * kStageBytes == kSmemBar, "dgrad ring must end at the barrier block");
+static_assert(8 * (2 * kDgStages + 4) + 4 <= 256, "barrier block overflow");
 __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages, bar_in = bar_empty + 8 * kStages,
+    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kDgStages, bar_in = bar_empty + 8 * kDgStages,
                    bar_acc = bar_in + 16;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (2 * kDgStages + 4));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
+        for (int s = 0; s < kDgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 1); mbar_init(bar_acc + 8 * t, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -801,10 +863,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
+                            bulk_g2s(sbase + kDgSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
                         }
                         __syncwarp();
-                        if (++stage == kStages) { stage = 0; ++round; }
+                        if (++stage == kDgStages) { stage = 0; ++round; }
                     }
                 }
             }
@@ -814,7 +876,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             uint32_t stage = 0, round = 0, use = 0;
             const uint32_t idesc = make_idesc(256);
             const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
-            const uint32_t ring_lo = (sbase + kSmemRing) >> 4;
+            const uint32_t ring_lo = (sbase + kDgSmemRing) >> 4;
             for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                     const int ns = m == 0 ? 4 : 8;
@@ -830,12 +892,38 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                             tc_mma(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + 512u), idesc, 1u);
                             if (s == ns - 1) tc_commit(bar_acc + 8 * t);
                             tc_commit(bar_empty + 8 * stage);
-                            if (++stage == kStages) { stage = 0; ++round; }
+                            if (++stage == kDgStages) { stage = 0; ++round; }
                         }
                     }
                 }
             }
         }
+    } else if (warp == 2 || warp == 3) {
+        // operand hand-off + gradient-stash write-out, one warp per tile.  Events per pair: e0 = dY_9 (prologue, 32 KB);
+        // e1..e9 = output of chain step e-1 = dY_{8-(e-1)} (64 KB); the last one feeds no MMA.  After every event the group
+        // gets its "tile may be overwritten" release (the very first write of the kernel is released up front).
+        const int t = warp - 2;
+        const uint32_t act = sbase + kSmemAct + t * kActBytes;
+        named_bar_arrive(1 + t, 160);
+        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + t;
+            uint8_t* ds_tile = tile < p.num_tiles ? p.dstash + (size_t)tile * kDstashTile : nullptr;
+            const bool last_pair = pair + gridDim.x >= num_pairs;
+            for (int e = 0; e <= kNumDgradLayers; ++e) {
+                handoff_wait(t);
+                if (lane == 0) {
+                    if (e < kNumDgradLayers) mbar_arrive(bar_in + 8 * t);
+                    if (ds_tile) {
+                        bulk_s2g(ds_tile + (e == 0 ? dstash_ofs(9) : dstash_ofs(8 - (e - 1))), act, e == 0 ? 32768u : 65536u);
+                        bulk_commit();
+                        bulk_wait_read0();
+                    }
+                }
+                __syncwarp();
+                if (!(last_pair && e == kNumDgradLayers)) named_bar_arrive(1 + t, 160);
+            }
+        }
+        if (lane == 0) bulk_wait_all0();
     } else if (warp >= 4) {
         const int t = (warp - 4) >> 2;
         const int r = (int)threadIdx.x - 128 - t * 128;
@@ -848,10 +936,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             const bool tile_ok = tile < p.num_tiles;
             const bool valid = tile_ok && q < p.Q;
             const uint8_t* st_tile = p.stash + (size_t)(tile_ok ? tile : 0) * kStashTile;
-            uint8_t* ds_tile = tile_ok ? p.dstash + (size_t)tile * kDstashTile : nullptr;
-            auto drow = [&](size_t ofs) -> uint8_t* { return ds_tile ? ds_tile + ofs + (size_t)r * 16 : nullptr; };
             // ---- prologue: d_raw -> dY_9 = (d_rgb . Wo) * (c > 0)   (color_out dgrad + color_fc ReLU mask) ----
             const float4 d = valid ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            named_bar_sync(1 + t, 160);            // the previous pair's last dY image has been copied out of the tile
             {
                 const uint8_t* mrow = st_tile + kStashMask + (size_t)r * 32;
                 const uint4 cbits = ldg16(mrow + 8 * 4096);                    // c mask (slot 8): 128 columns = 4 words
@@ -874,12 +961,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                             w[j2] = pack_bf16(ga, gb) & relu_mask_word(bits16, 4 * (c8 & 1) + j2);
                         }
                         st_chunk(act, g * 4 + c8, r, w[0], w[1], w[2], w[3]);
-                        st_chunk_g(drow(dstash_ofs(9)), g * 4 + c8, w[0], w[1], w[2], w[3]);
                     }
                 }
             }
-            fence_async_smem();
-            mbar_arrive(bar_in + 8 * t);
+            handoff_signal(t);
             for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                 // m == 0: no mask (feature is linear).  m >= 1: output is d(h_{9-m}), masked by h_{9-m} > 0 (mask slot 8-m)
                 uint4 mlo = make_uint4(0, 0, 0, 0), mhi = mlo;
@@ -889,13 +974,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
                 }
                 mbar_wait(bar_acc + 8 * t, use & 1);
                 tc_fence_after();
-                uint8_t* grow = drow(dstash_ofs(8 - m));
-                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
-                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
-                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mlo, mhi, d.w, grow);
-                tc_fence_before();
-                fence_async_smem();
-                if (m != kNumDgradLayers - 1) mbar_arrive(bar_in + 8 * t);
+                named_bar_sync(1 + t, 160);        // the tile's previous image (this step's A operand) has been copied out
+                if (m == 0) dgrad_columns<0>(tmem_row, act, r, lane, tail, mlo, mhi, d.w);
+                else if (m == 1) dgrad_columns<1>(tmem_row, act, r, lane, tail, mlo, mhi, d.w);
+                else dgrad_columns<2>(tmem_row, act, r, lane, tail, mlo, mhi, d.w);
+                handoff_signal(t);                 // the last step's image feeds no MMA, only the stash copy
             }
         }
     }
@@ -1223,14 +1306,16 @@ static int launch_fwd(tc::FwdParams& p, cudaStream_t st) {
     NSB_TRY(check_arch());
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(tc::field_fwd_kernel<FROM_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::field_fwd_kernel<FROM_ENC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::field_fwd_kernel<FROM_ENC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(field_fwd_kernel)");
         attr_set = true;
     }
     p.num_tiles = cdiv(p.Q, tc::TILE_M);
     const int64_t pairs = (p.num_tiles + 1) / 2;
     const int grid = (int)(pairs < num_sms() ? pairs : num_sms());
-    tc::field_fwd_kernel<FROM_ENC><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    if (p.stash) tc::field_fwd_kernel<FROM_ENC, true><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    else tc::field_fwd_kernel<FROM_ENC, false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     NSB_LAUNCH_CHECK("field_fwd_kernel");
     return NSB_OK;
 }
@@ -1349,7 +1434,11 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 int tc_debug_layer(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,
                    const void* packed, float* raw, float* dbg, int layer, int64_t B, int N, cudaStream_t st) {
     tc::FwdParams p{};
-    if (layer < 0) { p.cyc = reinterpret_cast<unsigned long long*>(dbg); dbg = nullptr; }   // layer -1: cycle counters instead
+    if (layer < 0) {   // layer -1: cycle counters instead; layer -2: same with the training stash written behind the 16 counters
+        p.cyc = reinterpret_cast<unsigned long long*>(dbg);
+        if (layer == -2) p.stash = reinterpret_cast<uint8_t*>(dbg) + 128;
+        dbg = nullptr;
+    }
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.ray_norm = ray_norm; p.viewdirs = viewdirs;
     p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw; p.dbg = dbg; p.dbg_layer = layer;
     p.Q = B * (int64_t)N; p.N = N;

@@ -6,16 +6,17 @@ import nerf_sandbox_b200 as nsb
 from nerf_sandbox_b200 import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 N = 192; dev = "cuda"; L = _lib.lib()
+STASH = len(sys.argv) > 2 and sys.argv[2] == "stash"
 fn = L.nsb_debug_tc_layer; fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
 net = nsb.NeRF(63, 27, mode="bf16").to(dev)
 o = torch.randn(B, 3, device=dev); d = torch.nn.functional.normalize(torch.randn(B, 3, device=dev), dim=-1)
 z = torch.sort(torch.rand(B, N, device=dev) * 4 + 2, -1).values.contiguous(); rn = torch.ones(B, device=dev)
-raw = torch.empty(B * N, 4, device=dev); cyc = torch.zeros(16, dtype=torch.int64, device=dev)
+raw = torch.empty(B * N, 4, device=dev); cyc = torch.zeros(16 + (B * N // 128 * 684032 // 8 if STASH else 0), dtype=torch.int64, device=dev)
 for _ in range(2):
-    _lib.check(fn(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(rn), _lib.ptr(d), _lib.ptr(net.packed()), _lib.ptr(raw), cyc.data_ptr(), -1, B, N, _lib.stream()))
+    _lib.check(fn(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(rn), _lib.ptr(d), _lib.ptr(net.packed()), _lib.ptr(raw), cyc.data_ptr(), -2 if STASH else -1, B, N, _lib.stream()))
 torch.cuda.synchronize()
-c = cyc.cpu().tolist()
+c = cyc[:16].cpu().tolist()
 pairs = (B * N // 128 + 1) // 2; per_cta = -(-pairs // 148)
 print(f"pairs/CTA {per_cta}; layers {per_cta*10}")
 print(f"producer: wait_empty {c[0]} of {c[1]} ({100*c[0]/max(c[1],1):.1f}%)")
