@@ -16,8 +16,10 @@
 //   * sigma_out (256->1) and color_out (128->3) are CUDA-core dot products inside the epilogues of layer 7
 //     and color_fc (fp32), so raw [r,g,b,sigma] leaves the chip as one float4 per point.
 // Training adds a bf16 stash of every layer input (bulk-stored tile images) for the backward kernels.
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <mutex>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -35,6 +37,10 @@ constexpr int kSmemBar = kSmemRing + kStages * kStageBytes; // 229376
 constexpr int kSmemBias = kSmemBar + 256;                   // 2 x 1 KB: per epilogue group, the current layer's bias
 constexpr int kSmemBytes = kSmemBias + 2048;
 constexpr int kThreads = 384;
+// forward kernel, CTA pair: a ring stage holds this CTA's half of a K=32 slab (N/2 weight rows) -> twice the stages
+constexpr int kStages2 = 8;
+constexpr int kStageBytes2 = kStageBytes / 2;
+static_assert(8 * (3 * kStages2 + 6) + 4 <= 256, "barrier block overflow");
 constexpr int kNumMmaLayers = 10;               // mlp.0..7, feature, color_fc
 constexpr uint32_t kTmemCols = 512;
 #ifndef NSB_TC_PINGPONG
@@ -95,8 +101,11 @@ __device__ __forceinline__ uint64_t global_ns() {
     return t;
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    const uint64_t t0 = global_ns();
-    while (!mbar_try_wait(bar, parity)) {
+    // the timer is read only every 4096 polls: %globaltimer is slow to read and would add its latency to every wake-up
+    uint64_t t0 = 0;
+    for (uint32_t i = 1; !mbar_try_wait(bar, parity); ++i) {
+        if (i & 0xFFFu) continue;
+        if (t0 == 0) { t0 = global_ns(); continue; }
         if (global_ns() - t0 > 2000000000ull) {   // 2 s
             printf("nsb tc: mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x);
             __trap();
@@ -139,6 +148,66 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA pair (cta_group::2): one MMA spans the two SMs of a cluster -- M = 256 = the 128-row tiles of both CTAs, each
+// CTA holds half of the B operand (N/2 weight rows), accumulators land in each CTA's own TMEM.  Only the leader
+// (cluster rank 0) issues; commits are multicast to the barriers at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// Half-slab load of a CTA pair: a 2-D tiled TMA copy (rows of 256 B of the packed buffer) into THIS CTA's ring stage whose
+// complete_tx is delivered to the barrier at the same offset in the LEADER CTA (.cta_group::2 allows the remote barrier), so
+// the leader's MMA thread sees both halves of a slab on one barrier and nobody has to relay the peer's arrival.
+__device__ __forceinline__ void tma_load_rows_to_leader(uint32_t dst, const CUtensorMap* tm, uint32_t row, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b32 lb;\n\tmapa.shared::cluster.u32 lb, %2, 0;\n\t"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [lb];\n\t}" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(0u), "r"(row)
+        : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  Default semantics on purpose: an explicit
+// .release.cluster made every arrive cost ~1000 cycles (measured: the relay thread spent >90 % of its time in it); what
+// the arrive publishes was written by the TMA engine / fenced for the async proxy before the relay observed it.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+                 "r"(cta)
+                 : "memory");
+}
+// wait on a barrier that a peer CTA arrives on (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_cl_slow(uint32_t bar, uint32_t parity) {
+    uint64_t t0 = 0;
+    for (uint32_t i = 1; !mbar_try_wait_cl(bar, parity); ++i) {
+        if (i & 0xFFFu) continue;
+        if (t0 == 0) { t0 = global_ns(); continue; }
+        if (global_ns() - t0 > 2000000000ull) {
+            printf("nsb tc: cluster mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait_cl(bar, parity)) mbar_wait_cl_slow(bar, parity);
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -183,6 +252,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
 __device__ __forceinline__ uint32_t make_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// the same for a CTA pair: M = 256 (128 rows per CTA)
+__device__ __forceinline__ uint32_t make_idesc2(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
 }
 
 // {lo = relu(a), hi = relu(b)} as bf16x2 in one instruction
@@ -308,6 +381,9 @@ struct FwdParams {
     unsigned long long* cyc;      // debug: per-role wait/busy cycle counters of CTA 0 (16 x u64), or null
     int64_t Q; int N;             // points, samples per ray
     int64_t num_tiles;
+    // the packed buffer as rows of 256 B: boxes of 32 rows (8 KB half slab, N = 256) and 16 rows (4 KB, N = 128)
+    alignas(64) CUtensorMap tm8;
+    alignas(64) CUtensorMap tm4;
 };
 
 // Stash of one tile (bytes), every block a shared-memory image ([K/8][128 rows][8] bf16):
@@ -352,6 +428,10 @@ __device__ __forceinline__ void handoff_wait(int t) {
     tc_fence_after();
     fence_async_smem();
     tc_fence_before();
+}
+// "this CTA's A tile t is in place": the leader's own tiles count on bar_in, the peer's on the leader's bar_pin
+__device__ __forceinline__ void arrive_in(uint32_t crank, uint32_t bar_in, uint32_t bar_pin, int t) {
+    if (crank == 0) mbar_arrive(bar_in + 8 * t); else mbar_arrive_remote(bar_pin + 8 * t, 0);
 }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -430,33 +510,41 @@ __device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __
 
 // STASH = training: the kernel also writes the stash (p.stash) that the backward kernels read
 template <bool FROM_ENC, bool STASH>
-__global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barriers: full[4] empty[4] in_ready[2] acc_full[2]; then the TMEM base address
-    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages, bar_in = bar_empty + 8 * kStages,
-                   bar_acc = bar_in + 16;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 4));
+    const uint32_t crank = cluster_ctarank();           // 0 = leader (issues the pair's MMAs)
+    // barriers: full[8] empty[8] in_ready[2] acc_full[2] peer_full[8] peer_in[2]; then the TMEM base address.
+    // full/in_ready are local; empty/acc_full get the leader's multicast commits; peer_* (used in the leader only) are
+    // arrived on by the peer's relay thread once the peer's half slab / A tile is in place.
+    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages2, bar_in = bar_empty + 8 * kStages2,
+                   bar_acc = bar_in + 16, bar_pfull = bar_acc + 16, bar_pin = bar_pfull + 8 * kStages2;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (3 * kStages2 + 6));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < kStages2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
         // inference (no stash): the 128 epilogue threads fence and arrive themselves; training: the tile's helper warp does
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, STASH ? 1 : 128); mbar_init(bar_acc + 8 * t, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, STASH ? 1 : 128); mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_pin + 8 * t, STASH ? 1 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {   // TMEM allocation (whole SM: 2 tiles x 256 fp32 columns)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+    if (warp == 2) {   // TMEM allocation (whole SM: 2 tiles x 256 fp32 columns), collectively with the peer CTA's warp 2
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                      "r"(kTmemCols)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();          // the peer's barriers and TMEM exist before anything is sent its way
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int64_t num_pairs = (p.num_tiles + 1) / 2;
+    // both CTAs of a cluster walk the weight stream in lockstep: same trip count (the leader's); a CTA whose pair index
+    // falls off the end computes on stale tiles and stores nothing
+    const int64_t first_pair = (int64_t)blockIdx.x - crank;
+    const int64_t n_iter = first_pair < num_pairs ? (num_pairs - first_pair + gridDim.x - 1) / gridDim.x : 0;
     const float* tail = reinterpret_cast<const float*>(p.packed + kBiasOfs);
 
     if (warp == 0) {
@@ -465,25 +553,31 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         {
             uint32_t stage = 0, round = 0;
             long long w_empty = 0; const long long t_begin = clock64();
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const uint32_t bytes = 32u * (uint32_t)layer_N(l) * 2u;
                     const uint8_t* src = p.packed + c_layer_ofs[l];
                     const int ns = layer_nslabs(l);
-                    // ping-pong: the layer's slabs are streamed once per tile (A, then B)
-                    for (int s2 = 0; s2 < (kPingPong ? 2 * ns : ns); ++s2) {
+                    // a layer whose slabs fit the ring is fetched once and used by tile A, then by tile B; the two longer
+                    // layers (the skip layer and color_fc) are streamed once per tile
+                    for (int s2 = 0; s2 < (ns <= kStages2 ? ns : 2 * ns); ++s2) {
                         const int s = s2 >= ns ? s2 - ns : s2;
                         mbar_wait_t(bar_empty + 8 * stage, (round & 1) ^ 1, w_empty);
                         if (elect_one()) {
-                            mbar_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src + (size_t)s * bytes, bytes, bar_full + 8 * stage);
+                            // this CTA's half of the slab: weight rows [crank * N/2, +N/2), contiguous in the packed image.
+                            // Both halves complete on the leader's barrier, which therefore expects the whole slab.
+                            const uint32_t half = bytes >> 1;
+                            if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, bytes);
+                            tma_load_rows_to_leader(sbase + kSmemRing + stage * kStageBytes2, half == 8192u ? &p.tm8 : &p.tm4,
+                                                    (c_layer_ofs[l] + (uint32_t)s * bytes + crank * half) >> 8, bar_full + 8 * stage);
                         }
                         __syncwarp();
-                        if (++stage == kStages) { stage = 0; ++round; }
+                        if (++stage == kStages2) { stage = 0; ++round; }
                     }
                 }
             }
             if (p.cyc && blockIdx.x == 0 && lane == 0) { p.cyc[0] = (unsigned long long)w_empty; p.cyc[1] = (unsigned long long)(clock64() - t_begin); }
+            if (p.cyc && blockIdx.x == 1 && lane == 0) { p.cyc[16] = (unsigned long long)w_empty; p.cyc[17] = (unsigned long long)(clock64() - t_begin); }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ========================================
@@ -491,47 +585,57 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         // to uniform registers without per-lane waterfalls and there is no per-slab warp re-convergence).
         // Schedule: tile A's whole layer, then tile B's -- while one tile's epilogue drains TMEM the tensor core works on
         // the other tile; the layer's weight slabs are streamed once per tile.
-        if (elect_one()) {
+        if (crank == 0 && elect_one()) {
             uint32_t stage = 0, round = 0, use = 0;   // use = layers completed (parity of in_ready / acc_full)
-            long long w_in = 0, w_full = 0; const long long t_begin = clock64();
+            long long w_in = 0, w_full = 0, w_pfull = 0, w_pin = 0; const long long t_begin = clock64();
             const uint64_t ahi = desc_hi(2048, 128);
             const uint32_t ring_lo = (sbase + kSmemRing) >> 4;
-            // issue `n` K=32 slabs whose A operand starts at a_lo (descriptor address units of 16 B) into accumulator d_tmem
+            // issue `n` K=32 slabs whose A operand starts at a_lo (descriptor address units of 16 B) into accumulator d_tmem.
+            // wait: the slabs have not been seen yet (first use);  release: hand the stages back to the producers after use
             auto issue = [&](uint32_t a_lo, int n, bool first_overwrites, uint32_t d_tmem, uint64_t bhi, uint32_t b_step, uint32_t idesc,
-                             uint32_t acc_bar) {
+                             uint32_t acc_bar, bool wait, bool release) {
                 for (int s = 0; s < n; ++s, a_lo += 512u) {
-                    if (p.cyc) mbar_wait_t(bar_full + 8 * stage, round & 1, w_full); else mbar_wait(bar_full + 8 * stage, round & 1);
-                    tc_fence_after();
-                    const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                    tc_mma(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, (first_overwrites && s == 0) ? 0u : 1u);
-                    tc_mma(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + b_step), idesc, 1u);
-                    if (acc_bar && s == n - 1) tc_commit(acc_bar);
-                    tc_commit(bar_empty + 8 * stage);
-                    if (++stage == kStages) { stage = 0; ++round; }
+                    if (wait) {
+                        if (p.cyc) mbar_wait_t(bar_full + 8 * stage, round & 1, w_full); else mbar_wait(bar_full + 8 * stage, round & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t b_lo = ring_lo + stage * (kStageBytes2 >> 4);
+                    tc_mma2(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, (first_overwrites && s == 0) ? 0u : 1u);
+                    tc_mma2(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + b_step), idesc, 1u);
+                    if (acc_bar && s == n - 1) tc_commit2(acc_bar);
+                    if (release) tc_commit2(bar_empty + 8 * stage);
+                    if (++stage == kStages2) { stage = 0; ++round; }
                 }
             };
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (int64_t it = 0; it < n_iter; ++it) {
                 for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
                     const int N = layer_N(l);
-                    const uint32_t idesc = make_idesc(N);
-                    const uint32_t lbo_b = (uint32_t)N * 16u;
+                    const uint32_t idesc = make_idesc2(N);
+                    const uint32_t lbo_b = (uint32_t)N * 8u;            // K-chunk stride inside a stage: N/2 rows x 16 B
                     const uint64_t bhi = desc_hi(lbo_b, 128);
                     const uint32_t b_step = (2u * lbo_b) >> 4;
                     // A-operand segments of the layer: n_act slabs from the activation buffer, then n_gx from the gamma buffer
                     const int n_act = l == 0 ? 0 : 8;
                     const int n_gx = l == 0 ? 2 : (l == 4 ? 2 : (l == 9 ? 1 : 0));
+                    const bool shared = n_act + n_gx <= kStages2;       // slabs fetched once, used by tile A then tile B
+                    const uint32_t stage0 = stage, round0 = round;
                     for (int t = 0; t < 2; ++t) {
                         if (p.cyc) mbar_wait_t(bar_in + 8 * t, use & 1, w_in); else mbar_wait(bar_in + 8 * t, use & 1);
+                        { const long long t0 = clock64(); mbar_wait_cl(bar_pin + 8 * t, use & 1); w_pin += clock64() - t0; }
+                        tc_fence_after();
+                        if (shared && t == 1) { stage = stage0; round = round0; }
+                        const bool wait = !shared || t == 0, release = !shared || t == 1;
                         const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
                         const uint32_t act_lo = (sbase + kSmemAct + t * kActBytes) >> 4, gx_lo = (sbase + kSmemGx + t * kGxBytes) >> 4;
                         const uint32_t acc_bar = bar_acc + 8 * t;
-                        if (n_act) issue(act_lo, n_act, true, d_tmem, bhi, b_step, idesc, n_gx ? 0u : acc_bar);
-                        if (n_gx) issue(gx_lo, n_gx, n_act == 0, d_tmem, bhi, b_step, idesc, acc_bar);
+                        if (n_act) issue(act_lo, n_act, true, d_tmem, bhi, b_step, idesc, n_gx ? 0u : acc_bar, wait, release);
+                        if (n_gx) issue(gx_lo, n_gx, n_act == 0, d_tmem, bhi, b_step, idesc, acc_bar, wait, release);
                     }
                 }
             }
             if (p.cyc && blockIdx.x == 0) {
                 p.cyc[2] = (unsigned long long)w_in; p.cyc[3] = (unsigned long long)w_full; p.cyc[4] = (unsigned long long)(clock64() - t_begin);
+                p.cyc[13] = (unsigned long long)w_pfull; p.cyc[14] = (unsigned long long)w_pin;
             }
         }
     } else if (STASH && (warp == 2 || warp == 3)) {
@@ -541,13 +645,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         const int t = warp - 2;
         const uint32_t act = sbase + kSmemAct + t * kActBytes;
         const int n_events = kNumMmaLayers + 1;
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
             const int64_t tile = pair * 2 + t;
             uint8_t* stash_tile = tile < p.num_tiles ? p.stash + (size_t)tile * kStashTile : nullptr;
             for (int e = 0; e < n_events; ++e) {
                 handoff_wait(t);
                 if (lane == 0) {
-                    if (e < kNumMmaLayers) mbar_arrive(bar_in + 8 * t);
+                    if (e < kNumMmaLayers) arrive_in(crank, bar_in, bar_pin, t);
                     if (stash_tile && e >= 1) {
                         const int l = e - 1;
                         const size_t ofs = l <= 7 ? kStashH + (size_t)l * 65536 : (l == 8 ? kStashFeat : kStashC);
@@ -569,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
         const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t use = 0;
         long long w_acc = 0, w_bar = 0, t_cols = 0; const long long t_begin = clock64();
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
             const int64_t tile = pair * 2 + t;
             const int64_t q = tile * TILE_M + r;
             const bool valid = tile < p.num_tiles && q < p.Q;
@@ -596,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                 const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
                 vdir[0] = vx * inv; vdir[1] = vy * inv; vdir[2] = vz * inv;
             }
-            if (do_stash) handoff_signal(t); else { fence_async_smem(); mbar_arrive(bar_in + 8 * t); }
+            if (do_stash) handoff_signal(t); else { fence_async_smem(); arrive_in(crank, bar_in, bar_pin, t); }
             float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
             const uint32_t sbias = sbase + kSmemBias + (uint32_t)t * 1024u;      // this group's bias staging (256 fp32)
             const bool want_dbg = p.dbg != nullptr;
@@ -707,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
                     else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
                 }
                 if (do_stash) handoff_signal(t);                // l == 9: only the stash copy of c waits for it
-                else if (l != 9) { tc_fence_before(); fence_async_smem(); mbar_arrive(bar_in + 8 * t); }
+                else if (l != 9) { tc_fence_before(); fence_async_smem(); arrive_in(crank, bar_in, bar_pin, t); }
             }
             if (valid) {
                 reinterpret_cast<float4*>(p.raw)[q] = make_float4(rgb[0] + tail[kBoOfs], rgb[1] + tail[kBoOfs + 1],
@@ -722,9 +826,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const FwdParams 
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the pair's MMAs or commits may still touch it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -737,9 +842,11 @@ __global__ void pack_tc_kernel(const float* __restrict__ params, uint8_t* __rest
         const int N = d.N, Kp = d.Kpad;
         __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + c_layer_ofs[m]);
         for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * Kp; idx += gridDim.x * blockDim.x) {
-            const int k = idx / N, n = idx % N;                 // image order: [k/8][n][k%8]
+            // image order: [K slab k/32][half of N (one per CTA of a pair)][K chunk (k/8)%4][n % (N/2)][k%8] -- a CTA's half
+            // of a K=32 slab is one contiguous block (8 KB at N=256)
+            const int k = idx / N, n = idx % N, hn = N >> 1;
             const float w = k < d.K ? params[d.w_off + (int64_t)n * d.K + k] : 0.f;
-            img[((size_t)(k >> 3) * N + n) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+            img[((((size_t)(k >> 5) * 2 + n / hn) * 4 + ((k >> 3) & 3)) * hn + n % hn) * 8 + (k & 7)] = __float2bfloat16_rn(w);
         }
         float* tail = reinterpret_cast<float*>(out + kBiasOfs);
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
@@ -769,6 +876,7 @@ struct DgradParams {
     const uint8_t* stash;         // forward stash
     uint8_t* dstash;              // gradient stash (output)
     int64_t Q; int64_t num_tiles;
+    alignas(64) CUtensorMap tm8;  // the packed buffer as rows of 256 B, boxes of 32 rows (one 8 KB half slab)
 };
 
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -821,49 +929,55 @@ __device__ __forceinline__ void dgrad_columns(uint32_t tmem_row, uint32_t act, i
     }
 }
 
-// the dgrad chain has no gamma(x)/gamma(d) operand, so its weight ring takes that space too: 6 stages instead of 4
-constexpr int kDgStages = 6;
+// the dgrad chain has no gamma(x)/gamma(d) operand, so its weight ring takes that space too: 96 KB = 12 half-slab stages;
+// it has no bias staging either, so its (larger) barrier block runs into that space
+constexpr int kDgStages = 12;
 constexpr int kDgSmemRing = kSmemGx;
-static_assert(kDgSmemRing + kDgStages * kStageBytes == kSmemBar, "dgrad ring must end at the barrier block");
-static_assert(8 * (2 * kDgStages + 4) + 4 <= 256, "barrier block overflow");
-__global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradParams p) {
+static_assert(kDgSmemRing + kDgStages * kStageBytes2 == kSmemBar, "dgrad ring must end at the barrier block");
+static_assert(kSmemBar + 8 * (3 * kDgStages + 6) + 4 <= kSmemBytes, "barrier block overflow");
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_dgrad_kernel(const __grid_constant__ DgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    // same CTA-pair protocol as the forward kernel: full/in local, empty/acc via the leader's multicast commits, peer_* in the leader
     const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kDgStages, bar_in = bar_empty + 8 * kDgStages,
-                   bar_acc = bar_in + 16;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (2 * kDgStages + 4));
+                   bar_acc = bar_in + 16, bar_pfull = bar_acc + 16, bar_pin = bar_pfull + 8 * kDgStages;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (3 * kDgStages + 6));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kDgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 1); mbar_init(bar_acc + 8 * t, 1); }
+        for (int s = 0; s < kDgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_in + 8 * t, 1); mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_pin + 8 * t, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                      "r"(kTmemCols)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t num_pairs = (p.num_tiles + 1) / 2;
+    const int64_t first_pair = (int64_t)blockIdx.x - crank;       // lockstep: both CTAs of a cluster run the leader's trip count
+    const int64_t n_iter = first_pair < num_pairs ? (num_pairs - first_pair + gridDim.x - 1) / gridDim.x : 0;
     const float* tail = reinterpret_cast<const float*>(p.packed + kBiasOfs);
 
     if (warp == 0) {
         {                                                  // TMA producer: K=32 x N=256 slabs of W^T
             uint32_t stage = 0, round = 0;
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
                 for (int m = 0; m < kNumDgradLayers; ++m) {
                     const uint8_t* src = p.packed + dgrad_layer_ofs(m);
                     const int ns = m == 0 ? 4 : 8;
-                    for (int s2 = 0; s2 < (kPingPong ? 2 * ns : ns); ++s2) {
-                        const int s = s2 >= ns ? s2 - ns : s2;
+                    for (int s = 0; s < ns; ++s) {                 // fetched once per step, used by tile A then tile B
                         mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
-                        if (elect_one()) {
-                            mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-                            bulk_g2s(sbase + kDgSmemRing + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full + 8 * stage);
+                        if (elect_one()) {      // this CTA's half of the slab (input features [128 crank, +128)) -> leader's barrier
+                            if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            tma_load_rows_to_leader(sbase + kDgSmemRing + stage * kStageBytes2, &p.tm8,
+                                                    (dgrad_layer_ofs(m) + (uint32_t)s * kStageBytes + crank * kStageBytes2) >> 8, bar_full + 8 * stage);
                         }
                         __syncwarp();
                         if (++stage == kDgStages) { stage = 0; ++round; }
@@ -872,26 +986,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {                                 // MMA issuer: one elected thread, ping-pong over the two tiles
+        if (crank == 0 && elect_one()) {                   // MMA issuer: the leader's elected thread, ping-pong over the two tiles
             uint32_t stage = 0, round = 0, use = 0;
-            const uint32_t idesc = make_idesc(256);
-            const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(4096, 128);
+            const uint32_t idesc = make_idesc2(256);
+            const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(2048, 128);
             const uint32_t ring_lo = (sbase + kDgSmemRing) >> 4;
-            for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (int64_t it = 0; it < n_iter; ++it) {
                 for (int m = 0; m < kNumDgradLayers; ++m, ++use) {
                     const int ns = m == 0 ? 4 : 8;
+                    const uint32_t stage0 = stage, round0 = round;
                     for (int t = 0; t < 2; ++t) {
                         mbar_wait(bar_in + 8 * t, use & 1);
+                        mbar_wait_cl(bar_pin + 8 * t, use & 1);
+                        tc_fence_after();
+                        if (t == 1) { stage = stage0; round = round0; }     // tile B reuses the slabs tile A has just used
                         const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
                         uint32_t a_lo = (sbase + kSmemAct + t * kActBytes) >> 4;
                         for (int s = 0; s < ns; ++s, a_lo += 512u) {
-                            mbar_wait(bar_full + 8 * stage, round & 1);
-                            tc_fence_after();
-                            const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                            tc_mma(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, s > 0 ? 1u : 0u);
-                            tc_mma(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + 512u), idesc, 1u);
-                            if (s == ns - 1) tc_commit(bar_acc + 8 * t);
-                            tc_commit(bar_empty + 8 * stage);
+                            if (t == 0) {
+                                mbar_wait(bar_full + 8 * stage, round & 1);
+                                tc_fence_after();
+                            }
+                            const uint32_t b_lo = ring_lo + stage * (kStageBytes2 >> 4);
+                            tc_mma2(d_tmem, ahi | (uint64_t)a_lo, bhi | (uint64_t)b_lo, idesc, s > 0 ? 1u : 0u);
+                            tc_mma2(d_tmem, ahi | (uint64_t)(a_lo + 256u), bhi | (uint64_t)(b_lo + 256u), idesc, 1u);
+                            if (s == ns - 1) tc_commit2(bar_acc + 8 * t);
+                            if (t == 1) tc_commit2(bar_empty + 8 * stage);
                             if (++stage == kDgStages) { stage = 0; ++round; }
                         }
                     }
@@ -905,14 +1025,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
         const int t = warp - 2;
         const uint32_t act = sbase + kSmemAct + t * kActBytes;
         named_bar_arrive(1 + t, 160);
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
             const int64_t tile = pair * 2 + t;
             uint8_t* ds_tile = tile < p.num_tiles ? p.dstash + (size_t)tile * kDstashTile : nullptr;
-            const bool last_pair = pair + gridDim.x >= num_pairs;
+            const bool last_pair = it + 1 == n_iter;
             for (int e = 0; e <= kNumDgradLayers; ++e) {
                 handoff_wait(t);
                 if (lane == 0) {
-                    if (e < kNumDgradLayers) mbar_arrive(bar_in + 8 * t);
+                    if (e < kNumDgradLayers) arrive_in(crank, bar_in, bar_pin, t);
                     if (ds_tile) {
                         bulk_s2g(ds_tile + (e == 0 ? dstash_ofs(9) : dstash_ofs(8 - (e - 1))), act, e == 0 ? 32768u : 65536u);
                         bulk_commit();
@@ -930,7 +1050,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
         const uint32_t act = sbase + kSmemAct + t * kActBytes;
         const uint32_t tmem_row = tmem_base + (uint32_t)t * 256u + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t use = 0;
-        for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
             const int64_t tile = pair * 2 + t;
             const int64_t q = tile * TILE_M + r;
             const bool tile_ok = tile < p.num_tiles;
@@ -984,9 +1104,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_dgrad_kernel(const DgradPar
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -1265,8 +1386,9 @@ __global__ void pack_tc_transposed_kernel(const float* __restrict__ params, uint
         const int Nout = d.N;                                  // contraction length (128 or 256)
         __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + dgrad_layer_ofs(m));
         for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Nout * 256; idx += gridDim.x * blockDim.x) {
-            const int n = idx / 256, j = idx % 256;            // W[n, j], j < 256 <= K
-            img[((size_t)(n >> 3) * 256 + j) * 8 + (n & 7)] = __float2bfloat16_rn(params[d.w_off + (int64_t)n * d.K + j]);
+            const int n = idx / 256, j = idx % 256;            // W[n, j], j < 256 <= K; same half-slab order with (k, n) := (n, j)
+            img[((((size_t)(n >> 5) * 2 + (j >> 7)) * 4 + ((n >> 3) & 3)) * 128 + (j & 127)) * 8 + (n & 7)] =
+                __float2bfloat16_rn(params[d.w_off + (int64_t)n * d.K + j]);
         }
     }
 }
@@ -1301,6 +1423,44 @@ static int check_arch() {
     return ok ? NSB_OK : NSB_E_ARCH;
 }
 
+// ---- tensor maps over a packed-weight buffer (rows of 256 B; boxes of 32 / 16 rows), cached per buffer address ----
+struct PackedMaps { const void* ptr; CUtensorMap tm8, tm4; };
+static int packed_maps(const void* packed, CUtensorMap* tm8, CUtensorMap* tm4) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::mutex mu;
+    static EncodeFn encode = nullptr;
+    static PackedMaps cache[16];
+    static int n_cached = 0, next = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].ptr == packed) { *tm8 = cache[i].tm8; if (tm4) *tm4 = cache[i].tm4; return NSB_OK; }
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return check_launch("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    PackedMaps m{};
+    m.ptr = packed;
+    const cuuint64_t dims[2] = {256, tc::kPackedTcBytes / 256};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int k = 0; k < 2; ++k) {
+        const cuuint32_t box[2] = {256, k == 0 ? 32u : 16u};
+        if (encode(k == 0 ? &m.tm8 : &m.tm4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(packed), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed for the packed weight buffer");
+            return NSB_E_CUDA;
+        }
+    }
+    cache[next] = m; next = (next + 1) % 16; if (n_cached < 16) ++n_cached;
+    *tm8 = m.tm8; if (tm4) *tm4 = m.tm4;
+    return NSB_OK;
+}
+
 template <bool FROM_ENC>
 static int launch_fwd(tc::FwdParams& p, cudaStream_t st) {
     NSB_TRY(check_arch());
@@ -1312,8 +1472,11 @@ static int launch_fwd(tc::FwdParams& p, cudaStream_t st) {
         attr_set = true;
     }
     p.num_tiles = cdiv(p.Q, tc::TILE_M);
+    NSB_TRY(packed_maps(p.packed, &p.tm8, &p.tm4));
     const int64_t pairs = (p.num_tiles + 1) / 2;
-    const int grid = (int)(pairs < num_sms() ? pairs : num_sms());
+    int grid = (int)(pairs < num_sms() ? pairs : num_sms());
+    grid = (grid + 1) / 2 * 2;                       // clusters of two CTAs (a CTA without a pair idles along)
+    if (grid > num_sms()) grid -= 2;
     if (p.stash) tc::field_fwd_kernel<FROM_ENC, true><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     else tc::field_fwd_kernel<FROM_ENC, false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     NSB_LAUNCH_CHECK("field_fwd_kernel");
@@ -1355,7 +1518,11 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     tc::DgradParams dp{};
     dp.d_raw = d_raw; dp.packed = reinterpret_cast<const uint8_t*>(packed); dp.stash = ws_stash(ws); dp.dstash = ws_dstash(ws, Q);
     dp.Q = Q; dp.num_tiles = tiles;
-    tc::field_dgrad_kernel<<<(int)(pairs < num_sms() ? pairs : num_sms()), tc::kThreads, tc::kSmemBytes, st>>>(dp);
+    NSB_TRY(packed_maps(packed, &dp.tm8, nullptr));
+    int dgrid = (int)(pairs < num_sms() ? pairs : num_sms());
+    dgrid = (dgrid + 1) / 2 * 2;                     // clusters of two CTAs
+    if (dgrid > num_sms()) dgrid -= 2;
+    tc::field_dgrad_kernel<<<dgrid, tc::kThreads, tc::kSmemBytes, st>>>(dp);
     NSB_LAUNCH_CHECK("field_dgrad_kernel");
 
     tc::WgradParams wp{};
@@ -1434,9 +1601,9 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 int tc_debug_layer(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,
                    const void* packed, float* raw, float* dbg, int layer, int64_t B, int N, cudaStream_t st) {
     tc::FwdParams p{};
-    if (layer < 0) {   // layer -1: cycle counters instead; layer -2: same with the training stash written behind the 16 counters
+    if (layer < 0) {   // layer -1: cycle counters instead; layer -2: same with the training stash written behind the 32 counters
         p.cyc = reinterpret_cast<unsigned long long*>(dbg);
-        if (layer == -2) p.stash = reinterpret_cast<uint8_t*>(dbg) + 128;
+        if (layer == -2) p.stash = reinterpret_cast<uint8_t*>(dbg) + 256;
         dbg = nullptr;
     }
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.ray_norm = ray_norm; p.viewdirs = viewdirs;
