@@ -38,6 +38,10 @@ constexpr int kSmemBias = kSmemBar + 256;                   // 2 x 1 KB: per epi
 constexpr int kSmemBytes = kSmemBias + 2048;
 constexpr int kThreads = 384;
 // forward kernel, CTA pair: a ring stage holds this CTA's half of a K=32 slab (N/2 weight rows) -> twice the stages
+#ifndef NSB_SHARE_SLABS
+#define NSB_SHARE_SLABS 1
+#endif
+constexpr bool kShareSlabs = NSB_SHARE_SLABS != 0;
 constexpr int kStages2 = 8;
 constexpr int kStageBytes2 = kStageBytes / 2;
 static_assert(8 * (3 * kStages2 + 6) + 4 <= 256, "barrier block overflow");
@@ -560,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                     const int ns = layer_nslabs(l);
                     // a layer whose slabs fit the ring is fetched once and used by tile A, then by tile B; the two longer
                     // layers (the skip layer and color_fc) are streamed once per tile
-                    for (int s2 = 0; s2 < (ns <= kStages2 ? ns : 2 * ns); ++s2) {
+                    for (int s2 = 0; s2 < (kShareSlabs && ns <= kStages2 ? ns : 2 * ns); ++s2) {
                         const int s = s2 >= ns ? s2 - ns : s2;
                         mbar_wait_t(bar_empty + 8 * stage, (round & 1) ^ 1, w_empty);
                         if (elect_one()) {
@@ -617,7 +621,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                     // A-operand segments of the layer: n_act slabs from the activation buffer, then n_gx from the gamma buffer
                     const int n_act = l == 0 ? 0 : 8;
                     const int n_gx = l == 0 ? 2 : (l == 4 ? 2 : (l == 9 ? 1 : 0));
-                    const bool shared = n_act + n_gx <= kStages2;       // slabs fetched once, used by tile A then tile B
+                    const bool shared = kShareSlabs && n_act + n_gx <= kStages2;       // slabs fetched once, used by tile A then tile B
                     const uint32_t stage0 = stage, round0 = round;
                     for (int t = 0; t < 2; ++t) {
                         if (p.cyc) mbar_wait_t(bar_in + 8 * t, use & 1, w_in); else mbar_wait(bar_in + 8 * t, use & 1);
@@ -1122,7 +1126,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_d
 // (d_raw-weighted column sums of the h8 / c images).
 // =======================================================================================================
 struct WgPiece { uint32_t ofs; uint32_t bytes; int from_stash; int dy_half; int head; };   // dy_half: -1 (X piece) | 0 | 1
-struct WgGroup { int a_piece, b_piece, tmem_col, n; };          // A = dY piece (M = 128 features), B = X piece (N = n columns)
+struct WgGroup { int a_piece, b_piece, b_piece2, tmem_col, n; };   // A = dY piece (M = 128 features), B = X piece(s) (N = n columns;
+                                                                   // b_piece2 >= 0: second half in the next ring slot, N = 256)
 enum { HEAD_NONE = 0, HEAD_SIGMA = 1, HEAD_RGB = 2 };
 struct WgradJob {
     int n_pieces; WgPiece pieces[4];
@@ -1140,7 +1145,7 @@ struct WgradJob {
 constexpr int kMaxJobs = 16;
 struct WgradParams {
     const uint8_t* stash; const uint8_t* dstash; const float* d_raw; float* grads;
-    int64_t num_tiles, Q; int num_jobs;
+    int64_t num_tiles, Q; int num_jobs; int dbg;
     WgradJob jobs[kMaxJobs];
 };
 constexpr int kWgPiece = 32768;                       // ring slot: one column half of a tile image
@@ -1233,14 +1238,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
             uint32_t slot = 0, round = 0;
             const uint64_t mnhi = desc_hi(128, 2048);
             bool first = true;
+            long long w_full = 0; const long long t_begin = clock64();
             for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
                 uint32_t pslot[4], pround[4];
                 for (int i = 0; i < job.n_pieces; ++i) { pslot[i] = slot; pround[i] = round; if (++slot == kWgSlots) { slot = 0; ++round; } }
                 uint32_t ready = 0;                    // bit i: piece i's full barrier has been observed
                 for (int g = 0; g < job.n_groups; ++g) {
                     const WgGroup& gr = job.groups[g];
+                    const long long tw0 = clock64();
                     if (!(ready >> gr.a_piece & 1)) { mbar_wait(bar_full + 8 * pslot[gr.a_piece], pround[gr.a_piece] & 1); ready |= 1u << gr.a_piece; }
                     if (!(ready >> gr.b_piece & 1)) { mbar_wait(bar_full + 8 * pslot[gr.b_piece], pround[gr.b_piece] & 1); ready |= 1u << gr.b_piece; }
+                    if (gr.b_piece2 >= 0 && !(ready >> gr.b_piece2 & 1)) {
+                        mbar_wait(bar_full + 8 * pslot[gr.b_piece2], pround[gr.b_piece2] & 1); ready |= 1u << gr.b_piece2;
+                    }
+                    w_full += clock64() - tw0;
                     tc_fence_after();
                     const uint32_t a_lo = (sbase + pslot[gr.a_piece] * kWgPiece) >> 4, b_lo = (sbase + pslot[gr.b_piece] * kWgPiece) >> 4;
                     const uint32_t idesc = make_idesc_mn(gr.n);
@@ -1256,6 +1267,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
                 first = false;
             }
             tc_commit(bar_done);
+            if (p.dbg && (part == 0)) printf("wgrad job %d (%d CTAs, %lld tiles): mma thread waited for pieces %lld of %lld cycles\n", ji, job.cta_count, (long long)my_tiles, w_full, clock64() - t_begin);
         }
     } else if (warp >= 4) {
         // ---- CUDA-core reductions over the pieces in shared memory (lanes over points -> conflict-free 16-byte reads) ----
@@ -1540,14 +1552,20 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
             j.pieces[j.n_pieces] = tc::WgPiece{ofs, bytes, from_stash, dy_half, hd}; j.release_after[j.n_pieces] = -1; return j.n_pieces++;
         };
         auto group = [&](int a, int b, int col, int n) {
-            j.groups[j.n_groups] = tc::WgGroup{a, b, col, n}; j.release_after[a] = j.n_groups; j.release_after[b] = j.n_groups; ++j.n_groups;
+            j.groups[j.n_groups] = tc::WgGroup{a, b, -1, col, n}; j.release_after[a] = j.n_groups; j.release_after[b] = j.n_groups; ++j.n_groups;
         };
-        const int a0 = piece(dy, 32768, 0, 0, 0);
         if (xcols == 256) {
+            // X halves first, in adjacent ring slots (a tile takes 4 or 3 of the 6 slots, so the pair starts on slot 0, 2, 4 or 0, 3
+            // and never wraps): one N = 256 MMA reads both.  An MN-major MMA costs ~200-250 cycles whatever its N (measured), so
+            // halving the instruction count is what counts here.
             const int b0 = piece((uint32_t)x_ofs, 32768, 1, -1, head), b1 = piece((uint32_t)x_ofs + 32768, 32768, 1, -1, head);
-            group(a0, b0, 0, 128); group(a0, b1, 128, 128);
-            if (halves == 2) { const int a1 = piece(dy + 32768, 32768, 0, 1, 0); group(a1, b0, 256, 128); group(a1, b1, 384, 128); }
+            const int a0 = piece(dy, 32768, 0, 0, 0);
+            group(a0, b0, 0, 256);
+            if (halves == 2) { const int a1 = piece(dy + 32768, 32768, 0, 1, 0); group(a1, b0, 256, 256); }
+            for (int g = 0; g < j.n_groups; ++g) j.groups[g].b_piece2 = b1;
+            j.release_after[b1] = j.n_groups - 1;
         } else {
+            const int a0 = piece(dy, 32768, 0, 0, 0);
             const int b0 = piece((uint32_t)x_ofs, xb, 1, -1, head);
             group(a0, b0, 0, xcols);
             if (halves == 2) { const int a1 = piece(dy + 32768, 32768, 0, 1, 0); group(a1, b0, 256, xcols); }
@@ -1557,6 +1575,7 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
         if (head == tc::HEAD_SIGMA) { const LayerDesc ds = layer_desc(9); j.head_w_dst = ds.w_off; j.head_b_dst = ds.b_off; }
         j.bytes_per_tile = 0;
         for (int i = 0; i < j.n_pieces; ++i) j.bytes_per_tile += j.pieces[i].bytes;
+        if (head == tc::HEAD_SIGMA) j.bytes_per_tile += j.bytes_per_tile / 6;     // its idle warps also reduce the sigma_out grads
     };
     add(0, tc::kStashGx, 64, 0, 0, 63, true, 0);
     for (int l = 1; l <= 7; ++l) {
@@ -1572,23 +1591,32 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
         j.pieces[0] = tc::WgPiece{(uint32_t)tc::kStashC, 32768, 1, -1, tc::HEAD_RGB}; j.release_after[0] = -1; j.n_pieces = 1;
         const LayerDesc dc = layer_desc(11);
         j.head_w_dst = dc.w_off; j.head_b_dst = dc.b_off; j.b_dst = -1;
-        j.bytes_per_tile = 3 * (32768 + 2048);      // CUDA-core bound: measured best at ~3x its byte share
+        j.bytes_per_tile = (32768 + 2048) * 3 / 2;      // CUDA-core bound: a little more than its byte share
     }
     wp.num_jobs = nj;
-    // CTAs per job in proportion to the bytes a tile costs (the kernel is HBM-bound), at least one each
+    wp.dbg = getenv("NSB_WG_DBG") != nullptr;
+    // CTAs per job: greedy min-max of (tiles per CTA) x (cycles per tile).  The per-tile cost is what the MMA thread of
+    // each job kind was measured to take on B200 (scripts/perf_bwd.py with NSB_WG_DBG=1): an MN-major MMA costs
+    // ~200-250 cycles whatever its N, so cost follows the instruction count more than the bytes.
     const int total = num_sms();
-    double sum = 0;
-    for (int i = 0; i < nj; ++i) sum += wp.jobs[i].bytes_per_tile;
-    int used = 0;
+    double cost[tc::kMaxJobs];
     for (int i = 0; i < nj; ++i) {
-        int c = (int)(wp.jobs[i].bytes_per_tile / sum * total);
-        if (c < 1) c = 1;
-        if ((int64_t)c > tiles) c = (int)tiles;
-        wp.jobs[i].cta_count = c; used += c;
+        const tc::WgradJob& j = wp.jobs[i];
+        if (j.n_groups == 0) cost[i] = 1750;                                   // color_out grads, CUDA cores only
+        else if (j.xcols == 256) cost[i] = j.halves == 2 ? 5600 : 3100;        // 16 / 8 MMAs of N = 256
+        else cost[i] = j.xcols == 64 ? 3750 : 2100;                            // gamma(x) blocks (16 MMAs) / gamma(d) block (8)
+        if (j.head_w_dst && j.n_groups) cost[i] += 100;                        // + sigma_out reductions on the idle warps
+        wp.jobs[i].cta_count = 1;
     }
-    for (int i = 0; used < total && i < 4 * nj; ++i) {      // hand out the remainder to the big jobs
-        tc::WgradJob& j = wp.jobs[i % nj];
-        if (j.xcols == 256 && (int64_t)j.cta_count < tiles) { ++j.cta_count; ++used; }
+    for (int used = nj; used < total; ++used) {
+        int worst = -1; double worst_t = -1;
+        for (int i = 0; i < nj; ++i) {
+            if ((int64_t)wp.jobs[i].cta_count >= tiles) continue;
+            const double t = cost[i] * (double)cdiv(tiles, wp.jobs[i].cta_count);
+            if (t > worst_t) { worst_t = t; worst = i; }
+        }
+        if (worst < 0) break;
+        ++wp.jobs[worst].cta_count;
     }
     int begin = 0;
     for (int i = 0; i < nj; ++i) { wp.jobs[i].cta_begin = begin; begin += wp.jobs[i].cta_count; }
