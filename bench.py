@@ -180,7 +180,10 @@ def main():
     W_ = max(args.warmup, 3)
     K = args.steps
 
-    tr = nsb.VanillaTrainer(dev, rays_per_batch=RAYS, nc=NC, nf=NF, near=2.0, far=6.0, mode=args.mode, seed=0, sigma_bias=0.3)
+    tr = nsb.VanillaTrainer(dev, rays_per_batch=RAYS, nc=NC, nf=NF, near=2.0, far=6.0, mode=args.mode, seed=0, sigma_bias=0.3,
+                            allreduce=os.environ.get("NSB_ALLREDUCE", "auto"))
+    exchange = ("all-reduce fused into the Adam kernel over NVLink peer loads (nsb_adam_allreduce_step)" if tr.peer is not None
+                else "NCCL all-reduce")
     rng = np.random.default_rng(1000 + rank)
     pool_n = 8
     host = [{k: torch.from_numpy(v).pin_memory() for k, v in blender_rays(rng, RAYS, s).items()} for s in range(pool_n)]
@@ -315,7 +318,7 @@ def main():
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step/GPU, 64 coarse + 128 fine, "
                                    "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])",
-                       "rays_per_step_per_gpu": RAYS, "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of 2x595,844 fp32 grads",
+                       "rays_per_step_per_gpu": RAYS, "parallelism": f"ray-sharded dp{world}, {exchange} of 2x595,844 fp32 grads",
                        "mode": args.mode, "l2": f"no flush: per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,

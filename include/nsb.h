@@ -149,6 +149,19 @@ int nsb_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws
 int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int64_t t, float grad_scale, void* stream);
 
+/* Data-parallel tail of a step in ONE kernel (replaces `all_reduce(grads)` + Adam, train/trainer.py:717-725 under
+ * DDP): waits until every rank's gradient buffer of this epoch is complete (flag exchange through peer memory), sums the
+ * `world` buffers in rank order with loads that go to the peers' HBM over NVLink/NVSwitch, and applies Adam (grads times
+ * grad_scale) to this rank's full parameter copies; the replicas stay bit-identical.
+ * params / m / v: HOST arrays of n_nets device pointers, n floats each (one entry per net); net k's gradients are
+ * peer_grads[r] + k * n.  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device addresses valid in this process:
+ * symmetric / peer-mapped allocations): rank r's gradient buffer [n_nets * n] and flag block (uint32[world], zeroed once).
+ * `epoch` starts at 1 and increases by one per step on every rank; the caller alternates between two gradient buffers by
+ * epoch parity (that is what makes one flag exchange per step sufficient).  n % 4 == 0. */
+int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
+                            void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
+                            float beta2, float eps, int64_t t, float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Whole-path entry points (one host call per step / per ray tile)
  * ---------------------------------------------------------------------------------------------- */

@@ -4,6 +4,7 @@
 // (layer 3 writes straight into the [h | gamma(x)] buffer of the skip layer, `feature` into the
 // [feat | gamma(d)] buffer of color_fc), dedicated warp-per-point kernels for the N=1/N=3 heads.
 // The tensor-core mode lives in field_tc.cu.
+#include <cstdio>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -561,9 +562,116 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// ---- data-parallel step tail: all-reduce of the gradient buffers through peer memory + Adam, one kernel ----------------
+// Every rank sums the `world` gradient buffers itself, in rank order (so the replicas stay bit-identical), with loads that
+// go straight to the peers' HBM over NVLink / NVSwitch, and applies Adam to its full parameter copy.  The only
+// synchronisation is a flag exchange at the top of the kernel: block 0 publishes "my gradients of this epoch are complete"
+// into every peer's flag block (release, system scope), every block waits until its own flag block shows the epoch for all
+// ranks (acquire).  The caller double-buffers the gradients (epoch parity), so no second barrier is needed: a rank can
+// only overwrite a buffer two epochs later, after every peer has announced the epoch in between.
+constexpr int kMaxPeers = 16;
+constexpr int kMaxNets = 4;
+struct AdamArParams {
+    float* p[kMaxNets]; float* m[kMaxNets]; float* v[kMaxNets];   // n floats each; net k's gradients are grads[r] + k * n
+    const float* grads[kMaxPeers];          // every rank's gradient buffer (peer-mapped addresses), n_nets * n floats
+    uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
+    int rank, world, n_nets; uint32_t epoch;
+    int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
+};
+__device__ __forceinline__ uint64_t ar_global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+    float4 x;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(p));
+    return x;
+}
+template <int WORLD>      // 0: run-time world size
+__global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_constant__ AdamArParams a) {
+    const int world = WORLD ? WORLD : a.world;
+    if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        if (blockIdx.x == 0) {      // the gradient kernels of this stream have finished: publish that to rank r
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(a.epoch) : "memory");
+        }
+        uint32_t seen;
+        uint64_t t0 = 0;
+        for (uint32_t i = 1;; ++i) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.flags[a.rank] + r) : "memory");
+            if ((int32_t)(seen - a.epoch) >= 0) break;
+            if (i & 0x3FFu) continue;
+            if (t0 == 0) { t0 = ar_global_ns(); continue; }
+            if (ar_global_ns() - t0 > 5000000000ull) {      // 5 s: a peer never arrived -- trap instead of hanging the GPU
+                printf("nsb adam_allreduce: rank %d still waiting for rank %d at epoch %u\n", a.rank, r, a.epoch);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t n4 = a.n >> 2, total4 = n4 * a.n_nets;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / n4);
+        const int64_t j = i - k * n4;
+        // all peers' loads in flight before the first add; summed in rank order: identical on every rank
+        float4 x[WORLD ? WORLD : 1];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (WORLD) {
+#pragma unroll
+            for (int r = 0; r < (WORLD ? WORLD : 1); ++r) x[r] = ld_peer(reinterpret_cast<const float4*>(a.grads[r]) + i);
+#pragma unroll
+            for (int r = 0; r < (WORLD ? WORLD : 1); ++r) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
+        } else {
+            for (int r = 0; r < world; ++r) {
+                const float4 y = ld_peer(reinterpret_cast<const float4*>(a.grads[r]) + i);
+                g.x += y.x; g.y += y.y; g.z += y.z; g.w += y.w;
+            }
+        }
+        float4 pm = reinterpret_cast<float4*>(a.m[k])[j], pv = reinterpret_cast<float4*>(a.v[k])[j], pp = reinterpret_cast<float4*>(a.p[k])[j];
+        float* gg = &g.x; float* mm = &pm.x; float* vv = &pv.x; float* pq = &pp.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float gi = gg[c] * a.grad_scale;
+            mm[c] = a.b1 * mm[c] + (1.0f - a.b1) * gi;
+            vv[c] = a.b2 * vv[c] + (1.0f - a.b2) * gi * gi;
+            pq[c] -= a.lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * a.inv_sqrt_bc2 + a.eps));
+        }
+        reinterpret_cast<float4*>(a.m[k])[j] = pm; reinterpret_cast<float4*>(a.v[k])[j] = pv; reinterpret_cast<float4*>(a.p[k])[j] = pp;
+    }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
+                                       void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
+                                       float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+    if (!params || !m || !v || !peer_grads || !peer_flags || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 || world < 1 ||
+        world > kMaxPeers || rank < 0 || rank >= world)
+        return NSB_E_BADARG;
+    AdamArParams a{};
+    for (int k = 0; k < n_nets; ++k) {
+        if (!params[k] || !m[k] || !v[k]) return NSB_E_BADARG;
+        a.p[k] = params[k]; a.m[k] = m[k]; a.v[k] = v[k];
+    }
+    for (int r = 0; r < world; ++r) {
+        if (!peer_grads[r] || !peer_flags[r]) return NSB_E_BADARG;
+        a.grads[r] = static_cast<const float*>(peer_grads[r]); a.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+    }
+    const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+    a.rank = rank; a.world = world; a.n_nets = n_nets; a.epoch = epoch; a.n = n;
+    a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    a.grad_scale = grad_scale;
+    // every block spins on the flag exchange first, so the grid must be co-resident: at most four blocks of 256 per SM
+    int grid = (int)cdiv((n >> 2) * n_nets, 256);
+    if (grid > 4 * num_sms()) grid = 4 * num_sms();
+    cudaStream_t st = as_stream(stream);
+    if (world == 2) adam_allreduce_kernel<2><<<grid, 256, 0, st>>>(a);
+    else if (world == 4) adam_allreduce_kernel<4><<<grid, 256, 0, st>>>(a);
+    else if (world == 8) adam_allreduce_kernel<8><<<grid, 256, 0, st>>>(a);
+    else adam_allreduce_kernel<0><<<grid, 256, 0, st>>>(a);
+    NSB_LAUNCH_CHECK("adam_allreduce_kernel");
+    return NSB_OK;
+}
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
     if (Q == 0) return NSB_OK;

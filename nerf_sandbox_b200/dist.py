@@ -33,6 +33,39 @@ def allreduce_grads(flat_grads: torch.Tensor, group=None) -> int:
     return world
 
 
+class PeerGrads:
+    """Double-buffered flat gradient buffers in symmetric memory (every rank can load every other rank's buffer over
+    NVLink) plus a flag block, for `nsb_adam_allreduce_step`: the all-reduce and Adam run as one kernel with no NCCL
+    call on the step path.  `buffer(epoch)` is the gradient buffer of that step (epoch parity), `pointers(epoch, ofs)`
+    the ctypes arrays of all ranks' addresses of it."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = world_info(group)
+        group = group if group is not None else dist.group.WORLD
+        self.n = int(n_floats)
+        self.buf = symm_mem.empty(2 * self.n, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.buf.zero_(); self.flags.zero_()
+        self._h_buf = symm_mem.rendezvous(self.buf, group.group_name)
+        self._h_flags = symm_mem.rendezvous(self.flags, group.group_name)
+        self.buf_ptrs = [int(p) for p in self._h_buf.buffer_ptrs]
+        self.flag_ptrs = [int(p) for p in self._h_flags.buffer_ptrs]
+        self._C = C
+        self.flag_array = (C.c_void_p * self.world)(*self.flag_ptrs)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # every rank's buffers are zeroed before anyone's first epoch
+
+    def buffer(self, epoch: int) -> torch.Tensor:
+        h = epoch & 1
+        return self.buf[h * self.n:(h + 1) * self.n]
+
+    def pointers(self, epoch: int, float_offset: int = 0):
+        byte_ofs = ((epoch & 1) * self.n + float_offset) * 4
+        return (self._C.c_void_p * self.world)(*[p + byte_ofs for p in self.buf_ptrs])
+
+
 def gather_shards(local: torch.Tensor, n_total: int, group=None, align: int = 1) -> torch.Tensor:
     """All-gather row shards produced with shard_range(n_total, rank, world, align) back into [n_total, ...]."""
     rank, world = world_info(group)

@@ -11,10 +11,12 @@ NeRF, Adam state -- and exposes
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
-from .dist import allreduce_grads
+from .dist import PeerGrads, allreduce_grads, world_info
 from .encoders import get_vanilla_nerf_encoders
 from .mlps import NeRF
 
@@ -46,7 +48,7 @@ class _FusedStepFn(torch.autograd.Function):
 class VanillaTrainer:
     def __init__(self, device="cuda", *, rays_per_batch=1024, nc=64, nf=128, near=2.0, far=6.0, white_bkgd=True,
                  raw_noise_std=1.0, infinite_last_bin=True, det_fine=False, lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
-                 mode="fp32", seed=0, sigma_bias=None, process_group=None):
+                 mode="fp32", seed=0, sigma_bias=None, process_group=None, allreduce="auto"):
         # hard-coded vanilla settings of the reference: trainer.py:277-291, :411-416; train_nerf.py:275,281
         self.device = torch.device(device)
         self.nc, self.nf, self.samp_near, self.samp_far = int(nc), int(nf), float(near), float(far)
@@ -71,7 +73,26 @@ class VanillaTrainer:
             m.to(self.device)
         n = _lib.N_PARAMS
         z = lambda: torch.zeros(n, device=self.device, dtype=torch.float32)
-        self.grads_all = torch.zeros(2 * n, device=self.device, dtype=torch.float32)   # one buffer -> one all-reduce
+        # multi-GPU: "p2p" = gradient buffers in symmetric memory, all-reduce fused into the Adam kernel over peer loads
+        # (nsb_adam_allreduce_step); "nccl" = one NCCL sum-allreduce + the plain Adam kernel; "auto" = p2p when the process
+        # group spans several CUDA ranks and symmetric memory can be set up, else nccl
+        self.peer = None
+        world = world_info(process_group)[1]
+        if allreduce not in ("auto", "p2p", "nccl"):
+            raise ValueError("allreduce must be 'auto', 'p2p' or 'nccl'")
+        if world > 1 and allreduce in ("auto", "p2p") and self.device.type == "cuda":
+            try:
+                self.peer = PeerGrads(2 * n, self.device, process_group)
+            except Exception as exc:                                   # no symmetric memory on this system / torch build
+                if allreduce == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"symmetric-memory gradient buffers unavailable ({exc!r}); using the NCCL all-reduce")
+        self.epoch = 0
+        if self.peer is not None:
+            self.grads_all = self.peer.buffer(1)
+        else:
+            self.grads_all = torch.zeros(2 * n, device=self.device, dtype=torch.float32)   # one buffer -> one all-reduce
         self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self.m_c, self.v_c, self.m_f, self.v_f = z(), z(), z(), z()
         self.scalars = torch.zeros(4, device=self.device, dtype=torch.float32)
@@ -121,11 +142,26 @@ class VanillaTrainer:
     def step(self, batch, draws=None):
         """forward + backward (+ all-reduce) + Adam + re-pack.  Returns the device scalars tensor
         [loss, psnr, mse_c, mse_f] of this rank's shard (no host sync)."""
+        L = _lib.lib()
+        n = _lib.N_PARAMS
+        self.epoch += 1
+        if self.peer is not None:                             # this step's gradient buffer (double-buffered by epoch parity)
+            self.grads_all = self.peer.buffer(self.epoch)
+            self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self._fwd_bwd(batch, draws, grad_scale=1.0)
-        world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
         self.adam_t += 1
         self.global_step += 1
-        L = _lib.lib()
+        if self.peer is not None:
+            # all-reduce + Adam in one kernel per net: peer loads over NVLink, no NCCL call on the step path
+            pr = self.peer
+            arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+            _lib.check(L.nsb_adam_allreduce_step(arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]), arr([self.m_c, self.m_f]),
+                                                 arr([self.v_c, self.v_f]), 2, pr.pointers(self.epoch), pr.flag_array, pr.rank, pr.world,
+                                                 self.epoch, n, self.lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
+                                                 1.0 / pr.world, _lib.stream()), "nsb_adam_allreduce_step")
+            self.nerf_c.packed(force=True); self.nerf_f.packed(force=True)
+            return self.scalars
+        world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
         for nerf, g, m, v in ((self.nerf_c, self.grads_c, self.m_c, self.v_c), (self.nerf_f, self.grads_f, self.m_f, self.v_f)):
             flat = nerf.flat_params()
             _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, self.lr,

@@ -1,5 +1,5 @@
-"""2-GPU NCCL test (skipped on a 1-GPU box): ray-sharded training keeps the replicas identical and the pixel-tiled
-frame equals the single-GPU frame."""
+"""2-GPU test (skipped on a 1-GPU box): ray-sharded training keeps the replicas identical with both gradient exchanges (NCCL
+all-reduce; all-reduce fused into the Adam kernel over peer memory) and the pixel-tiled frame equals the single-GPU frame."""
 import os
 import subprocess
 import sys
@@ -20,13 +20,46 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
 dist.init_process_group("nccl", device_id=dev)
 T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-tr = nsb.VanillaTrainer(dev, mode=os.environ.get("NSB_MODE", "bf16"), seed=0, sigma_bias=0.4)
-for step in range(3):
-    rays = O.synthetic_rays(np.random.default_rng(100 * step + rank), 256)      # different rays per rank
-    tr.step({k: T(v) for k, v in rays.items()})
-flat = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()])
-ref = flat.clone(); dist.broadcast(ref, 0)
-assert torch.equal(flat, ref), "replicas diverged"
+flats = {}
+for ar in ("nccl", "p2p"):          # NCCL sum-allreduce + Adam   vs   nsb_adam_allreduce_step (peer loads, one kernel)
+    tr = nsb.VanillaTrainer(dev, mode=os.environ.get("NSB_MODE", "bf16"), seed=0, sigma_bias=0.4, allreduce=ar)
+    assert (tr.peer is not None) == (ar == "p2p")
+    for step in range(4):
+        rays = O.synthetic_rays(np.random.default_rng(100 * step + rank), 256)      # different rays per rank
+        tr.step({k: T(v) for k, v in rays.items()})
+    flat = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()])
+    ref = flat.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref), f"replicas diverged ({ar})"
+    flats[ar] = flat
+# (the two trainers are not compared with each other: the wgrad flush uses float atomics, and Adam turns last-bit gradient
+# differences into +-lr parameter differences in the first steps)
+# nsb_adam_allreduce_step against NCCL all-reduce + nsb_adam_step on the SAME gradients: two summands commute, so at world
+# size 2 the results must agree bit for bit; otherwise to rounding of the different summation order
+import ctypes as C
+from nerf_sandbox_b200 import _lib
+L = _lib.lib(); n = 4096
+pg = D.PeerGrads(2 * n, dev)
+g = torch.Generator(device=dev); g.manual_seed(5)
+st = [[torch.randn(n, device=dev, generator=g) * s for s in (1.0, 0.0, 0.0)] for _ in range(2)]     # p, m, v of 2 nets ...
+st += [[t.clone() for t in trip] for trip in st]                                                    # ... for the two paths
+arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+for epoch in range(1, 4):
+    gr = torch.Generator(device=dev); gr.manual_seed(1000 * epoch + rank)
+    grads = torch.randn(2 * n, device=dev, generator=gr)
+    pg.buffer(epoch).copy_(grads)
+    _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
+                                         pg.pointers(epoch), pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
+                                         1.0 / world, _lib.stream()), "fused")
+    red = grads.clone(); dist.all_reduce(red)
+    for k in range(2):
+        _lib.check(L.nsb_adam_step(_lib.ptr(st[2 + k][0]), _lib.ptr(red[k * n:(k + 1) * n]), _lib.ptr(st[2 + k][1]), _lib.ptr(st[2 + k][2]),
+                                   n, 5e-4, 0.9, 0.999, 1e-8, epoch, 1.0 / world, _lib.stream()), "adam")
+    for k in range(2):
+        for a, b in zip(st[k], st[2 + k]):
+            if world == 2:
+                assert torch.equal(a, b), (epoch, k, float((a - b).abs().max()))
+            else:
+                torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
 H, W = 20, 31
 rays = O.synthetic_rays(np.random.default_rng(7), H * W)
 args = (T(rays["rays_o_marching"]), T(rays["rays_d_marching_unit"]), T(rays["rays_d_marching_norm"]).reshape(-1))
