@@ -124,6 +124,10 @@ size_t nsb_packed_weights_bytes(void);
  * mode selects which section is refreshed: NSB_MODE_FP32, NSB_MODE_BF16, or -1 for both. */
 int nsb_pack_weights(const float* params, void* packed, int mode, void* stream);
 
+/* The same for up to four nets in one call (training re-packs coarse + fine after every optimiser step: one kernel launch in
+ * tensor-core mode).  params / packed: HOST arrays of n_nets device pointers. */
+int nsb_pack_weights_batch(const float* const* params, void* const* packed, int n_nets, int mode, void* stream);
+
 /* Workspace for one pass over Q = B*N points.  stash != 0 keeps what the backward needs. */
 size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash);
 

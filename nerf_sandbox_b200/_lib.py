@@ -39,6 +39,7 @@ SIGNATURES = {
     "nsb_encode": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p]),
     "nsb_packed_weights_bytes": (_sz, []),
     "nsb_pack_weights": (_i32, [_p, _p, _i32, _p]),
+    "nsb_pack_weights_batch": (_i32, [_p, _p, _i32, _i32, _p]),
     "nsb_field_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "nsb_field_fwd_enc": (_i32, [_p, _p, _p, _p, _p, _sz, _i64, _i32, _i32, _p]),
     "nsb_field_fwd_rays": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i32, _i32, _i32, _p]),

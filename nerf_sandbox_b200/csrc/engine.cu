@@ -39,7 +39,7 @@ int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash,
 int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
 // field_tc.cu
 size_t tc_workspace_bytes(int64_t Q, int stash);
-int tc_pack(const float* params, void* packed_bf16, cudaStream_t st);
+int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st);
 int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
                       float* raw, void* ws, int64_t B, int N, int stash, cudaStream_t st);
 int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, void* ws, int64_t Q,
@@ -72,11 +72,20 @@ extern "C" const char* nsb_last_cuda_error(void) { return g_cuda_err; }
 extern "C" int64_t nsb_launch_count(void) { return g_launches; }
 
 extern "C" size_t nsb_packed_weights_bytes(void) { return packed_layout().total; }
-extern "C" int nsb_pack_weights(const float* params, void* packed, int mode, void* stream) {
-    if (!params || !packed || mode < -1 || mode > NSB_MODE_BF16) return NSB_E_BADARG;
-    if (mode != NSB_MODE_BF16) NSB_TRY(pack_fp32(params, packed, as_stream(stream)));
-    if (mode != NSB_MODE_FP32) NSB_TRY(tc_pack(params, reinterpret_cast<char*>(packed) + packed_layout().bf16_off, as_stream(stream)));
+extern "C" int nsb_pack_weights_batch(const float* const* params, void* const* packed, int n_nets, int mode, void* stream) {
+    if (!params || !packed || n_nets < 1 || n_nets > 4 || mode < -1 || mode > NSB_MODE_BF16) return NSB_E_BADARG;
+    void* bf16[4];
+    for (int i = 0; i < n_nets; ++i) {
+        if (!params[i] || !packed[i]) return NSB_E_BADARG;
+        bf16[i] = reinterpret_cast<char*>(packed[i]) + packed_layout().bf16_off;
+        if (mode != NSB_MODE_BF16) NSB_TRY(pack_fp32(params[i], packed[i], as_stream(stream)));
+    }
+    if (mode != NSB_MODE_FP32) NSB_TRY(tc_pack(params, bf16, n_nets, as_stream(stream)));     // one launch for all nets and images
     return NSB_OK;
+}
+
+extern "C" int nsb_pack_weights(const float* params, void* packed, int mode, void* stream) {
+    return nsb_pack_weights_batch(&params, &packed, 1, mode, stream);
 }
 
 extern "C" size_t nsb_field_workspace_bytes(int64_t Q, int mode, int stash) { return field_ws(Q, mode, stash); }

@@ -838,9 +838,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
 }
 
 // ---- weight packing: flat fp32 params -> bf16 shared-memory images + fp32 tail ------------------------
-__global__ void pack_tc_kernel(const float* __restrict__ params, uint8_t* __restrict__ out) {
+__device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params, uint8_t* __restrict__ out, int m) {
     // MMA layer m (0..9) <- parameter layer index: 0..7 trunk, 8 feature, 10 color_fc
-    for (int m = blockIdx.y; m < kNumMmaLayers; m += gridDim.y) {
+    {
         const int pl = m < 9 ? m : 10;
         const LayerDesc d = layer_desc(pl);
         const int N = d.N, Kp = d.Kpad;
@@ -856,7 +856,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ params, uint8_t* __rest
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
             tail[layer_bias_ofs(m) + n] = params[d.b_off + n];
     }
-    if (blockIdx.y == 0) {
+    if (m == 0) {
         float* tail = reinterpret_cast<float*>(out + kBiasOfs);
         const LayerDesc ds = layer_desc(9), dc = layer_desc(11);
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 256; i += gridDim.x * blockDim.x) tail[kWsigOfs + i] = params[ds.w_off + i];
@@ -1391,8 +1391,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
 }
 
 // transposed images for the dgrad chain
-__global__ void pack_tc_transposed_kernel(const float* __restrict__ params, uint8_t* __restrict__ out) {
-    for (int m = blockIdx.y; m < kNumDgradLayers; m += gridDim.y) {
+__device__ __forceinline__ void pack_tc_transposed(const float* __restrict__ params, uint8_t* __restrict__ out, int m) {
+    {
         const int pl = m == 0 ? 10 : (m == 1 ? 8 : 9 - m);
         const LayerDesc d = layer_desc(pl);
         const int Nout = d.N;                                  // contraction length (128 or 256)
@@ -1403,6 +1403,14 @@ __global__ void pack_tc_transposed_kernel(const float* __restrict__ params, uint
                 __float2bfloat16_rn(params[d.w_off + (int64_t)n * d.K + j]);
         }
     }
+}
+// one launch packs every image of up to four nets: blockIdx.y = forward layer 0..9 | 10 + dgrad step 0..8, blockIdx.z = net
+struct PackBatch { const float* params[4]; uint8_t* out[4]; };
+__global__ void pack_tc_kernel(const PackBatch b) {
+    const float* params = b.params[blockIdx.z];
+    uint8_t* out = b.out[blockIdx.z];
+    if (blockIdx.y < kNumMmaLayers) pack_tc_forward(params, out, blockIdx.y);
+    else pack_tc_transposed(params, out, blockIdx.y - kNumMmaLayers);
 }
 
 }  // namespace tc
@@ -1416,11 +1424,11 @@ size_t tc_workspace_bytes(int64_t Q, int stash) {
 static inline uint8_t* ws_stash(void* ws) { return reinterpret_cast<uint8_t*>(ws) + 256; }
 static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (size_t)cdiv(Q, tc::TILE_M) * tc::kStashTile; }
 
-int tc_pack(const float* params, void* packed_bf16, cudaStream_t st) {
-    tc::pack_tc_kernel<<<dim3(32, tc::kNumMmaLayers), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed_bf16));
+int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st) {
+    tc::PackBatch b{};
+    for (int i = 0; i < n_nets; ++i) { b.params[i] = params[i]; b.out[i] = reinterpret_cast<uint8_t*>(packed_bf16[i]); }
+    tc::pack_tc_kernel<<<dim3(32, tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
     NSB_LAUNCH_CHECK("pack_tc_kernel");
-    tc::pack_tc_transposed_kernel<<<dim3(32, tc::kNumDgradLayers), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed_bf16));
-    NSB_LAUNCH_CHECK("pack_tc_transposed_kernel");
     return NSB_OK;
 }
 

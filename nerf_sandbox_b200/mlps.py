@@ -154,6 +154,19 @@ class NeRF(nn.Module):
             self._packed_version = version
         return self._packed
 
+    @staticmethod
+    def repack(nets) -> None:
+        """Re-pack several nets with one call (nsb_pack_weights_batch: a single launch in tensor-core mode); what the
+        trainer does after every optimiser step."""
+        import ctypes as C
+        nets = list(nets)
+        bufs = [n.packed() if n._packed is None else n._packed for n in nets]
+        arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+        _lib.check(_lib.lib().nsb_pack_weights_batch(arr([n.flat_params() for n in nets]), arr(bufs), len(nets), nets[0].mode,
+                                                     _lib.stream()), "nsb_pack_weights_batch")
+        for n in nets:
+            n._packed_version = sum(p._version for p in n.ordered_params())
+
     # ---- forward ------------------------------------------------------------------------------------
     def forward(self, enc_pos: torch.Tensor, enc_dir: torch.Tensor) -> torch.Tensor:
         if self._debug_active():

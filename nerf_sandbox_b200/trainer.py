@@ -159,7 +159,7 @@ class VanillaTrainer:
                                                  arr([self.v_c, self.v_f]), 2, pr.pointers(self.epoch), pr.flag_array, pr.rank, pr.world,
                                                  self.epoch, n, self.lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
                                                  1.0 / pr.world, _lib.stream()), "nsb_adam_allreduce_step")
-            self.nerf_c.packed(force=True); self.nerf_f.packed(force=True)
+            NeRF.repack((self.nerf_c, self.nerf_f))
             return self.scalars
         world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
         for nerf, g, m, v in ((self.nerf_c, self.grads_c, self.m_c, self.v_c), (self.nerf_f, self.grads_f, self.m_f, self.v_f)):
@@ -167,7 +167,7 @@ class VanillaTrainer:
             _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, self.lr,
                                        self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.stream()),
                        "nsb_adam_step")
-            nerf.packed(force=True)
+        NeRF.repack((self.nerf_c, self.nerf_f))
         return self.scalars
 
     def state_dict(self):                                      # trainer.py:596-621 (hot-path subset)
