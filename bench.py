@@ -204,18 +204,25 @@ def main():
 
     # ---- device-resident timing ("value") --------------------------------------------------------------
     clk = ClockSampler(local) if rank == 0 else None      # samples through warm-up + both timed regions (all under load)
+    # the step is one CUDA-graph replay (VanillaTrainer.step_graph = nsb_train_step captured once; step count, Philox streams
+    # and Adam bias corrections live in device memory) unless NSB_BENCH_GRAPH=0 or the gradient exchange goes through NCCL
+    use_graph = os.environ.get("NSB_BENCH_GRAPH", "1") != "0" and (world == 1 or tr.peer is not None)
+    do_step = tr.step_graph if use_graph else tr.step
     for i in range(W_):
-        tr.step(devb[i % pool_n])
+        do_step(devb[i % pool_n])
     barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        tr.step(devb[i % pool_n])
+        do_step(devb[i % pool_n])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - l0 + (K if world > 1 else 0)      # + one NCCL all-reduce kernel per step
+    if use_graph:
+        launches = K * tr._graph_launches                              # kernels of ours inside one replayed graph x steps
+    else:
+        launches = _lib.launch_count() - l0 + (K if world > 1 and tr.peer is None else 0)      # + one NCCL all-reduce kernel per step
     loss_dev = float(tr.scalars[0])
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------------------
@@ -227,12 +234,12 @@ def main():
     stage = {k: dpack[offs[i]:offs[i + 1]].view(host[0][k].shape) for i, k in enumerate(keys)}
     for i in range(3):
         dpack.copy_(hpack[i % pool_n], non_blocking=True)
-        tr.step(stage); tr.scalars.cpu()
+        do_step(stage); tr.scalars.cpu()
     barrier()
     e0.record()
     for i in range(K):
         dpack.copy_(hpack[i % pool_n], non_blocking=True)
-        loss_host = tr.step(stage).cpu()
+        loss_host = do_step(stage).cpu()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -319,7 +326,8 @@ def main():
             "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step/GPU, 64 coarse + 128 fine, "
                                    "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])",
                        "rays_per_step_per_gpu": RAYS, "parallelism": f"ray-sharded dp{world}, {exchange} of 2x595,844 fp32 grads",
-                       "mode": args.mode, "l2": f"no flush: per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2"},
+                       "mode": args.mode, "step": "one CUDA-graph replay (nsb_train_step)" if use_graph else "eager launches",
+                       "l2": f"no flush: per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS * K / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / K},

@@ -64,7 +64,8 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      const float* __restrict__ noise, float noise_std, const float* __restrict__ z,
                      const float* __restrict__ ray_norm, float* __restrict__ comp, float* __restrict__ weights,
                      float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N, uint32_t flags,
-                     float eps, uint64_t seed, uint64_t offset) {
+                     float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
     const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
@@ -118,7 +119,8 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
                      const float* __restrict__ g_weights, const float* __restrict__ g_acc,
                      const float* __restrict__ g_depth, float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma,
-                     int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t offset) {
+                     int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_alpha = smem + (size_t)warp * 3 * N;
@@ -248,7 +250,7 @@ static int launch_bwd(const float* a, const float* sigma, const float* noise, fl
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(composite_bwd_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     composite_bwd_kernel<RAW><<<comp_grid(B), kCompWarps * 32, smem, as_stream(stream)>>>(
-        a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off);
+        a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev);
     NSB_LAUNCH_CHECK("composite_bwd_kernel");
     return NSB_OK;
 }
@@ -300,7 +302,7 @@ extern "C" int nsb_composite_fwd(const float* rgb, const float* sigma, const flo
     if (B == 0) return NSB_OK;
     if (!rgb || !sigma || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     composite_fwd_kernel<false><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
-        rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0);
+        rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, nullptr);
     NSB_LAUNCH_CHECK("composite_fwd_kernel");
     return NSB_OK;
 }
@@ -321,7 +323,7 @@ extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float
     if (B == 0) return NSB_OK;
     if (!raw || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     composite_fwd_kernel<true><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
-        raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset);
+        raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, g_step_dev);
     NSB_LAUNCH_CHECK("composite_raw_fwd_kernel");
     return NSB_OK;
 }

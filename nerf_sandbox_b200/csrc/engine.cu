@@ -39,6 +39,7 @@ int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash,
 int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
 // field_tc.cu
 size_t tc_workspace_bytes(int64_t Q, int stash);
+thread_local const uint64_t* g_step_dev = nullptr;
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st);
 int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
                       float* raw, void* ws, int64_t B, int N, int stash, cudaStream_t st);
@@ -199,6 +200,51 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
     NSB_TRY(nsb_field_bwd(t.d_raw, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, stream));
     if (comp_c && cudaMemcpyAsync(comp_c, t.comp_c, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
     if (comp_f && cudaMemcpyAsync(comp_f, t.comp_f, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
+    return NSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whole optimisation step, replayable as a CUDA graph
+// ---------------------------------------------------------------------------------------------------
+namespace nsb {
+int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int64_t t,
+              float grad_scale, const uint64_t* t_dev, void* stream);
+int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
+                        void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
+                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, void* stream);
+__global__ void counter_inc_kernel(uint64_t* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
+}  // namespace nsb
+
+extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
+                              const float* target, float* const* params, float* const* m, float* const* v, void* const* packed,
+                              float* grads, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes, int64_t B,
+                              int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
+                              uint64_t seed, float lr, float beta1, float beta2, float eps, uint64_t* step_counter,
+                              const void* const* peer_grads, void* const* peer_flags, int rank, int world, void* stream) {
+    if (!params || !m || !v || !packed || !grads || !step_counter) return NSB_E_BADARG;
+    for (int k = 0; k < 2; ++k)
+        if (!params[k] || !m[k] || !v[k] || !packed[k]) return NSB_E_BADARG;
+    if (world < 1 || (world > 1 && (!peer_grads || !peer_flags))) return NSB_E_BADARG;
+    // forward + backward with the Philox streams shifted by the device-side step count
+    g_step_dev = step_counter;
+    int rc = nsb_train_fwd_bwd(rays_o, rays_d, ray_norm, viewdirs, target, packed[0], packed[1], grads, grads + NSB_N_PARAMS, scalars,
+                               comp_c, comp_f, ws, ws_bytes, B, Nc, Nf, near_, far_, noise_std, flags, det_fine, mode, 1.0f, seed,
+                               /*step=*/0, nullptr, nullptr, nullptr, nullptr, stream);
+    g_step_dev = nullptr;
+    if (rc) return rc;
+    // optimiser (+ gradient exchange over peer memory), t = *step_counter + 1
+    if (world > 1) {
+        NSB_TRY(adam_allreduce_impl(params, m, v, 2, peer_grads, peer_flags, rank, world, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1,
+                                    1.0f / (float)world, step_counter, stream));
+    } else {
+        for (int k = 0; k < 2; ++k)
+            NSB_TRY(adam_impl(params[k], grads + (size_t)k * NSB_N_PARAMS, m[k], v[k], NSB_N_PARAMS, lr, beta1, beta2, eps, 1, 1.0f,
+                              step_counter, stream));
+    }
+    const float* cparams[2] = {params[0], params[1]};
+    NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode, stream));
+    counter_inc_kernel<<<1, 32, 0, as_stream(stream)>>>(step_counter);
+    NSB_LAUNCH_CHECK("counter_inc_kernel");
     return NSB_OK;
 }
 

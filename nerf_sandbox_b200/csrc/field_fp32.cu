@@ -550,9 +550,21 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 }
 
 // ---- Adam --------------------------------------------------------------------------------------------
+// bias corrections of step t = *t_dev + 1 (CUDA-graph replay: the step count lives in device memory)
+__device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, float lr, float b1, float b2, float& lr_over_bc1, float& inv_sqrt_bc2) {
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)(*t_dev + 1);
+        s_bc[0] = (float)((double)lr / (1.0 - pow((double)b1, t)));
+        s_bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+    }
+    __syncthreads();
+    lr_over_bc1 = s_bc[0]; inv_sqrt_bc2 = s_bc[1];
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
-                            float inv_sqrt_bc2, float grad_scale) {
+                            float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr) {
+    if (t_dev) adam_bias_corrections(t_dev, lr, b1, b2, lr_over_bc1, inv_sqrt_bc2);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -577,6 +589,7 @@ struct AdamArParams {
     uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
+    const uint64_t* t_dev; float lr;       // graph replay: step count (and epoch) = *t_dev + 1
 };
 __device__ __forceinline__ uint64_t ar_global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
@@ -587,21 +600,24 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 template <int WORLD>      // 0: run-time world size
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_constant__ AdamArParams a) {
     const int world = WORLD ? WORLD : a.world;
+    float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2;
+    uint32_t epoch = a.epoch;
+    if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
     if (threadIdx.x < world) {
         const int r = threadIdx.x;
         if (blockIdx.x == 0) {      // the gradient kernels of this stream have finished: publish that to rank r
             __threadfence_system();
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(a.epoch) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(epoch) : "memory");
         }
         uint32_t seen;
         uint64_t t0 = 0;
         for (uint32_t i = 1;; ++i) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.flags[a.rank] + r) : "memory");
-            if ((int32_t)(seen - a.epoch) >= 0) break;
+            if ((int32_t)(seen - epoch) >= 0) break;
             if (i & 0x3FFu) continue;
             if (t0 == 0) { t0 = ar_global_ns(); continue; }
             if (ar_global_ns() - t0 > 5000000000ull) {      // 5 s: a peer never arrived -- trap instead of hanging the GPU
-                printf("nsb adam_allreduce: rank %d still waiting for rank %d at epoch %u\n", a.rank, r, a.epoch);
+                printf("nsb adam_allreduce: rank %d still waiting for rank %d at epoch %u\n", a.rank, r, epoch);
                 __trap();
             }
         }
@@ -632,7 +648,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
             const float gi = gg[c] * a.grad_scale;
             mm[c] = a.b1 * mm[c] + (1.0f - a.b1) * gi;
             vv[c] = a.b2 * vv[c] + (1.0f - a.b2) * gi * gi;
-            pq[c] -= a.lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * a.inv_sqrt_bc2 + a.eps));
+            pq[c] -= lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * inv_sqrt_bc2 + a.eps));
         }
         reinterpret_cast<float4*>(a.m[k])[j] = pm; reinterpret_cast<float4*>(a.v[k])[j] = pv; reinterpret_cast<float4*>(a.p[k])[j] = pp;
     }
@@ -642,9 +658,10 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
 
 using namespace nsb;
 
-extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
-                                       void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                                       float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+namespace nsb {
+int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
+                        void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
+                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, void* stream) {
     if (!params || !m || !v || !peer_grads || !peer_flags || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 || world < 1 ||
         world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
@@ -660,7 +677,7 @@ extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, fl
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     a.rank = rank; a.world = world; a.n_nets = n_nets; a.epoch = epoch; a.n = n;
     a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    a.grad_scale = grad_scale;
+    a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr;
     // every block spins on the flag exchange first, so the grid must be co-resident: at most four blocks of 256 per SM
     int grid = (int)cdiv((n >> 2) * n_nets, 256);
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
@@ -672,6 +689,14 @@ extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, fl
     NSB_LAUNCH_CHECK("adam_allreduce_kernel");
     return NSB_OK;
 }
+}  // namespace nsb
+
+extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
+                                       void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
+                                       float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+    return adam_allreduce_impl(params, m, v, n_nets, peer_grads, peer_flags, rank, world, epoch, n, lr, beta1, beta2, eps, t, grad_scale,
+                               nullptr, stream);
+}
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
     if (Q == 0) return NSB_OK;
@@ -682,12 +707,19 @@ extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, i
     return NSB_OK;
 }
 
-extern "C" int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
-                             float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+namespace nsb {
+int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int64_t t,
+              float grad_scale, const uint64_t* t_dev, void* stream) {
     if (!params || !grads || !m || !v || n < 1 || t < 1) return NSB_E_BADARG;
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     adam_kernel<<<elem_grid(n), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
-                                                            (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                            (float)(1.0 / sqrt(bc2)), grad_scale, t_dev, lr);
     NSB_LAUNCH_CHECK("adam_kernel");
     return NSB_OK;
+}
+}  // namespace nsb
+
+extern "C" int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+    return adam_impl(params, grads, m, v, n, lr, beta1, beta2, eps, t, grad_scale, nullptr, stream);
 }

@@ -17,7 +17,8 @@ __device__ __forceinline__ float coarse_z_at(int i, int Nc, float near_, float f
 }
 
 __global__ void stratified_kernel(float* __restrict__ z, const float* __restrict__ U, int64_t B, int Nc,
-                                  float near_, float far_, int jitter, uint64_t seed, uint64_t offset) {
+                                  float near_, float far_, int jitter, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
     const int64_t total = B * (int64_t)Nc;
     // four consecutive samples per thread: one Philox4x32 block feeds all four uniforms
     for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; base < total;
@@ -168,7 +169,8 @@ __device__ __forceinline__ int lower_bound_f(const float* a, int n, float v) {
 __global__ void resample_merge_kernel(const float* __restrict__ zc, const float* __restrict__ w_c,
                                       const float* __restrict__ u_in, float* __restrict__ z_all,
                                       float* __restrict__ z_fine, int64_t B, int Nc, int Nf, int sort_len,
-                                      int deterministic, uint64_t seed, uint64_t offset) {
+                                      int deterministic, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = Nc - 1;
@@ -229,7 +231,7 @@ extern "C" int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, flo
     const int64_t total = B * Nc;
     const int64_t want = cdiv(total, 256 * 4);
     const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
-    stratified_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset);
+    stratified_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset, g_step_dev);
     NSB_LAUNCH_CHECK("stratified_kernel");
     return NSB_OK;
 }
@@ -260,7 +262,7 @@ extern "C" int nsb_resample_merge(const float* zc, const float* w_c, const float
     if (smem > 200 * 1024) return NSB_E_BADARG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     resample_merge_kernel<<<grid_for_rays(B), kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
-        zc, w_c, u, z_all, z_fine, B, Nc, Nf, sort_len, deterministic, seed, offset);
+        zc, w_c, u, z_all, z_fine, B, Nc, Nf, sort_len, deterministic, seed, offset, g_step_dev);
     NSB_LAUNCH_CHECK("resample_merge_kernel");
     return NSB_OK;
 }

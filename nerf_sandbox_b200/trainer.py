@@ -97,6 +97,7 @@ class VanillaTrainer:
         self.m_c, self.v_c, self.m_f, self.v_f = z(), z(), z(), z()
         self.scalars = torch.zeros(4, device=self.device, dtype=torch.float32)
         self._ws = None
+        self._graphs = None
         self.nerf_c.packed(); self.nerf_f.packed()
 
     # ---- helpers ---------------------------------------------------------------------------------------
@@ -168,6 +169,66 @@ class VanillaTrainer:
                                        self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.stream()),
                        "nsb_adam_step")
         NeRF.repack((self.nerf_c, self.nerf_f))
+        return self.scalars
+
+    # ---- fast path, CUDA-graph replay ------------------------------------------------------------------------
+    def _launch_train_step(self, parity: int):
+        """nsb_train_step on the static batch buffers: the whole step with the step count in device memory."""
+        L = _lib.lib()
+        n = _lib.N_PARAMS
+        st = self._static
+        B = st["rays_o_marching"].shape[0]
+        ws, wsb = self._workspace(B)
+        arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+        if self.peer is not None:
+            grads, pg, pf, rank, world = self.peer.buffer(parity), self.peer.pointers(parity), self.peer.flag_array, self.peer.rank, self.peer.world
+        else:
+            grads, pg, pf, rank, world = self.grads_all, None, None, 0, 1
+        _lib.check(L.nsb_train_step(
+            _lib.ptr(st["rays_o_marching"]), _lib.ptr(st["rays_d_marching_unit"]), _lib.ptr(st["rays_d_marching_norm"].reshape(B)),
+            _lib.ptr(st["rays_d_world_unit"]), _lib.ptr(st["rgb"]), arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]),
+            arr([self.m_c, self.m_f]), arr([self.v_c, self.v_f]), arr([self.nerf_c.packed(), self.nerf_f.packed()]), _lib.ptr(grads),
+            _lib.ptr(self.scalars), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
+            self.nf, self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode, self.seed,
+            self.lr, self.betas[0], self.betas[1], self.eps, _lib.ptr(self._step_dev), pg, pf, rank, world, _lib.stream()),
+            "nsb_train_step")
+
+    def step_graph(self, batch):
+        """`step()` as ONE CUDA-graph replay (train/trainer.py:702-729 without per-step host work).  The batch is copied
+        into static device buffers (host tensors: an H2D copy; pinned memory makes it asynchronous); random draws and the
+        Adam bias corrections follow a step counter in device memory.  With several GPUs this needs the peer-memory
+        gradient exchange (`allreduce='p2p'`): NCCL calls are not part of the captured step.  Returns the device
+        scalars tensor [loss, psnr, mse_c, mse_f] (no host sync)."""
+        if world_info(self.pg)[1] > 1 and self.peer is None:
+            raise RuntimeError("step_graph needs the peer-memory gradient exchange (allreduce='p2p') on several GPUs")
+        if self.adam_t != self.global_step:
+            raise RuntimeError("step_graph derives Philox streams and Adam's t from one counter: adam_t must equal global_step")
+        B = batch["rays_o_marching"].shape[0]
+        if self._graphs is None or self._static["rays_o_marching"].shape[0] != B:
+            self._static = {k: torch.empty(tuple(batch[k].shape), dtype=torch.float32, device=self.device) for k in BATCH_KEYS}
+            self._static_comp = (torch.empty((B, 3), device=self.device), torch.empty((B, 3), device=self.device))
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            for k in BATCH_KEYS:
+                self._static[k].copy_(batch[k])
+            self._fwd_bwd(self._static)                      # eager warm-up of every kernel on the path (no state change)
+            self.nerf_c.packed(); self.nerf_f.packed()
+            torch.cuda.synchronize(self.device)
+            self._graphs, self._graph_launches = [], 0
+            for parity in ((0, 1) if self.peer is not None else (0,)):
+                g = torch.cuda.CUDAGraph()
+                before = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    self._launch_train_step(parity)
+                self._graph_launches = _lib.launch_count() - before
+                self._graphs.append(g)
+            self._step_host = -1
+        if self._step_host != self.adam_t:                   # (re)synchronise the device counter with the host's step count
+            self._step_dev.fill_(self.adam_t)
+            self._step_host = self.adam_t
+        for k in BATCH_KEYS:
+            self._static[k].copy_(batch[k], non_blocking=True)
+        self.epoch += 1; self.adam_t += 1; self.global_step += 1; self._step_host += 1
+        self._graphs[self.adam_t & 1 if self.peer is not None else 0].replay()
         return self.scalars
 
     def state_dict(self):                                      # trainer.py:596-621 (hot-path subset)
