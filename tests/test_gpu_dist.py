@@ -27,6 +27,11 @@ for ar in ("nccl", "p2p"):          # NCCL sum-allreduce + Adam   vs   nsb_adam_
     for step in range(4):
         rays = O.synthetic_rays(np.random.default_rng(100 * step + rank), 256)      # different rays per rank
         tr.step({k: T(v) for k, v in rays.items()})
+    if ar == "p2p":                 # the same exchange inside the CUDA-graph step (one graph per gradient-buffer parity)
+        for step in range(4, 9):
+            rays = O.synthetic_rays(np.random.default_rng(100 * step + rank), 256)
+            tr.step_graph({k: T(v) for k, v in rays.items()})
+        assert tr.adam_t == 9 and int(tr._step_dev.item()) == 9
     flat = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()])
     ref = flat.clone(); dist.broadcast(ref, 0)
     assert torch.equal(flat, ref), f"replicas diverged ({ar})"
