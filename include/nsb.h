@@ -234,6 +234,16 @@ int nsb_sample_pixel_batch(const float* images, int F, int H, int W, int C, cons
                            float* o_world, float* d_world_unit, float* d_world_norm, float* o_march, float* d_march_unit,
                            float* d_march_norm, void* stream);
 
+/* Eval output path: what ValidationRenderer does with a rendered frame,
+ * utils/validation_renderer.py:485-533 with save_rgb_png / save_gray_png (utils/render_utils.py:28-47) and _compute_psnr
+ * (:171-196), without leaving the device: rgb8[n,3] / acc8[n] / depth8[n] = (clamp(x,0,1) * 255 + 0.5) truncated to uint8,
+ * depth first mapped to clamp((depth - near) / (far - near + 1e-8)) (or used as is when use_ndc); any output may be NULL.
+ * With gt_rgb[n,3] (and optional mask[n], 1 = valid): psnr_out[0] = -10 log10(max(mse, 1e-10)), psnr_out[1] = mse with
+ * mse = sum(mask * diff^2) / max(3 * sum(mask), 1e-8) over clamped values; psnr_scratch = 2 doubles of device scratch. */
+int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, float depth_near, float depth_far,
+                     int use_ndc, uint8_t* rgb8, uint8_t* acc8, uint8_t* depth8, const float* gt_rgb, const float* mask,
+                     double* psnr_scratch, float* psnr_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

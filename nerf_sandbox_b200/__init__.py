@@ -9,6 +9,8 @@ from .render import volume_render_rays, nerf_forward_pass, render_image_chunked,
 from .rays import get_camera_rays, render_pose
 from .samplers import RandomPixelRaySampler
 from .trainer import VanillaTrainer
+from .validation import frame_outputs, compute_psnr
 
 __all__ = ["PositionalEncoder", "get_vanilla_nerf_encoders", "NeRF", "log_nerf_arch", "sample_pdf", "volume_render_rays",
-           "nerf_forward_pass", "render_image_chunked", "render_rays", "get_camera_rays", "render_pose", "RandomPixelRaySampler", "VanillaTrainer"]
+           "nerf_forward_pass", "render_image_chunked", "render_rays", "get_camera_rays", "render_pose", "RandomPixelRaySampler", "VanillaTrainer",
+           "frame_outputs", "compute_psnr"]

@@ -53,6 +53,7 @@ SIGNATURES = {
                               _p, _p, _p, _i32, _i32, _p]),
     "nsb_render_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nsb_render_rays": (_i32, [_p] * 10 + [_sz, _i64, _i32, _i32, _f32, _f32, _u32, _i32, _p]),
+    "nsb_frame_output": (_i32, [_p, _p, _p, _i64, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "nsb_camera_rays": (_i32, [_i32, _i32, _p, _p, _i32, _i32, _i32, _i32, _f32, _p, _i64] + [_p] * 7),
     "nsb_sample_pixel_batch": (_i32, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32,
                                       _i64, _u64, _u64] + [_p] * 10),

@@ -105,9 +105,67 @@ __global__ void sample_pixel_batch_kernel(const float* __restrict__ images, int 
     }
 }
 
+// ---- eval output path: what validation_renderer.py:485-533 + render_utils.py:28-47 do with a frame ----
+// u8 = (clamp(x, 0, 1) * 255 + 0.5) truncated  (two roundings: this file is compiled with -fmad=false, like numpy)
+__device__ __forceinline__ uint8_t to_u8(float x) { return (uint8_t)(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f); }
+__global__ void frame_output_kernel(const float* __restrict__ rgb, const float* __restrict__ acc, const float* __restrict__ depth, int64_t n,
+                                    float near_, float inv_range, int use_ndc, uint8_t* __restrict__ rgb8, uint8_t* __restrict__ acc8,
+                                    uint8_t* __restrict__ depth8, const float* __restrict__ gt, const float* __restrict__ mask,
+                                    double* __restrict__ psnr_acc) {
+    double se = 0.0, wsum = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+        if (rgb8) { rgb8[3 * i] = to_u8(r); rgb8[3 * i + 1] = to_u8(g); rgb8[3 * i + 2] = to_u8(b); }
+        if (acc8 && acc) acc8[i] = to_u8(acc[i]);
+        if (depth8 && depth) depth8[i] = to_u8(use_ndc ? depth[i] : (depth[i] - near_) * inv_range);     // :491-492
+        if (gt && psnr_acc) {                                                                           // _compute_psnr, :171-196
+            const float m = mask ? mask[i] : 1.0f;
+            float e = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float d = fminf(fmaxf(rgb[3 * i + c], 0.0f), 1.0f) - fminf(fmaxf(gt[3 * i + c], 0.0f), 1.0f);
+                e += d * d;
+            }
+            se += (double)(e * m); wsum += (double)m;
+        }
+    }
+    if (gt && psnr_acc) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, d); wsum += __shfl_xor_sync(0xffffffffu, wsum, d); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(psnr_acc, se); atomicAdd(psnr_acc + 1, wsum); }
+    }
+}
+__global__ void psnr_finish_kernel(const double* __restrict__ acc, float* __restrict__ out) {
+    // mse = sum(diff^2 * m) / max(sum(m) * 3, 1e-8);  psnr = -10 log10(max(mse, 1e-10))
+    const double denom = acc[1] * 3.0 > 1e-8 ? acc[1] * 3.0 : 1e-8;
+    const double mse = acc[0] / denom;
+    out[0] = (float)(-10.0 * log10(mse > 1e-10 ? mse : 1e-10));
+    out[1] = (float)mse;
+}
+
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, float depth_near, float depth_far,
+                                int use_ndc, uint8_t* rgb8, uint8_t* acc8, uint8_t* depth8, const float* gt_rgb, const float* mask,
+                                double* psnr_scratch, float* psnr_out, void* stream) {
+    if (n == 0) return NSB_OK;
+    if (!rgb || n < 0) return NSB_E_BADARG;
+    if (gt_rgb && (!psnr_scratch || !psnr_out)) return NSB_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    if (gt_rgb && cudaMemsetAsync(psnr_scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return NSB_E_CUDA;
+    const int64_t want = cdiv(n, 256), cap = (int64_t)num_sms() * 8;
+    const float inv_range = 1.0f / (depth_far - depth_near + 1e-8f);
+    frame_output_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rgb, acc, depth, n, depth_near, inv_range, use_ndc, rgb8, acc8, depth8,
+                                                                       gt_rgb, mask, gt_rgb ? psnr_scratch : nullptr);
+    NSB_LAUNCH_CHECK("frame_output_kernel");
+    if (gt_rgb) {
+        psnr_finish_kernel<<<1, 1, 0, st>>>(psnr_scratch, psnr_out);
+        NSB_LAUNCH_CHECK("psnr_finish_kernel");
+    }
+    return NSB_OK;
+}
 
 extern "C" int nsb_camera_rays(int H, int W, const float* K_host, const float* c2w_host, int c2w_cols, int convention,
                                int pixel_center, int as_ndc, float near_plane, const float* pixels_xy, int64_t n_pixels,

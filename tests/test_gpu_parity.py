@@ -418,3 +418,32 @@ def test_llff_ndc_shape_train_step_fp32(nsb):
         got = N(torch.cat([q.grad.reshape(-1) for q in net.parameters()]))
         want = O.flatten_params(ref[f"grads_{tag}"])
         assert np.linalg.norm(got - want) <= (2e-2 if tag == "f" else 2e-3) * np.linalg.norm(want)
+
+
+def test_frame_outputs_match_reference_image_path():
+    """uint8 images as save_rgb_png / save_gray_png write them (render_utils.py:28-47), depth normalisation of
+    validation_renderer.py:491-492 and _compute_psnr (:171-196)."""
+    import nerf_sandbox_b200 as nsb
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    H, W = 37, 53
+    rgb = torch.rand((H, W, 3), device=dev, generator=g) * 1.3 - 0.15           # values outside [0,1] exercise the clamps
+    acc = torch.rand((H, W, 1), device=dev, generator=g) * 1.2 - 0.1
+    depth = torch.rand((H, W, 1), device=dev, generator=g) * 6 + 1
+    gt = torch.rand((H, W, 3), device=dev, generator=g)
+    mask = (torch.rand((H, W, 1), device=dev, generator=g) > 0.3).float()
+    out = nsb.frame_outputs({"rgb": rgb, "acc": acc, "depth": depth}, near=2.0, far=6.0, gt_rgb=gt, mask=mask)
+    u8 = lambda t: (t.clamp(0, 1).cpu().numpy() * 255.0 + 0.5).astype(np.uint8)
+    assert np.array_equal(out["rgb"].cpu().numpy(), u8(rgb))
+    assert np.array_equal(out["opacity"].cpu().numpy(), u8(acc.squeeze(-1)))
+    dn = ((depth.squeeze(-1) - 2.0) / (6.0 - 2.0 + 1e-8)).clamp(0, 1)
+    d8 = out["depth"].cpu().numpy().astype(np.int32)
+    assert np.abs(d8 - u8(dn).astype(np.int32)).max() <= 1          # (depth-near)*inv_range vs a division: last-bit ties
+    assert (d8 != u8(dn)).mean() < 0.01
+    pred, gtc = rgb.clamp(0, 1), gt.clamp(0, 1)
+    mse = (((pred - gtc) ** 2) * mask).sum() / (mask.sum() * 3).clamp_min(1e-8)
+    psnr = -10.0 * torch.log10(mse.clamp_min(1e-10))
+    assert abs(float(out["psnr"]) - float(psnr)) <= 1e-4 * abs(float(psnr))
+    assert abs(nsb.compute_psnr(rgb, gt) - float(-10.0 * torch.log10(torch.nn.functional.mse_loss(pred, gtc)))) <= 1e-3
+    nd = nsb.frame_outputs({"rgb": rgb, "acc": acc, "depth": depth / 7.0}, near=0.0, far=1.0, use_ndc=True)
+    assert np.array_equal(nd["depth"].cpu().numpy(), u8((depth / 7.0).squeeze(-1)))
