@@ -141,8 +141,24 @@ extern "C" int nsb_debug_tc_layer(const float* rays_o, const float* rays_d, cons
 // whole train step
 // ---------------------------------------------------------------------------------------------------
 namespace {
+// one side stream (+ fork/join events) per device, created on first use; NSB_SIDE_STREAM=0 keeps everything on the caller's stream
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+SideStream* side_stream() {
+    static SideStream table[64];
+    static int state[64];          // 0 = not tried, 1 = ready, -1 = unavailable
+    static const bool enabled = [] { const char* e = getenv("NSB_SIDE_STREAM"); return !(e && e[0] == '0'); }();
+    int dev = 0;
+    if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (state[dev] == 0) {
+        SideStream& s = table[dev];
+        state[dev] = (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess) ? 1 : -1;
+    }
+    return state[dev] == 1 ? &table[dev] : nullptr;
+}
 struct TrainWs {
-    float *zc, *w_c, *z_all, *raw_c, *raw_f, *d_raw, *comp_c, *comp_f, *g_c, *g_f;
+    float *zc, *w_c, *z_all, *raw_c, *raw_f, *d_raw, *d_raw_c, *comp_c, *comp_f, *g_c, *g_f;
     void *field_c, *field_f;
     size_t field_c_bytes, field_f_bytes, bytes;
 };
@@ -153,7 +169,7 @@ TrainWs carve_train(void* base, int64_t B, int Nc, int Nf, int mode) {
     auto take = [&](size_t bytes) { void* r = p + off; off += align_up(bytes, 256); return r; };
     const int64_t Qc = B * (int64_t)Nc, Qf = B * (int64_t)(Nc + Nf);
     t.zc = (float*)take(Qc * 4); t.w_c = (float*)take(Qc * 4); t.z_all = (float*)take(Qf * 4);
-    t.raw_c = (float*)take(Qc * 16); t.raw_f = (float*)take(Qf * 16); t.d_raw = (float*)take(Qf * 16);
+    t.raw_c = (float*)take(Qc * 16); t.raw_f = (float*)take(Qf * 16); t.d_raw = (float*)take(Qf * 16); t.d_raw_c = (float*)take(Qc * 16);
     t.comp_c = (float*)take(B * 12); t.comp_f = (float*)take(B * 12); t.g_c = (float*)take(B * 12); t.g_f = (float*)take(B * 12);
     t.field_c_bytes = field_ws(Qc, mode, 1); t.field_f_bytes = field_ws(Qf, mode, 1);
     t.field_c = take(t.field_c_bytes); t.field_f = take(t.field_f_bytes);
@@ -194,10 +210,21 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
     NSB_TRY(nsb_composite_raw_fwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.comp_f, nullptr, nullptr, nullptr, B, Nt, f, seed, s_nf, stream));   // :984-996
     // loss (:999-1006) and backward (:717)
     NSB_TRY(nsb_mse_loss(t.comp_c, t.comp_f, target, t.g_c, t.g_f, scalars, B, grad_scale, stream));
+    // The two backward chains are independent (coarse weights only feed the detached resampling), so the coarse one runs on
+    // a side stream forked here and joined below: its CTAs fill the SMs the fine kernels leave idle in their last round
+    // (768 tile pairs on 148 SMs = 5.19 rounds).  Fork/join through events, so the sequence stays graph-capturable.
+    SideStream* side = side_stream();
+    void* sstream = side ? static_cast<void*>(side->stream) : stream;
+    if (side) {
+        if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) return NSB_E_CUDA;
+    }
     NSB_TRY(nsb_composite_raw_bwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.g_f, t.d_raw, B, Nt, f, seed, s_nf, stream));
     NSB_TRY(nsb_field_bwd(t.d_raw, packed_f, grads_f, t.field_f, t.field_f_bytes, Qf, mode, stream));
-    NSB_TRY(nsb_composite_raw_bwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.g_c, t.d_raw, B, Nc, f, seed, s_nc, stream));
-    NSB_TRY(nsb_field_bwd(t.d_raw, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, stream));
+    NSB_TRY(nsb_composite_raw_bwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.g_c, t.d_raw_c, B, Nc, f, seed, s_nc, sstream));
+    NSB_TRY(nsb_field_bwd(t.d_raw_c, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, sstream));
+    if (side) {
+        if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return NSB_E_CUDA;
+    }
     if (comp_c && cudaMemcpyAsync(comp_c, t.comp_c, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
     if (comp_f && cudaMemcpyAsync(comp_f, t.comp_f, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
     return NSB_OK;
