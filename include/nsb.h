@@ -177,12 +177,15 @@ size_t nsb_train_workspace_bytes(int64_t B, int Nc, int Nf, int mode);
  * can be captured once into a CUDA graph and replayed (train/trainer.py:702-729 without per-step host work): Philox streams
  * use step = *step_counter, Adam and the flag epoch use t = *step_counter + 1, and the last kernel increments the counter.
  * params / m / v / packed: HOST arrays of two device pointers (coarse, fine); grads: [2 * NSB_N_PARAMS] (with world > 1 this
- * rank's buffer of the current epoch parity, i.e. capture one graph per parity); draws are always generated in-kernel. */
+ * rank's buffer of the current epoch parity, i.e. capture one graph per parity); draws are always generated in-kernel.
+ * lr_T_max > 0: the learning rate follows CosineAnnealingLR(T_max, eta_min) from base `lr` (make_scheduler, train/trainer.py:81-88),
+ * evaluated on the device from the step count; lr_T_max <= 0: constant lr. */
 int nsb_train_step(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
                    const float* target, float* const* params, float* const* m, float* const* v, void* const* packed,
                    float* grads, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes, int64_t B,
                    int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
-                   uint64_t seed, float lr, float beta1, float beta2, float eps, uint64_t* step_counter,
+                   uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
+                   uint64_t* step_counter,
                    const void* const* peer_grads, void* const* peer_flags, int rank, int world, void* stream);
 
 /* Trainer._train_step + loss.backward(), train/trainer.py:876-1013 and :717.  Batch tensors as

@@ -235,10 +235,10 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
 // ---------------------------------------------------------------------------------------------------
 namespace nsb {
 int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int64_t t,
-              float grad_scale, const uint64_t* t_dev, void* stream);
+              float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream);
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, void* stream);
+                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream);
 __global__ void counter_inc_kernel(uint64_t* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
 }  // namespace nsb
 
@@ -246,7 +246,8 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
                               const float* target, float* const* params, float* const* m, float* const* v, void* const* packed,
                               float* grads, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes, int64_t B,
                               int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
-                              uint64_t seed, float lr, float beta1, float beta2, float eps, uint64_t* step_counter,
+                              uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
+                              uint64_t* step_counter,
                               const void* const* peer_grads, void* const* peer_flags, int rank, int world, void* stream) {
     if (!params || !m || !v || !packed || !grads || !step_counter) return NSB_E_BADARG;
     for (int k = 0; k < 2; ++k)
@@ -262,11 +263,11 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
     // optimiser (+ gradient exchange over peer memory), t = *step_counter + 1
     if (world > 1) {
         NSB_TRY(adam_allreduce_impl(params, m, v, 2, peer_grads, peer_flags, rank, world, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1,
-                                    1.0f / (float)world, step_counter, stream));
+                                    1.0f / (float)world, step_counter, lr_eta_min, lr_T_max, stream));
     } else {
         for (int k = 0; k < 2; ++k)
             NSB_TRY(adam_impl(params[k], grads + (size_t)k * NSB_N_PARAMS, m[k], v[k], NSB_N_PARAMS, lr, beta1, beta2, eps, 1, 1.0f,
-                              step_counter, stream));
+                              step_counter, lr_eta_min, lr_T_max, stream));
     }
     const float* cparams[2] = {params[0], params[1]};
     NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode, stream));

@@ -550,11 +550,14 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 }
 
 // ---- Adam --------------------------------------------------------------------------------------------
-// bias corrections of step t = *t_dev + 1 (CUDA-graph replay: the step count lives in device memory)
-__device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, float lr, float b1, float b2, float& lr_over_bc1, float& inv_sqrt_bc2) {
+// bias corrections of step t = *t_dev + 1 (CUDA-graph replay: the step count lives in device memory); with T_max > 0 the
+// learning rate follows CosineAnnealingLR(T_max, eta_min) after *t_dev scheduler steps (make_scheduler, train/trainer.py:81-88)
+__device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, float lr, float eta_min, int64_t T_max, float b1, float b2,
+                                                      float& lr_over_bc1, float& inv_sqrt_bc2) {
     __shared__ float s_bc[2];
     if (threadIdx.x == 0) {
         const double t = (double)(*t_dev + 1);
+        if (T_max > 0) lr = (float)((double)eta_min + ((double)lr - (double)eta_min) * (1.0 + cos(3.141592653589793 * (double)*t_dev / (double)T_max)) * 0.5);
         s_bc[0] = (float)((double)lr / (1.0 - pow((double)b1, t)));
         s_bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
     }
@@ -563,8 +566,8 @@ __device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, flo
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
-                            float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr) {
-    if (t_dev) adam_bias_corrections(t_dev, lr, b1, b2, lr_over_bc1, inv_sqrt_bc2);
+                            float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr, float eta_min, int64_t T_max) {
+    if (t_dev) adam_bias_corrections(t_dev, lr, eta_min, T_max, b1, b2, lr_over_bc1, inv_sqrt_bc2);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -589,7 +592,7 @@ struct AdamArParams {
     uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
-    const uint64_t* t_dev; float lr;       // graph replay: step count (and epoch) = *t_dev + 1
+    const uint64_t* t_dev; float lr, eta_min; int64_t T_max;       // graph replay: step count (and epoch) = *t_dev + 1
 };
 __device__ __forceinline__ uint64_t ar_global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
     const int world = WORLD ? WORLD : a.world;
     float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2;
     uint32_t epoch = a.epoch;
-    if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
+    if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.eta_min, a.T_max, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
     if (threadIdx.x < world) {
         const int r = threadIdx.x;
         if (blockIdx.x == 0) {      // the gradient kernels of this stream have finished: publish that to rank r
@@ -661,7 +664,7 @@ using namespace nsb;
 namespace nsb {
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, void* stream) {
+                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream) {
     if (!params || !m || !v || !peer_grads || !peer_flags || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 || world < 1 ||
         world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
@@ -677,7 +680,7 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     a.rank = rank; a.world = world; a.n_nets = n_nets; a.epoch = epoch; a.n = n;
     a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr;
+    a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr; a.eta_min = eta_min; a.T_max = T_max;
     // every block spins on the flag exchange first, so the grid must be co-resident: at most four blocks of 256 per SM
     int grid = (int)cdiv((n >> 2) * n_nets, 256);
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
@@ -695,7 +698,7 @@ extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, fl
                                        void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
                                        float beta2, float eps, int64_t t, float grad_scale, void* stream) {
     return adam_allreduce_impl(params, m, v, n_nets, peer_grads, peer_flags, rank, world, epoch, n, lr, beta1, beta2, eps, t, grad_scale,
-                               nullptr, stream);
+                               nullptr, 0.f, 0, stream);
 }
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
@@ -709,11 +712,11 @@ extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, i
 
 namespace nsb {
 int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int64_t t,
-              float grad_scale, const uint64_t* t_dev, void* stream) {
+              float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream) {
     if (!params || !grads || !m || !v || n < 1 || t < 1) return NSB_E_BADARG;
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     adam_kernel<<<elem_grid(n), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
-                                                            (float)(1.0 / sqrt(bc2)), grad_scale, t_dev, lr);
+                                                            (float)(1.0 / sqrt(bc2)), grad_scale, t_dev, lr, eta_min, T_max);
     NSB_LAUNCH_CHECK("adam_kernel");
     return NSB_OK;
 }
@@ -721,5 +724,5 @@ int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, 
 
 extern "C" int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                              float beta2, float eps, int64_t t, float grad_scale, void* stream) {
-    return adam_impl(params, grads, m, v, n, lr, beta1, beta2, eps, t, grad_scale, nullptr, stream);
+    return adam_impl(params, grads, m, v, n, lr, beta1, beta2, eps, t, grad_scale, nullptr, 0.f, 0, stream);
 }

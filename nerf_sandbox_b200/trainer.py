@@ -48,7 +48,8 @@ class _FusedStepFn(torch.autograd.Function):
 class VanillaTrainer:
     def __init__(self, device="cuda", *, rays_per_batch=1024, nc=64, nf=128, near=2.0, far=6.0, white_bkgd=True,
                  raw_noise_std=1.0, infinite_last_bin=True, det_fine=False, lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
-                 mode="fp32", seed=0, sigma_bias=None, process_group=None, allreduce="auto"):
+                 mode="fp32", seed=0, sigma_bias=None, process_group=None, allreduce="auto", lr_scheduler="none",
+                 lr_scheduler_params=None, grad_clip_norm=0.0):
         # hard-coded vanilla settings of the reference: trainer.py:277-291, :411-416; train_nerf.py:275,281
         self.device = torch.device(device)
         self.nc, self.nf, self.samp_near, self.samp_far = int(nc), int(nf), float(near), float(far)
@@ -57,6 +58,15 @@ class VanillaTrainer:
         self.sigma_activation = "relu"
         self.rays_per_batch = int(rays_per_batch)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        # make_scheduler (train/trainer.py:81-90): "none"/"constant" or "cosine" = CosineAnnealingLR(T_max, eta_min)
+        name = (lr_scheduler or "none").lower()
+        if name not in ("none", "constant", "cosine"):
+            raise ValueError(f"unknown lr_scheduler {lr_scheduler!r}")
+        sp = lr_scheduler_params or {}
+        self.lr_T_max = int(sp["T_max"]) if name == "cosine" else 0
+        self.lr_eta_min = float(sp.get("eta_min", 0.0)) if name == "cosine" else 0.0
+        if float(grad_clip_norm or 0.0) > 0:
+            raise NotImplementedError("grad_clip_norm is not on the fused step path (the reference default is 0 = off)")
         self.mode = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}[mode]
         self.seed, self.global_step, self.adam_t = int(seed), 0, 0
         self.pg = process_group
@@ -99,6 +109,14 @@ class VanillaTrainer:
         self._ws = None
         self._graphs = None
         self.nerf_c.packed(); self.nerf_f.packed()
+
+    def current_lr(self, sched_steps=None) -> float:
+        """Learning rate after `sched_steps` scheduler steps (default: now) -- closed form of CosineAnnealingLR."""
+        t = self.adam_t if sched_steps is None else int(sched_steps)
+        if self.lr_T_max <= 0:
+            return self.lr
+        import math
+        return self.lr_eta_min + (self.lr - self.lr_eta_min) * (1.0 + math.cos(math.pi * t / self.lr_T_max)) * 0.5
 
     # ---- helpers ---------------------------------------------------------------------------------------
     def parameters(self):
@@ -150,6 +168,7 @@ class VanillaTrainer:
             self.grads_all = self.peer.buffer(self.epoch)
             self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self._fwd_bwd(batch, draws, grad_scale=1.0)
+        lr = self.current_lr()                                # sched.step() follows opt.step(): t-1 scheduler steps so far
         self.adam_t += 1
         self.global_step += 1
         if self.peer is not None:
@@ -158,14 +177,14 @@ class VanillaTrainer:
             arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
             _lib.check(L.nsb_adam_allreduce_step(arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]), arr([self.m_c, self.m_f]),
                                                  arr([self.v_c, self.v_f]), 2, pr.pointers(self.epoch), pr.flag_array, pr.rank, pr.world,
-                                                 self.epoch, n, self.lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
+                                                 self.epoch, n, lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
                                                  1.0 / pr.world, _lib.stream()), "nsb_adam_allreduce_step")
             NeRF.repack((self.nerf_c, self.nerf_f))
             return self.scalars
         world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
         for nerf, g, m, v in ((self.nerf_c, self.grads_c, self.m_c, self.v_c), (self.nerf_f, self.grads_f, self.m_f, self.v_f)):
             flat = nerf.flat_params()
-            _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, self.lr,
+            _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, lr,
                                        self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.stream()),
                        "nsb_adam_step")
         NeRF.repack((self.nerf_c, self.nerf_f))
@@ -190,7 +209,8 @@ class VanillaTrainer:
             arr([self.m_c, self.m_f]), arr([self.v_c, self.v_f]), arr([self.nerf_c.packed(), self.nerf_f.packed()]), _lib.ptr(grads),
             _lib.ptr(self.scalars), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
             self.nf, self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode, self.seed,
-            self.lr, self.betas[0], self.betas[1], self.eps, _lib.ptr(self._step_dev), pg, pf, rank, world, _lib.stream()),
+            self.lr, self.lr_eta_min, self.lr_T_max, self.betas[0], self.betas[1], self.eps, _lib.ptr(self._step_dev), pg, pf, rank,
+            world, _lib.stream()),
             "nsb_train_step")
 
     def step_graph(self, batch):
