@@ -1,21 +1,25 @@
-// K1 (bf16 tensor-core mode) -- positional encoder + NeRF MLP as ONE persistent tcgen05 kernel.
+// K1 (bf16 tensor-core mode) -- positional encoder + NeRF MLP as ONE persistent tcgen05 kernel per pass.
 //
-// One CTA per SM walks pairs of 128-point tiles.  Per pair, the whole chain
+// Clusters of two CTAs (one per SM, cta_group::2) walk 128-point tiles, two tiles per CTA at a time.  Per tile, the chain
 //     gamma(x) -> mlp.0..7 (skip concat at layer 4) -> feature -> color_fc -> heads
 // runs without touching HBM for activations:
-//   * A operand (activations, bf16) lives in shared memory in the tcgen05 canonical K-major layout
-//     (8x16B core matrices, no swizzle); the epilogue of layer l writes the A operand of layer l+1 in place;
-//   * B operand (weights, bf16) is pre-packed by nsb_pack_weights in exactly that shared-memory image, so a
-//     K=32 slab is one contiguous block streamed by the TMA engine (cp.async.bulk + mbarrier tx-count)
-//     through a 4-stage ring, shared by the two tiles of the pair;
-//   * accumulators (fp32) live in TMEM: 2 tiles x 256 columns = all 512 columns;
-//   * roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 4-7 / 8-11 = epilogue
-//     groups of tile A / tile B (thread == accumulator row: tcgen05.ld 32x32b, bias + ReLU, bf16 pack,
-//     conflict-free st.shared, fence.proxy.async, mbarrier arrive).  While one tile's epilogue runs, the
-//     tensor core works on the other tile.
-//   * sigma_out (256->1) and color_out (128->3) are CUDA-core dot products inside the epilogues of layer 7
-//     and color_fc (fp32), so raw [r,g,b,sigma] leaves the chip as one float4 per point.
-// Training adds a bf16 stash of every layer input (bulk-stored tile images) for the backward kernels.
+//   * A operand (activations, bf16) lives in shared memory in the tcgen05 canonical K-major layout (8x16 B core matrices,
+//     no swizzle); the epilogue of layer l writes the A operand of layer l+1 in place;
+//   * B operand (weights, bf16) is pre-packed by nsb_pack_weights in exactly that shared-memory image, ordered so that the
+//     half of a K=32 slab one CTA of the pair needs (N/2 weight rows) is one contiguous 8 KB block; the TMA engine streams
+//     it through an 8-stage ring with tensor-map loads whose complete_tx lands on the LEADER CTA's mbarrier;
+//   * one tcgen05.mma spans both SMs: M = 256 = the tiles of the two CTAs, each CTA supplies half of B; accumulators (fp32)
+//     live in each CTA's own TMEM: 2 tiles x 256 columns = all 512 columns;
+//   * roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only, one elected thread; commits are multicast
+//     to both CTAs), warps 2-3 = per-tile helpers in training (proxy fence, hand-off, stash copy), warps 4-7 / 8-11 =
+//     epilogue groups of tile A / tile B (thread == accumulator row: tcgen05.ld 32x32b, bias + ReLU, bf16 pack,
+//     conflict-free st.shared).  While one tile's epilogue drains TMEM the tensor cores work on the other tile; a layer's
+//     slabs are fetched once and used by tile A, then tile B;
+//   * sigma_out (256->1) and color_out (128->3) are CUDA-core dot products inside the epilogues of layer 7 and color_fc
+//     (fp32), so raw [r,g,b,sigma] leaves the chip as one float4 per point.
+// Training adds a bf16 stash of every layer input (tile images + 1-bit ReLU masks) for the backward kernels: the dgrad chain
+// (same CTA-pair machinery on transposed weight images) and wgrad (tile images as MN-major operands, accumulators resident in
+// TMEM across all tiles of a CTA).  DESIGN.md section 4 has the measurements behind each of these choices.
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -47,10 +51,6 @@ constexpr int kStageBytes2 = kStageBytes / 2;
 static_assert(8 * (3 * kStages2 + 6) + 4 <= 256, "barrier block overflow");
 constexpr int kNumMmaLayers = 10;               // mlp.0..7, feature, color_fc
 constexpr uint32_t kTmemCols = 512;
-#ifndef NSB_TC_PINGPONG
-#define NSB_TC_PINGPONG 1
-#endif
-constexpr bool kPingPong = NSB_TC_PINGPONG != 0;    // 1: tiles alternate per layer (weights streamed per tile); 0: interleaved per slab
 
 // bf16 image offsets (bytes) of the 10 MMA layers: [K/8][N][8] bf16 each
 __constant__ uint32_t c_layer_ofs[kNumMmaLayers] = {0,      32768,  163840, 294912, 425984,
@@ -74,7 +74,6 @@ constexpr uint32_t kPackedTcBytes = kTImgOfs + 65536 + 8 * 131072;
 __host__ __device__ inline int layer_nslabs(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 9 ? 9 : 8)); }
 __host__ __device__ inline int layer_N(int l) { return l == 9 ? 128 : 256; }
 __host__ __device__ inline int layer_bias_ofs(int l) { return l * 256; }
-constexpr int kSlabsPerPair = 2 + 3 * 8 + 10 + 3 * 8 + 8 + 9;   // 77
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -560,7 +559,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
             for (int64_t it = 0, pair = blockIdx.x; it < n_iter; ++it, pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const uint32_t bytes = 32u * (uint32_t)layer_N(l) * 2u;
-                    const uint8_t* src = p.packed + c_layer_ofs[l];
                     const int ns = layer_nslabs(l);
                     // a layer whose slabs fit the ring is fetched once and used by tile A, then by tile B; the two longer
                     // layers (the skip layer and color_fc) are streamed once per tile
@@ -887,9 +885,6 @@ __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterp
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 // dgrad epilogue column loop.  KIND 0: plain (feature is linear)   1: + d_sigma * w_sigma, then ReLU mask   2: ReLU mask
 // The mask comes as 8 bit words per row (one per 32 columns) written by the forward epilogue -- loaded once per layer,
 // so nothing inside the column loop waits on global memory.
@@ -1140,7 +1135,6 @@ struct WgradJob {
     int64_t b_dst;         // float offset of the bias grad, or -1
     int64_t head_w_dst, head_b_dst;   // HEAD_SIGMA: g w_sigma[256], g b_sigma;  HEAD_RGB: g Wo[3][128], g bo[3]
     int cta_begin, cta_count;
-    uint32_t bytes_per_tile;
 };
 constexpr int kMaxJobs = 16;
 struct WgradParams {
@@ -1581,9 +1575,6 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
         j.halves = halves; j.xcols = xcols;
         j.w_dst = d.w_off + col0; j.ldw = d.K; j.ncols_valid = valid; j.b_dst = bias ? d.b_off : -1;
         if (head == tc::HEAD_SIGMA) { const LayerDesc ds = layer_desc(9); j.head_w_dst = ds.w_off; j.head_b_dst = ds.b_off; }
-        j.bytes_per_tile = 0;
-        for (int i = 0; i < j.n_pieces; ++i) j.bytes_per_tile += j.pieces[i].bytes;
-        if (head == tc::HEAD_SIGMA) j.bytes_per_tile += j.bytes_per_tile / 6;     // its idle warps also reduce the sigma_out grads
     };
     add(0, tc::kStashGx, 64, 0, 0, 63, true, 0);
     for (int l = 1; l <= 7; ++l) {
@@ -1599,7 +1590,6 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
         j.pieces[0] = tc::WgPiece{(uint32_t)tc::kStashC, 32768, 1, -1, tc::HEAD_RGB}; j.release_after[0] = -1; j.n_pieces = 1;
         const LayerDesc dc = layer_desc(11);
         j.head_w_dst = dc.w_off; j.head_b_dst = dc.b_off; j.b_dst = -1;
-        j.bytes_per_tile = (32768 + 2048) * 3 / 2;      // CUDA-core bound: a little more than its byte share
     }
     wp.num_jobs = nj;
     wp.dbg = getenv("NSB_WG_DBG") != nullptr;
