@@ -843,12 +843,18 @@ __device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params
         const LayerDesc d = layer_desc(pl);
         const int N = d.N, Kp = d.Kpad;
         __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + c_layer_ofs[m]);
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * Kp; idx += gridDim.x * blockDim.x) {
-            // image order: [K slab k/32][half of N (one per CTA of a pair)][K chunk (k/8)%4][n % (N/2)][k%8] -- a CTA's half
-            // of a K=32 slab is one contiguous block (8 KB at N=256)
-            const int k = idx / N, n = idx % N, hn = N >> 1;
-            const float w = k < d.K ? params[d.w_off + (int64_t)n * d.K + k] : 0.f;
-            img[((((size_t)(k >> 5) * 2 + n / hn) * 4 + ((k >> 3) & 3)) * hn + n % hn) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+        // image order: [K slab k/32][half of N (one per CTA of a pair)][K chunk (k/8)%4][n % (N/2)][k%8] -- a CTA's half
+        // of a K=32 slab is one contiguous block (8 KB at N=256).  One 16-byte chunk (8 consecutive k of one row) per
+        // thread, consecutive threads on consecutive rows: sector-sized reads, fully coalesced writes.
+        const int hn = N >> 1;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * (Kp >> 3); idx += gridDim.x * blockDim.x) {
+            const int k8 = idx / N, n = idx % N;
+            const float* row = params + d.w_off + (int64_t)n * d.K + 8 * k8;
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                w[j] = pack_bf16(8 * k8 + 2 * j < d.K ? row[2 * j] : 0.f, 8 * k8 + 2 * j + 1 < d.K ? row[2 * j + 1] : 0.f);
+            reinterpret_cast<uint4*>(img)[(((size_t)(k8 >> 2) * 2 + n / hn) * 4 + (k8 & 3)) * hn + n % hn] = make_uint4(w[0], w[1], w[2], w[3]);
         }
         float* tail = reinterpret_cast<float*>(out + kBiasOfs);
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
@@ -1391,10 +1397,15 @@ __device__ __forceinline__ void pack_tc_transposed(const float* __restrict__ par
         const LayerDesc d = layer_desc(pl);
         const int Nout = d.N;                                  // contraction length (128 or 256)
         __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + dgrad_layer_ofs(m));
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Nout * 256; idx += gridDim.x * blockDim.x) {
-            const int n = idx / 256, j = idx % 256;            // W[n, j], j < 256 <= K; same half-slab order with (k, n) := (n, j)
-            img[((((size_t)(n >> 5) * 2 + (j >> 7)) * 4 + ((n >> 3) & 3)) * 128 + (j & 127)) * 8 + (n & 7)] =
-                __float2bfloat16_rn(params[d.w_off + (int64_t)n * d.K + j]);
+        // W[n, j], j < 256 <= K; same half-slab order with (k, n) := (n, j); one chunk = 8 consecutive out-features n of one
+        // in-feature j per thread, consecutive threads on consecutive j (coalesced reads of 8 rows, coalesced writes)
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (Nout >> 3) * 256; idx += gridDim.x * blockDim.x) {
+            const int n8 = idx >> 8, j = idx & 255;
+            const float* col = params + d.w_off + (int64_t)(8 * n8) * d.K + j;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = pack_bf16(col[(int64_t)(2 * q) * d.K], col[(int64_t)(2 * q + 1) * d.K]);
+            reinterpret_cast<uint4*>(img)[(((size_t)(n8 >> 2) * 2 + (j >> 7)) * 4 + (n8 & 3)) * 128 + (j & 127)] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
