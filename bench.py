@@ -299,6 +299,10 @@ def main():
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                 "kernel": f"field fwd+bwd ({args.mode}) on the fine pass, {Q} points, {ms_field:.3f} ms/launch-set",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"}
+    if traffic:      # the same launch set against the HBM roof: the backward half of it is bandwidth-bound (stash round trip)
+        hbm_peak = float(peaks.get("hbm_gbs", 6452.5)) if peaks else 6452.5
+        roofline["hbm"] = {"achieved": traffic / (ms_field * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": traffic / (ms_field * 1e-3) / 1e9 / hbm_peak}
 
     # ---- secondary metric: 800x800 eval frame (configs[2]) -----------------------------------------------
     extra = {}
