@@ -254,3 +254,35 @@ def test_full_frame_properties_bf16(setup):
     assert float(a["rgb"].min()) >= 0 and float(a["rgb"].max()) <= 1 and float(a["acc"].min()) >= 0 and float(a["acc"].max()) <= 1
     assert float(a["depth"].min()) >= 0 and float(a["depth"].max()) <= 6.0 + 1e-3
     assert float(a["acc"].std()) > 0                            # a non-trivial image (sigma bias makes the volume visible)
+
+
+def test_tc_random_sizes_and_poisoned_workspace(setup):
+    """CTA-pair kernels on awkward sizes (1 point ... several rounds of clusters, odd tile and pair counts): the bf16 field
+    matches the fp32 mode, and neither the forward nor the training step depends on what the workspace held before
+    (every byte the kernels read has been written by them: the workspace is poisoned with NaN bit patterns first)."""
+    nsb, _lib, net, p, rays, z = setup
+    L = _lib.lib()
+    net32 = nsb.NeRF(63, 27, mode="fp32").to(DEV)
+    net32.load_state_dict(net.state_dict())
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    rng = np.random.default_rng(77)
+    for Q in (1, 127, 129, 257, 128 * 3, 128 * 149 + 5, 128 * 297, 40000):
+        ep = pe.to(DEV)(T(rng.uniform(-4, 4, (Q, 3)).astype(np.float32)))
+        ed = de.to(DEV)(T(O._normalize(rng.standard_normal((Q, 3)).astype(np.float32))))
+        with torch.no_grad():
+            a, b = net(ep, ed), net32(ep, ed)
+        assert torch.isfinite(a).all()
+        assert rel_l2(N(a), N(b)) < 3e-2, Q
+    # training step: poisoned vs zeroed workspace give the same loss and the same gradients (up to atomic-add order)
+    batch = {k: T(v) for k, v in O.synthetic_rays(np.random.default_rng(3), 300).items()}
+    res = []
+    for fill in (0xFF, 0x00):
+        tr = nsb.VanillaTrainer(DEV, mode="bf16", seed=5, sigma_bias=0.4)
+        ws, _ = tr._workspace(300)
+        ws.fill_(fill)
+        sc, _, _ = tr._fwd_bwd(batch)
+        torch.cuda.synchronize()
+        assert torch.isfinite(sc).all() and torch.isfinite(tr.grads_all).all()
+        res.append((sc.clone(), tr.grads_all.clone()))
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-6, atol=0)        # (the loss reduction itself uses float atomics)
+    assert rel_l2(N(res[0][1]), N(res[1][1])) < 1e-5
