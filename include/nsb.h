@@ -161,10 +161,12 @@ int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t
  * peer_grads[r] + k * n.  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device addresses valid in this process:
  * symmetric / peer-mapped allocations): rank r's gradient buffer [n_nets * n] and flag block (uint32[world], zeroed once).
  * `epoch` starts at 1 and increases by one per step on every rank; the caller alternates between two gradient buffers by
- * epoch parity (that is what makes one flag exchange per step sufficient).  n % 4 == 0. */
+ * epoch parity (that is what makes one flag exchange per step sufficient).  n % 4 == 0.
+ * mc_grads (optional): multicast (NVLS) address of the same gradient buffers; when given, the sum is one
+ * `multimem.ld_reduce` per 16 bytes -- the NVSwitch reduces, every rank receives n_nets * n floats instead of world times that. */
 int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
-                            void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                            float beta2, float eps, int64_t t, float grad_scale, void* stream);
+                            const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr,
+                            float beta1, float beta2, float eps, int64_t t, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-path entry points (one host call per step / per ray tile)
@@ -186,7 +188,7 @@ int nsb_train_step(const float* rays_o, const float* rays_d, const float* ray_no
                    int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
                    uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
                    uint64_t* step_counter,
-                   const void* const* peer_grads, void* const* peer_flags, int rank, int world, void* stream);
+                   const void* const* peer_grads, const void* mc_grads, void* const* peer_flags, int rank, int world, void* stream);
 
 /* Trainer._train_step + loss.backward(), train/trainer.py:876-1013 and :717.  Batch tensors as
  * trainer.py:880-884.  grads_c/grads_f[NSB_N_PARAMS] are overwritten with dloss/dparams * grad_scale.

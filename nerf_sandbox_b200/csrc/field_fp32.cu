@@ -589,12 +589,20 @@ constexpr int kMaxNets = 4;
 struct AdamArParams {
     float* p[kMaxNets]; float* m[kMaxNets]; float* v[kMaxNets];   // n floats each; net k's gradients are grads[r] + k * n
     const float* grads[kMaxPeers];          // every rank's gradient buffer (peer-mapped addresses), n_nets * n floats
+    const float* mc_grads;                  // multicast address of the same buffers (NVLS), or null
     uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
     const uint64_t* t_dev; float lr, eta_min; int64_t T_max;       // graph replay: step count (and epoch) = *t_dev + 1
 };
 __device__ __forceinline__ uint64_t ar_global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// NVLS: one load returns the sum over every rank's copy, reduced inside the NVSwitch
+__device__ __forceinline__ float4 ld_reduce_mc(const float4* p) {
+    float4 x;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                 : "l"(p) : "memory");
+    return x;
+}
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
     float4 x;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(p));
@@ -633,7 +641,9 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
         // all peers' loads in flight before the first add; summed in rank order: identical on every rank
         float4 x[WORLD ? WORLD : 1];
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (WORLD) {
+        if (a.mc_grads) {
+            g = ld_reduce_mc(reinterpret_cast<const float4*>(a.mc_grads) + i);
+        } else if (WORLD) {
 #pragma unroll
             for (int r = 0; r < (WORLD ? WORLD : 1); ++r) x[r] = ld_peer(reinterpret_cast<const float4*>(a.grads[r]) + i);
 #pragma unroll
@@ -664,7 +674,8 @@ using namespace nsb;
 namespace nsb {
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream) {
+                        float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max,
+                        const void* mc_grads, void* stream) {
     if (!params || !m || !v || !peer_grads || !peer_flags || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 || world < 1 ||
         world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
@@ -681,6 +692,7 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
     a.rank = rank; a.world = world; a.n_nets = n_nets; a.epoch = epoch; a.n = n;
     a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr; a.eta_min = eta_min; a.T_max = T_max;
+    a.mc_grads = static_cast<const float*>(mc_grads);
     // every block spins on the flag exchange first, so the grid must be co-resident: at most four blocks of 256 per SM
     int grid = (int)cdiv((n >> 2) * n_nets, 256);
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
@@ -695,10 +707,10 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
 }  // namespace nsb
 
 extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
-                                       void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
-                                       float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+                                       const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n,
+                                       float lr, float beta1, float beta2, float eps, int64_t t, float grad_scale, void* stream) {
     return adam_allreduce_impl(params, m, v, n_nets, peer_grads, peer_flags, rank, world, epoch, n, lr, beta1, beta2, eps, t, grad_scale,
-                               nullptr, 0.f, 0, stream);
+                               nullptr, 0.f, 0, mc_grads, stream);
 }
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {

@@ -51,6 +51,14 @@ class PeerGrads:
         self._h_buf = symm_mem.rendezvous(self.buf, group.group_name)
         self._h_flags = symm_mem.rendezvous(self.flags, group.group_name)
         self.buf_ptrs = [int(p) for p in self._h_buf.buffer_ptrs]
+        # NVLS: multicast address of the gradient buffers (0 when the fabric has no multicast support).  NSB_NVLS=0 disables
+        # it, =1 requires it; by default it is used from 4 ranks up, where it beats reading world-1 peer buffers
+        import os
+        want = os.environ.get("NSB_NVLS", "auto")
+        mc = int(getattr(self._h_buf, "multicast_ptr", 0) or 0) if want != "0" else 0
+        if want == "1" and not mc:
+            raise RuntimeError("NSB_NVLS=1 but the symmetric-memory handle reports no multicast support")
+        self.mc_ptr = mc if (want == "1" or self.world >= 4) else 0
         self.flag_ptrs = [int(p) for p in self._h_flags.buffer_ptrs]
         self._C = C
         self.flag_array = (C.c_void_p * self.world)(*self.flag_ptrs)
@@ -60,6 +68,10 @@ class PeerGrads:
     def buffer(self, epoch: int) -> torch.Tensor:
         h = epoch & 1
         return self.buf[h * self.n:(h + 1) * self.n]
+
+    def multicast(self, epoch: int):
+        """Multicast address of the gradient buffer of `epoch` (None without NVLS)."""
+        return (self.mc_ptr + (epoch & 1) * self.n * 4) if self.mc_ptr else None
 
     def pointers(self, epoch: int, float_offset: int = 0):
         byte_ofs = ((epoch & 1) * self.n + float_offset) * 4

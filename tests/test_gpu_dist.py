@@ -52,8 +52,9 @@ for epoch in range(1, 4):
     gr = torch.Generator(device=dev); gr.manual_seed(1000 * epoch + rank)
     grads = torch.randn(2 * n, device=dev, generator=gr)
     pg.buffer(epoch).copy_(grads)
+    mc = pg.multicast(epoch) if os.environ.get("NSB_NVLS") == "1" else None      # NVLS variant: multimem.ld_reduce
     _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
-                                         pg.pointers(epoch), pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
+                                         pg.pointers(epoch), mc, pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
                                          1.0 / world, _lib.stream()), "fused")
     red = grads.clone(); dist.all_reduce(red)
     for k in range(2):
@@ -82,6 +83,7 @@ def test_two_gpu_training_and_tiled_eval(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, NSB_ROOT=ROOT)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    nproc = os.environ.get("NSB_TEST_NPROC", "2")            # e.g. 8 on a full node (NVLS path: NSB_NVLS=1 or >= 4 ranks)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", nproc, "--master-addr",
                         "127.0.0.1", "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
