@@ -39,6 +39,7 @@ int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash,
 int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
 // field_tc.cu
 size_t tc_workspace_bytes(int64_t Q, int stash);
+size_t tc_stash_tile_bytes();
 thread_local const uint64_t* g_step_dev = nullptr;
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st);
 int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
@@ -200,31 +201,67 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
     const uint64_t s_jit = step * 8 + 0, s_u = step * 8 + 1, s_nc = step * 8 + 2, s_nf = step * 8 + 3;
     if (cudaMemsetAsync(grads_c, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
     if (cudaMemsetAsync(grads_f, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
-    // coarse
-    NSB_TRY(nsb_stratified_z(t.zc, U, B, Nc, near_, far_, 1, seed, s_jit, stream));                                    // trainer.py:901-908
-    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.zc, ray_norm, viewdirs, packed_c, t.raw_c, t.field_c, t.field_c_bytes, B, Nc, mode, 1, stream));
-    NSB_TRY(nsb_composite_raw_fwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.comp_c, t.w_c, nullptr, nullptr, B, Nc, f, seed, s_nc, stream));   // :911-923
-    // resample + merge, fine
-    NSB_TRY(nsb_resample_merge(t.zc, t.w_c, u_fine, t.z_all, nullptr, B, Nc, Nf, det_fine, seed, s_u, stream));       // :926-934, :981
-    NSB_TRY(nsb_field_fwd_rays(rays_o, rays_d, t.z_all, ray_norm, viewdirs, packed_f, t.raw_f, t.field_f, t.field_f_bytes, B, Nt, mode, 1, stream));
-    NSB_TRY(nsb_composite_raw_fwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.comp_f, nullptr, nullptr, nullptr, B, Nt, f, seed, s_nf, stream));   // :984-996
+    // Forward chain (coarse pass, resampling, fine pass) of rays [b0, b0 + nb) on `strm`; Philox streams shifted by `sid`.
+    // A half batch writes its own rows / tiles of every buffer, so the backward can treat the batch as a whole.
+    auto forward = [&](int64_t b0, int64_t nb, uint64_t sid, void* strm) -> int {
+        const float* rn = ray_norm ? ray_norm + b0 : nullptr;
+        const float* vd = viewdirs ? viewdirs + 3 * b0 : nullptr;
+        auto opt = [](const float* p, int64_t ofs) { return p ? p + ofs : nullptr; };
+        float* zc = t.zc + b0 * Nc; float* z_all = t.z_all + b0 * Nt; float* w_c = t.w_c + b0 * Nc;
+        float* raw_c = t.raw_c + 4 * b0 * Nc; float* raw_f = t.raw_f + 4 * b0 * Nt;
+        // field workspaces: tile k of the stash lives k tiles in, and a half batch starts on a tile boundary (checked below)
+        const size_t tile = mode == NSB_MODE_BF16 ? tc_stash_tile_bytes() : 0;
+        const size_t off_c = (size_t)(b0 * Nc / 128) * tile, off_f = (size_t)(b0 * Nt / 128) * tile;
+        NSB_TRY(nsb_stratified_z(zc, opt(U, b0 * Nc), nb, Nc, near_, far_, 1, seed, s_jit + sid, strm));                     // trainer.py:901-908
+        NSB_TRY(nsb_field_fwd_rays(rays_o + 3 * b0, rays_d + 3 * b0, zc, rn, vd, packed_c, raw_c, static_cast<char*>(t.field_c) + off_c,
+                                   t.field_c_bytes - off_c, nb, Nc, mode, 1, strm));
+        NSB_TRY(nsb_composite_raw_fwd(raw_c, opt(noise_c, b0 * Nc), noise_std, zc, rn, t.comp_c + 3 * b0, w_c, nullptr, nullptr, nb, Nc, f,
+                                      seed, s_nc + sid, strm));                                                              // :911-923
+        NSB_TRY(nsb_resample_merge(zc, w_c, opt(u_fine, b0 * Nf), z_all, nullptr, nb, Nc, Nf, det_fine, seed, s_u + sid, strm));   // :926-934, :981
+        NSB_TRY(nsb_field_fwd_rays(rays_o + 3 * b0, rays_d + 3 * b0, z_all, rn, vd, packed_f, raw_f, static_cast<char*>(t.field_f) + off_f,
+                                   t.field_f_bytes - off_f, nb, Nt, mode, 1, strm));
+        return nsb_composite_raw_fwd(raw_f, opt(noise_f, b0 * Nt), noise_std, z_all, rn, t.comp_f + 3 * b0, nullptr, nullptr, nullptr, nb, Nt,
+                                     f, seed, s_nf + sid, strm);                                                             // :984-996
+    };
+    // d raw of rays [b0, b0 + nb) from the composite gradients (regenerates the same noise as `forward`)
+    auto composite_bwd = [&](int64_t b0, int64_t nb, uint64_t sid, bool fine, void* strm) -> int {
+        const float* rn = ray_norm ? ray_norm + b0 : nullptr;
+        if (fine)
+            return nsb_composite_raw_bwd(t.raw_f + 4 * b0 * Nt, noise_f ? noise_f + b0 * Nt : nullptr, noise_std, t.z_all + b0 * Nt, rn,
+                                         t.g_f + 3 * b0, t.d_raw + 4 * b0 * Nt, nb, Nt, f, seed, s_nf + sid, strm);
+        return nsb_composite_raw_bwd(t.raw_c + 4 * b0 * Nc, noise_c ? noise_c + b0 * Nc : nullptr, noise_std, t.zc + b0 * Nc, rn,
+                                     t.g_c + 3 * b0, t.d_raw_c + 4 * b0 * Nc, nb, Nc, f, seed, s_nc + sid, strm);
+    };
+    // Two half batches on two streams (tensor-core mode): each persistent field kernel ends with a partly filled round of
+    // tiles (e.g. 768 tile pairs on 148 SMs = 5.19 rounds); with the other half's kernels in flight those SMs are not idle.
+    SideStream* side = side_stream();
+    const int64_t hb = B / 2;
+    const bool split = side && mode == NSB_MODE_BF16 && B % 2 == 0 && hb >= 128 && (hb * Nc) % 128 == 0 && (hb * Nt) % 128 == 0;
+    const uint64_t sid1 = 1ull << 40;                     // Philox stream shift of the second half
+    void* sstream = side ? static_cast<void*>(side->stream) : stream;
+    auto fork = [&]() { return cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess; };
+    auto join = [&]() { return cudaEventRecord(side->join, side->stream) == cudaSuccess && cudaStreamWaitEvent(st, side->join, 0) == cudaSuccess; };
+    if (split) {
+        if (!fork()) return NSB_E_CUDA;
+        NSB_TRY(forward(0, hb, 0, stream));
+        NSB_TRY(forward(hb, hb, sid1, sstream));
+        if (!join()) return NSB_E_CUDA;
+    } else {
+        NSB_TRY(forward(0, B, 0, stream));
+    }
     // loss (:999-1006) and backward (:717)
     NSB_TRY(nsb_mse_loss(t.comp_c, t.comp_f, target, t.g_c, t.g_f, scalars, B, grad_scale, stream));
     // The two backward chains are independent (coarse weights only feed the detached resampling), so the coarse one runs on
-    // a side stream forked here and joined below: its CTAs fill the SMs the fine kernels leave idle in their last round
-    // (768 tile pairs on 148 SMs = 5.19 rounds).  Fork/join through events, so the sequence stays graph-capturable.
-    SideStream* side = side_stream();
-    void* sstream = side ? static_cast<void*>(side->stream) : stream;
-    if (side) {
-        if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) return NSB_E_CUDA;
-    }
-    NSB_TRY(nsb_composite_raw_bwd(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, t.g_f, t.d_raw, B, Nt, f, seed, s_nf, stream));
+    // the side stream forked here and joined below: its CTAs fill the SMs the fine kernels leave idle in their last round.
+    // Fork/join through events, so the sequence stays graph-capturable.
+    if (side && !fork()) return NSB_E_CUDA;
+    if (split) { NSB_TRY(composite_bwd(0, hb, 0, true, stream)); NSB_TRY(composite_bwd(hb, hb, sid1, true, stream)); }
+    else NSB_TRY(composite_bwd(0, B, 0, true, stream));
     NSB_TRY(nsb_field_bwd(t.d_raw, packed_f, grads_f, t.field_f, t.field_f_bytes, Qf, mode, stream));
-    NSB_TRY(nsb_composite_raw_bwd(t.raw_c, noise_c, noise_std, t.zc, ray_norm, t.g_c, t.d_raw_c, B, Nc, f, seed, s_nc, sstream));
+    if (split) { NSB_TRY(composite_bwd(0, hb, 0, false, sstream)); NSB_TRY(composite_bwd(hb, hb, sid1, false, sstream)); }
+    else NSB_TRY(composite_bwd(0, B, 0, false, sstream));
     NSB_TRY(nsb_field_bwd(t.d_raw_c, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, sstream));
-    if (side) {
-        if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return NSB_E_CUDA;
-    }
+    if (side && !join()) return NSB_E_CUDA;
     if (comp_c && cudaMemcpyAsync(comp_c, t.comp_c, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
     if (comp_f && cudaMemcpyAsync(comp_f, t.comp_f, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
     return NSB_OK;

@@ -1426,6 +1426,7 @@ size_t tc_workspace_bytes(int64_t Q, int stash) {
     const int64_t tiles = cdiv(Q, tc::TILE_M);
     return 256 + (stash ? (size_t)tiles * (tc::kStashTile + tc::kDstashTile) : 0);
 }
+size_t tc_stash_tile_bytes() { return tc::kStashTile; }      // a field workspace offset by k of these starts at tile k
 static inline uint8_t* ws_stash(void* ws) { return reinterpret_cast<uint8_t*>(ws) + 256; }
 static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (size_t)cdiv(Q, tc::TILE_M) * tc::kStashTile; }
 
