@@ -303,10 +303,10 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
     if (world > 1) {
         NSB_TRY(adam_allreduce_impl(params, m, v, 2, peer_grads, peer_flags, rank, world, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1,
                                     1.0f / (float)world, step_counter, lr_eta_min, lr_T_max, mc_grads, stream));
-    } else {
-        for (int k = 0; k < 2; ++k)
-            NSB_TRY(adam_impl(params[k], grads + (size_t)k * NSB_N_PARAMS, m[k], v[k], NSB_N_PARAMS, lr, beta1, beta2, eps, 1, 1.0f,
-                              step_counter, lr_eta_min, lr_T_max, stream));
+    } else {        // one rank: the same kernel without the exchange -- both nets in one launch
+        const void* own[1] = {grads};
+        NSB_TRY(adam_allreduce_impl(params, m, v, 2, own, nullptr, 0, 1, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1, 1.0f, step_counter,
+                                    lr_eta_min, lr_T_max, nullptr, stream));
     }
     const float* cparams[2] = {params[0], params[1]};
     NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode, stream));

@@ -568,6 +568,25 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
                             float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr, float eta_min, int64_t T_max) {
     if (t_dev) adam_bias_corrections(t_dev, lr, eta_min, T_max, b1, b2, lr_over_bc1, inv_sqrt_bc2);
+    // 16-byte accesses when the buffers allow it (the flat parameter buffers do: 595,844 = 4 x 148,961)
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+            const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+            float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+            const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x; float* pp = &p4.x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float gi = gg[c] * grad_scale;
+                mm[c] = b1 * mm[c] + (1.0f - b1) * gi;
+                vv[c] = b2 * vv[c] + (1.0f - b2) * gi * gi;
+                pp[c] -= lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * inv_sqrt_bc2 + eps));
+            }
+            reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; reinterpret_cast<float4*>(p)[i] = p4;
+        }
+        return;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -614,7 +633,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
     float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2;
     uint32_t epoch = a.epoch;
     if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.eta_min, a.T_max, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
-    if (threadIdx.x < world) {
+    if (world > 1 && threadIdx.x < world) {     // (a single rank has nobody to wait for)
         const int r = threadIdx.x;
         if (blockIdx.x == 0) {      // the gradient kernels of this stream have finished: publish that to rank r
             __threadfence_system();
@@ -676,8 +695,8 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
                         float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max,
                         const void* mc_grads, void* stream) {
-    if (!params || !m || !v || !peer_grads || !peer_flags || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 || world < 1 ||
-        world > kMaxPeers || rank < 0 || rank >= world)
+    if (!params || !m || !v || !peer_grads || (!peer_flags && world > 1) || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 ||
+        world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
     AdamArParams a{};
     for (int k = 0; k < n_nets; ++k) {
@@ -685,8 +704,8 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
         a.p[k] = params[k]; a.m[k] = m[k]; a.v[k] = v[k];
     }
     for (int r = 0; r < world; ++r) {
-        if (!peer_grads[r] || !peer_flags[r]) return NSB_E_BADARG;
-        a.grads[r] = static_cast<const float*>(peer_grads[r]); a.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+        if (!peer_grads[r] || (world > 1 && !peer_flags[r])) return NSB_E_BADARG;
+        a.grads[r] = static_cast<const float*>(peer_grads[r]); a.flags[r] = world > 1 ? static_cast<uint32_t*>(peer_flags[r]) : nullptr;
     }
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     a.rank = rank; a.world = world; a.n_nets = n_nets; a.epoch = epoch; a.n = n;
@@ -697,7 +716,8 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
     int grid = (int)cdiv((n >> 2) * n_nets, 256);
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
     cudaStream_t st = as_stream(stream);
-    if (world == 2) adam_allreduce_kernel<2><<<grid, 256, 0, st>>>(a);
+    if (world == 1) adam_allreduce_kernel<1><<<grid, 256, 0, st>>>(a);
+    else if (world == 2) adam_allreduce_kernel<2><<<grid, 256, 0, st>>>(a);
     else if (world == 4) adam_allreduce_kernel<4><<<grid, 256, 0, st>>>(a);
     else if (world == 8) adam_allreduce_kernel<8><<<grid, 256, 0, st>>>(a);
     else adam_allreduce_kernel<0><<<grid, 256, 0, st>>>(a);
