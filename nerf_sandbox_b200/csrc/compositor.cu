@@ -285,6 +285,39 @@ __global__ void mse_loss_kernel(const float* __restrict__ comp_c, const float* _
     if ((threadIdx.x & 31) == 0) { atomicAdd(&scalars[2], sc * inv_n); atomicAdd(&scalars[3], sf * inv_n); }
 }
 
+// small batches (the training step: 3 x 1024 values): one block does zero + reduce + finish, deterministically
+__global__ void __launch_bounds__(256) mse_single_block_kernel(const float* __restrict__ comp_c, const float* __restrict__ comp_f,
+                                                               const float* __restrict__ target, float* __restrict__ g_c,
+                                                               float* __restrict__ g_f, float* __restrict__ scalars, int64_t n,
+                                                               float grad_scale) {
+    __shared__ float s_c[8], s_f[8];
+    float sc = 0.f, sf = 0.f;
+    const float inv_n = 1.0f / (float)n;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        bool pt, pc, pf;
+        const float t = guard01(target[i], &pt);
+        if (comp_c) {
+            const float c = guard01(comp_c[i], &pc);
+            const float d = c - t; sc += d * d;
+            if (g_c) g_c[i] = pc ? 2.0f * d * inv_n * grad_scale : 0.0f;
+        }
+        const float f = guard01(comp_f[i], &pf);
+        const float d = f - t; sf += d * d;
+        if (g_f) g_f[i] = pf ? 2.0f * d * inv_n * grad_scale : 0.0f;
+    }
+    sc = warp_sum(sc); sf = warp_sum(sf);
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = sc; s_f[threadIdx.x >> 5] = sf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mc = 0.f, mf = 0.f;
+        for (int w = 0; w < 8; ++w) { mc += s_c[w]; mf += s_f[w]; }
+        mc *= inv_n; mf *= inv_n;
+        scalars[2] = mc; scalars[3] = mf;
+        scalars[0] = mc + mf;                                              // :1005
+        scalars[1] = -10.0f * log10f(fmaxf(mf, 1e-10f));                   // trainer.py:77-78
+    }
+}
+
 __global__ void mse_finish_kernel(float* scalars) {
     if (threadIdx.x == 0) {
         scalars[0] = scalars[2] + scalars[3];                              // :1005
@@ -341,6 +374,11 @@ extern "C" int nsb_mse_loss(const float* comp_c, const float* comp_f, const floa
                             float* scalars, int64_t B, float grad_scale, void* stream) {
     if (!comp_f || !target || !scalars || B < 1) return NSB_E_BADARG;
     const int64_t n = B * 3;
+    if (n <= 16384) {
+        mse_single_block_kernel<<<1, 256, 0, as_stream(stream)>>>(comp_c, comp_f, target, g_c, g_f, scalars, n, grad_scale);
+        NSB_LAUNCH_CHECK("mse_single_block_kernel");
+        return NSB_OK;
+    }
     mse_zero_kernel<<<1, 32, 0, as_stream(stream)>>>(scalars);
     NSB_LAUNCH_CHECK("mse_zero_kernel");
     const int grid = (int)(cdiv(n, 256) < 296 ? cdiv(n, 256) : 296);

@@ -199,8 +199,12 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
     const uint32_t f = flags | NSB_TRAINING;
     // independent Philox streams per (step, purpose)
     const uint64_t s_jit = step * 8 + 0, s_u = step * 8 + 1, s_nc = step * 8 + 2, s_nf = step * 8 + 3;
-    if (cudaMemsetAsync(grads_c, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
-    if (cudaMemsetAsync(grads_f, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+    if (grads_f == grads_c + NSB_N_PARAMS) {          // one flat buffer (the trainer's layout): one memset
+        if (cudaMemsetAsync(grads_c, 0, 2 * sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+    } else {
+        if (cudaMemsetAsync(grads_c, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+        if (cudaMemsetAsync(grads_f, 0, sizeof(float) * NSB_N_PARAMS, st) != cudaSuccess) return NSB_E_CUDA;
+    }
     // Forward chain (coarse pass, resampling, fine pass) of rays [b0, b0 + nb) on `strm`; Philox streams shifted by `sid`.
     // A half batch writes its own rows / tiles of every buffer, so the backward can treat the batch as a whole.
     auto forward = [&](int64_t b0, int64_t nb, uint64_t sid, void* strm) -> int {
