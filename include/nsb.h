@@ -33,7 +33,8 @@ extern "C" {
 /* flags for the compositor / forward pass */
 #define NSB_WHITE_BKGD 1u        /* render_utils.py:161-162 */
 #define NSB_INFINITE_LAST_BIN 2u /* render_utils.py:132-135 */
-#define NSB_TRAINING 4u          /* render_utils.py:239: add raw noise to sigma before ReLU */
+#define NSB_TRAINING 4u          /* render_utils.py:239: add raw noise to sigma before the activation */
+#define NSB_SIGMA_SOFTPLUS 8u    /* render_utils.py:243-246: sigma = softplus(raw) instead of relu(raw) (raw entry points) */
 
 /* arithmetic mode of the field (encoder + MLP) kernels */
 #define NSB_MODE_FP32 0  /* CUDA-core FFMA, fp32 everywhere: the 1e-4 parity mode           */

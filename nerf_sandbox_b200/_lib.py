@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libnsb.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MODE_FP32, MODE_BF16 = 0, 1
-WHITE_BKGD, INFINITE_LAST_BIN, TRAINING = 1, 2, 4
+WHITE_BKGD, INFINITE_LAST_BIN, TRAINING, SIGMA_SOFTPLUS = 1, 2, 4, 8
 N_PARAMS = 595844
 
 _p, _i64, _i32, _u32, _u64, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint64, C.c_float, C.c_size_t

@@ -17,7 +17,7 @@ template <bool RAW>
 __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                                               const float* __restrict__ noise, float noise_std, bool add_noise,
                                               uint64_t seed, uint64_t offset, int64_t q, float* pre_out,
-                                              const float* pre_in = nullptr) {
+                                              const float* pre_in = nullptr, bool softplus = false) {
     Sample s;
     if (RAW) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(rgb_or_raw) + q);
@@ -28,7 +28,8 @@ __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_r
         if (pre_in) pre = *pre_in;                            // reverse pass: noisy pre-activation kept from pass 1
         else if (add_noise) pre += (noise ? noise[q] : hash_normal(seed, offset, (uint64_t)q)) * noise_std;   // :239-241
         if (pre_out) *pre_out = pre;
-        s.sigma = fmaxf(pre, 0.0f);                           // :246 relu
+        // :243-246 relu, or F.softplus (beta = 1, threshold = 20: identity above it)
+        s.sigma = softplus ? (pre > 20.0f ? pre : log1pf(expf(pre))) : fmaxf(pre, 0.0f);
     } else {
         s.r = rgb_or_raw[q * 3 + 0]; s.g = rgb_or_raw[q * 3 + 1]; s.b = rgb_or_raw[q * 3 + 2];
         s.sigma = sigma[q];
@@ -69,6 +70,7 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
     const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
     for (int64_t b = blockIdx.x * (int64_t)kCompWarps + warp; b < B; b += (int64_t)gridDim.x * kCompWarps) {
         const float* zrow = z + b * N;
         const bool has_rn = ray_norm != nullptr;
@@ -81,7 +83,7 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             Sample s = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 zi = zrow[i];
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, nullptr);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, nullptr, nullptr, softplus);
                 const float sdt = fminf(fmaxf(s.sigma * delta_at(zrow, i, N, inf_last, rn, has_rn), 0.0f), 60.0f);  // :144
                 alpha = 1.0f - expf(-sdt);                     // :145
                 f = (1.0f - alpha) + eps;                      // :149
@@ -128,6 +130,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
     float* s_pre = s_T + N;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
     const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
     for (int64_t b = blockIdx.x * (int64_t)kCompWarps + warp; b < B; b += (int64_t)gridDim.x * kCompWarps) {
         const float* zrow = z + b * N;
         const bool has_rn = ray_norm != nullptr;
@@ -142,7 +145,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             if (valid) {
                 zi = zrow[i];
                 float pre1 = 0.f;
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre1);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre1, nullptr, softplus);
                 if (RAW) s_pre[i] = pre1;
                 const float sdt = fminf(fmaxf(s.sigma * delta_at(zrow, i, N, inf_last, rn, has_rn), 0.0f), 60.0f);
                 alpha = 1.0f - expf(-sdt);
@@ -188,7 +191,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             Sample s = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 alpha = s_alpha[i]; T = s_T[i];
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre, RAW ? &s_pre[i] : nullptr);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre, RAW ? &s_pre[i] : nullptr, softplus);
                 delta = delta_at(zrow, i, N, inf_last, rn, has_rn);
                 const float wraw = T * alpha;
                 const bool fin = isfinite(wraw);
@@ -220,7 +223,8 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                     o.x = w * gc[0] * s.r * (1.0f - s.r);
                     o.y = w * gc[1] * s.g * (1.0f - s.g);
                     o.z = w * gc[2] * s.b * (1.0f - s.b);
-                    o.w = pre > 0.0f ? ds : 0.0f;                  // relu backward
+                    // relu / softplus backward (softplus: sigmoid(pre), 1 above the threshold)
+                    o.w = softplus ? (pre > 20.0f ? ds : ds / (1.0f + expf(-pre))) : (pre > 0.0f ? ds : 0.0f);
                     reinterpret_cast<float4*>(d_rgb_or_raw)[q] = o;
                 } else {
                     d_rgb_or_raw[q * 3 + 0] = w * gc[0];

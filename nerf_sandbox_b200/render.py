@@ -134,7 +134,10 @@ def nerf_forward_pass(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, z_vals: t
         assert ray_norms.shape[:1] == (B,), f"ray_norms {ray_norms.shape} must broadcast with batch {B}"
     flags = ((_lib.WHITE_BKGD if white_bkgd else 0) | (_lib.INFINITE_LAST_BIN if infinite_last_bin else 0)
              | (_lib.TRAINING if training else 0))
-    if _is_fused_triplet(pos_enc, dir_enc, nerf) and sigma_activation == "relu":
+    act = (sigma_activation or "relu").lower()
+    if _is_fused_triplet(pos_enc, dir_enc, nerf) and act in ("relu", "softplus"):
+        if act == "softplus":
+            flags |= _lib.SIGMA_SOFTPLUS                      # render_utils.py:243-244, fused into the compositor kernels
         o, d, z = _lib.f32c(rays_o), _lib.f32c(rays_d_unit), _lib.f32c(z_vals)
         rn = None if ray_norms is None else _lib.f32c(ray_norms).reshape(B)
         vd = None if viewdirs_world_unit is None else _lib.f32c(viewdirs_world_unit)
@@ -171,7 +174,7 @@ _render_ws = {}
 
 
 def render_rays(rays_o, rays_d_unit, ray_norms, viewdirs, nerf_c, nerf_f, *, near, far, nc, nf, white_bkgd,
-                infinite_last_bin=False, out=None):
+                infinite_last_bin=False, out=None, sigma_activation="relu"):
     """One ray tile through nsb_render_rays (coarse linspace -> coarse pass -> deterministic resample ->
     fine pass).  Returns (rgb (B,3), acc (B,), depth (B,)); ``out`` may hold preallocated slices."""
     L = _lib.lib()
@@ -190,6 +193,11 @@ def render_rays(rays_o, rays_d_unit, ray_norms, viewdirs, nerf_c, nerf_f, *, nea
         out = (torch.empty((B, 3), device=dev), torch.empty((B,), device=dev), torch.empty((B,), device=dev))
     rgb, acc, depth = out
     flags = (_lib.WHITE_BKGD if white_bkgd else 0) | (_lib.INFINITE_LAST_BIN if infinite_last_bin else 0)
+    act = (sigma_activation or "relu").lower()
+    if act not in ("relu", "softplus"):
+        raise ValueError(f"unknown sigma_activation {sigma_activation!r}")
+    if act == "softplus":
+        flags |= _lib.SIGMA_SOFTPLUS
     _lib.check(L.nsb_render_rays(_lib.ptr(rays_o), _lib.ptr(rays_d_unit), _lib.ptr(ray_norms), _lib.ptr(viewdirs),
                                  _lib.ptr(nerf_c.packed()), _lib.ptr(nerf_f.packed()) if fine else None, _lib.ptr(rgb),
                                  _lib.ptr(acc), _lib.ptr(depth), _lib.ptr(ws), wsb, B, int(nc), nfi, float(near), float(far),
@@ -206,8 +214,8 @@ def render_image_chunked(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, ray_no
     """Render an image by tiling rays into chunks; returns {"rgb": (H,W,3), "acc": (H,W,1), "depth": (H,W,1)}."""
     if perturb:
         raise NotImplementedError("eval rendering is deterministic (every caller in the reference passes perturb=False)")
-    if not (_is_fused_triplet(pos_enc, dir_enc, nerf_c) and sigma_activation == "relu"):
-        raise NotImplementedError("render_image_chunked needs nerf_sandbox_b200 NeRF/PositionalEncoder modules (relu sigma)")
+    if not (_is_fused_triplet(pos_enc, dir_enc, nerf_c) and (sigma_activation or "relu").lower() in ("relu", "softplus")):
+        raise NotImplementedError("render_image_chunked needs nerf_sandbox_b200 NeRF/PositionalEncoder modules (relu or softplus sigma)")
     n = H * W
     dev = torch.device(device)
     o = _lib.f32c(rays_o.reshape(n, 3).to(dev)); d = _lib.f32c(rays_d_unit.reshape(n, 3).to(dev))
@@ -221,5 +229,5 @@ def render_image_chunked(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, ray_no
         e = min(n, s + chunk)
         render_rays(o[s:e], d[s:e], rn[s:e], None if vd is None else vd[s:e], nerf_c, nerf_f, near=near, far=far,
                     nc=nc_eval, nf=nf_eval, white_bkgd=white_bkgd, infinite_last_bin=infinite_last_bin,
-                    out=(rgb[s:e], acc[s:e], depth[s:e]))
+                    out=(rgb[s:e], acc[s:e], depth[s:e]), sigma_activation=sigma_activation)
     return {"rgb": rgb.reshape(H, W, 3), "acc": acc.reshape(H, W, 1), "depth": depth.reshape(H, W, 1)}

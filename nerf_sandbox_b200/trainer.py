@@ -49,13 +49,15 @@ class VanillaTrainer:
     def __init__(self, device="cuda", *, rays_per_batch=1024, nc=64, nf=128, near=2.0, far=6.0, white_bkgd=True,
                  raw_noise_std=1.0, infinite_last_bin=True, det_fine=False, lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
                  mode="fp32", seed=0, sigma_bias=None, process_group=None, allreduce="auto", lr_scheduler="none",
-                 lr_scheduler_params=None, grad_clip_norm=0.0):
+                 lr_scheduler_params=None, grad_clip_norm=0.0, sigma_activation="relu"):
         # hard-coded vanilla settings of the reference: trainer.py:277-291, :411-416; train_nerf.py:275,281
         self.device = torch.device(device)
         self.nc, self.nf, self.samp_near, self.samp_far = int(nc), int(nf), float(near), float(far)
         self.white_bkgd, self.raw_noise_std = bool(white_bkgd), float(raw_noise_std)
         self.infinite_last_bin, self.det_fine = bool(infinite_last_bin), bool(det_fine)
-        self.sigma_activation = "relu"
+        self.sigma_activation = (sigma_activation or "relu").lower()      # vanilla: relu (trainer.py:277-291); softplus is fused too
+        if self.sigma_activation not in ("relu", "softplus"):
+            raise ValueError(f"unknown sigma_activation {sigma_activation!r}")
         self.rays_per_batch = int(rays_per_batch)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         # make_scheduler (train/trainer.py:81-90): "none"/"constant" or "cosine" = CosineAnnealingLR(T_max, eta_min)
@@ -73,8 +75,8 @@ class VanillaTrainer:
         gen_state = torch.random.get_rng_state()
         torch.manual_seed(seed)
         self.pos_enc, self.dir_enc = get_vanilla_nerf_encoders()
-        self.nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu", mode=mode)      # trainer.py:326-341
-        self.nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu", mode=mode)
+        self.nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)      # trainer.py:326-341
+        self.nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)
         torch.random.set_rng_state(gen_state)
         if sigma_bias is not None:
             with torch.no_grad():
@@ -123,7 +125,8 @@ class VanillaTrainer:
         return list(self.nerf_c.parameters()) + list(self.nerf_f.parameters())     # trainer.py:383-386
 
     def _flags(self):
-        return (_lib.WHITE_BKGD if self.white_bkgd else 0) | (_lib.INFINITE_LAST_BIN if self.infinite_last_bin else 0)
+        return ((_lib.WHITE_BKGD if self.white_bkgd else 0) | (_lib.INFINITE_LAST_BIN if self.infinite_last_bin else 0)
+                | (_lib.SIGMA_SOFTPLUS if self.sigma_activation == "softplus" else 0))
 
     def _workspace(self, B):
         need = _lib.lib().nsb_train_workspace_bytes(B, self.nc, self.nf, self.mode)

@@ -447,3 +447,38 @@ def test_frame_outputs_match_reference_image_path():
     assert abs(nsb.compute_psnr(rgb, gt) - float(-10.0 * torch.log10(torch.nn.functional.mse_loss(pred, gtc)))) <= 1e-3
     nd = nsb.frame_outputs({"rgb": rgb, "acc": acc, "depth": depth / 7.0}, near=0.0, far=1.0, use_ndc=True)
     assert np.array_equal(nd["depth"].cpu().numpy(), u8((depth / 7.0).squeeze(-1)))
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_softplus_sigma_fused_matches_torch_composition(nsb, training):
+    """sigma_activation='softplus' (render_utils.py:243-244) fused into the compositor kernels against the generic
+    composition (our NeRF.forward + torch.sigmoid / F.softplus + volume_render_rays), values and parameter gradients."""
+    g = golden("forward_pass")
+    net, _ = load_nerf(g["seed"], g["sigma_bias"])
+    pe, de = nsb.get_vanilla_nerf_encoders()
+    pe, de = pe.to(DEV), de.to(DEV)
+
+    class Foreign(torch.nn.Module):            # same network, but not recognised as the fused triplet
+        def __init__(self, inner):
+            super().__init__(); self.inner = inner
+        def forward(self, a, b):
+            return self.inner(a, b)
+
+    kw = dict(ray_norms=T(g["rays_d_marching_norm"]), viewdirs_world_unit=T(g["viewdirs"]), white_bkgd=True, infinite_last_bin=True,
+              sigma_activation="softplus", training=training, raw_noise_std=1.0 if training else 0.0,
+              raw_noise=T(g["noise"]) if training else None)
+    args = (T(g["rays_o_marching"]), T(g["rays_d_marching_unit"]), T(g["z"]))
+    tgt = torch.rand((24, 3), device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    outs, grads = [], []
+    for nerf in (net, Foreign(net)):
+        net.zero_grad()
+        comp, w, acc, depth = nsb.nerf_forward_pass(*args, pos_enc=pe, dir_enc=de, nerf=nerf, **kw)
+        ((comp - tgt) ** 2).mean().backward()
+        outs.append([N(comp), N(w), N(acc), N(depth)])
+        grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone())
+    for a, b in zip(*outs):
+        close(a, b, 1e-4, 1e-6)
+    # softplus keeps every sample alive (unlike relu), so the two differ from the relu goldens
+    assert np.abs(outs[0][0] - g["train_comp" if training else "eval_comp"]).max() > 1e-4 or not training
+    ga, gb = N(grads[0]).astype(np.float64), N(grads[1]).astype(np.float64)
+    assert np.linalg.norm(ga - gb) <= 2e-4 * np.linalg.norm(gb)
