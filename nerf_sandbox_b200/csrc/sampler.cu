@@ -190,16 +190,61 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
         // weights_bins = 0.5*(w[1:]+w[:-1]) + 1e-5 (:927-928); sample_pdf adds another 1e-5 and clamps (:38)
         build_cdf(cdf, M, lane, [&](int j) { return fmaxf((0.5f * (wrow[j + 1] + wrow[j]) + 1e-5f) + 1e-5f, 0.0f); });
         __syncwarp();
-        for (int s = lane; s < Nf; s += 32) {
-            float u;
-            if (deterministic) u = linspace01(s, Nf);
-            else u = u_in ? u_in[b * Nf + s] : philox_uniform(seed, offset, (uint64_t)(b * Nf + s));
-            int ind;
-            const float zf = invert(cdf, edges, M, u, &ind);
-            fine[s] = zf;
-            if (z_fine) z_fine[b * Nf + s] = zf;
+        const bool draw_sorted = !deterministic && !u_in;
+        if (draw_sorted) {
+            // In-kernel draws: the merge below only needs the SORTED fine samples, and sorted iid uniforms are exactly the
+            // normalised partial sums of Nf+1 iid exponentials (order statistics of the uniform distribution), so they are
+            // generated in order: u_(k) = (E_1 + .. + E_k) / (E_1 + .. + E_{Nf+1}).  One prefix sum instead of a 28-stage
+            // bitonic sort, and one Philox block per four draws.  Same distribution as sort(rand()); the explicit-u path
+            // below keeps the draw-then-sort form.
+            const int cnt = (Nf + 1 + 31) >> 5;                       // draws per lane, a contiguous block
+            const int s0 = lane * cnt;
+            float local = 0.f;
+            for (int q = 0; q < cnt; q += 4) {
+                const uint4 r = philox4(seed, offset, ((uint64_t)b * 32 + lane) * 8 + (uint64_t)(q >> 2));
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int sidx = s0 + q + e;
+                    if (q + e < cnt && sidx <= Nf) {
+                        const float ex = -__logf(((float)(rw[e] >> 8) + 1.0f) * (1.0f / 16777216.0f));     // Exp(1), argument in (0,1]
+                        local += ex;
+                        if (sidx < Nf) fine[sidx] = ex;                      // (the last one only enters the total)
+                    }
+                }
+            }
+            float incl = local;                                       // inclusive scan of the lane totals
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float tsum = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += tsum;
+            }
+            const float total = __shfl_sync(0xffffffffu, incl, 31);
+            // this lane's partial sums run from the previous lane's inclusive total to its own (clamped: monotone across
+            // lane boundaries whatever the rounding of the in-lane additions)
+            float run = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) run = 0.f;
+            __syncwarp();
+            for (int q = 0; q < cnt; ++q) {
+                const int sidx = s0 + q;
+                if (sidx < Nf) {
+                    run = fminf(run + fine[sidx], incl);
+                    int ind;
+                    const float zf = invert(cdf, edges, M, fminf(run / total, 1.0f), &ind);
+                    fine[sidx] = zf;
+                    if (z_fine) z_fine[b * Nf + sidx] = zf;
+                }
+            }
+        } else {
+            for (int s = lane; s < Nf; s += 32) {
+                const float u = deterministic ? linspace01(s, Nf) : u_in[b * Nf + s];
+                int ind;
+                const float zf = invert(cdf, edges, M, u, &ind);
+                fine[s] = zf;
+                if (z_fine) z_fine[b * Nf + s] = zf;
+            }
         }
-        if (!deterministic) {
+        if (!deterministic && !draw_sorted) {
             for (int j = Nf + lane; j < sort_len; j += 32) fine[j] = __int_as_float(0x7f800000);   // +inf pad
             __syncwarp();
             warp_bitonic_sort(fine, sort_len, lane);

@@ -482,3 +482,32 @@ def test_softplus_sigma_fused_matches_torch_composition(nsb, training):
     assert np.abs(outs[0][0] - g["train_comp" if training else "eval_comp"]).max() > 1e-4 or not training
     ga, gb = N(grads[0]).astype(np.float64), N(grads[1]).astype(np.float64)
     assert np.linalg.norm(ga - gb) <= 2e-4 * np.linalg.norm(gb)
+
+
+def test_resample_in_kernel_draws_are_sorted_uniform_order_statistics(nsb):
+    """Without explicit u the resampler draws the sorted uniforms directly (normalised partial sums of exponentials = the
+    order statistics of iid uniforms).  Check against the draw-then-sort path with explicit iid u on the same PDF: same
+    pooled distribution of fine samples, same mean of every order statistic; merged rows sorted and complete."""
+    from nerf_sandbox_b200 import _lib
+    L = _lib.lib()
+    B, Nc, Nf = 8192, 64, 128
+    rng = np.random.default_rng(3)
+    zc1 = O.stratified_z(2.0, 6.0, Nc, rng.uniform(0, 1, (1, Nc)).astype(np.float32))
+    w1 = (np.exp(-0.5 * ((zc1 - 3.7) / 0.35) ** 2) + 0.02).astype(np.float32)          # one peaked PDF shared by all rays
+    zc, w = T(np.repeat(zc1, B, 0)), T(np.repeat(w1, B, 0))
+    outs = []
+    for u in (None, T(rng.uniform(0, 1, (B, Nf)).astype(np.float32))):
+        z_all = torch.empty((B, Nc + Nf), device=DEV); z_f = torch.empty((B, Nf), device=DEV)
+        _lib.check(L.nsb_resample_merge(_lib.ptr(zc), _lib.ptr(w), _lib.ptr(u), _lib.ptr(z_all), _lib.ptr(z_f), B, Nc, Nf, 0, 123, 7,
+                                        _lib.stream()), "resample")
+        za, zf = N(z_all), np.sort(N(z_f), axis=1)
+        assert (np.diff(za, axis=1) >= 0).all()
+        assert np.array_equal(np.sort(np.concatenate([N(zc), N(z_f)], 1), axis=1), za)
+        outs.append(zf)
+    a, b = outs
+    assert not np.array_equal(a[0], a[1])                                              # rays draw independently
+    ha, _ = np.histogram(a, bins=64, range=(2.0, 6.0)); hb, _ = np.histogram(b, bins=64, range=(2.0, 6.0))
+    assert np.abs(ha - hb).max() / a.size < 2e-3                                       # pooled distribution
+    se = np.sqrt(a.var(0) / B + b.var(0) / B)                                          # every order statistic: same mean ...
+    assert (np.abs(a.mean(0) - b.mean(0)) / se).max() < 5.0
+    assert np.abs(a.std(0) / b.std(0) - 1.0).max() < 0.06                              # ... and spread (sd of a sample sd ~ 0.8 %)
