@@ -150,9 +150,17 @@ int nsb_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws
                   int64_t Q, int mode, void* stream);
 
 /* torch.optim.Adam step (train/trainer.py:383-386, :722) on flat buffers; grads are multiplied by
- * grad_scale first (1/world_size after a sum-allreduce). t is the 1-based step count. */
+ * grad_scale first (1/world_size after a sum-allreduce). t is the 1-based step count.
+ * loss_guard [opt]: device pointer to the step's loss; when it is not finite the update is skipped, as the reference
+ * loop does (train/trainer.py:713-716). */
 int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int64_t t, float grad_scale, void* stream);
+                  float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) (train/trainer.py:719-721) on a flat gradient buffer: the total L2 norm
+ * of pre_scale * grads[n] is taken over ALL n entries (both nets when they share one buffer) and grads *= min(1,
+ * max_norm / (norm + 1e-6)).  pre_scale = the grad_scale the following Adam call will apply (1/world after a sum-allreduce).
+ * scratch: one float of device memory. */
+int nsb_grad_clip(float* grads, int64_t n, float max_norm, float pre_scale, float* scratch, void* stream);
 
 /* Data-parallel tail of a step in ONE kernel (replaces `all_reduce(grads)` + Adam, train/trainer.py:717-725 under
  * DDP): waits until every rank's gradient buffer of this epoch is complete (flag exchange through peer memory), sums the
@@ -160,14 +168,24 @@ int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t
  * grad_scale) to this rank's full parameter copies; the replicas stay bit-identical.
  * params / m / v: HOST arrays of n_nets device pointers, n floats each (one entry per net); net k's gradients are
  * peer_grads[r] + k * n.  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device addresses valid in this process:
- * symmetric / peer-mapped allocations): rank r's gradient buffer [n_nets * n] and flag block (uint32[world], zeroed once).
+ * symmetric / peer-mapped allocations): rank r's gradient buffer [n_nets * n] and flag block (uint32[3 * world], zeroed once: epoch flags, then one "my loss is
+ * not finite" word per rank and epoch parity).
  * `epoch` starts at 1 and increases by one per step on every rank; the caller alternates between two gradient buffers by
  * epoch parity (that is what makes one flag exchange per step sufficient).  n % 4 == 0.
  * mc_grads (optional): multicast (NVLS) address of the same gradient buffers; when given, the sum is one
- * `multimem.ld_reduce` per 16 bytes -- the NVSwitch reduces, every rank receives n_nets * n floats instead of world times that. */
+ * `multimem.ld_reduce` per 16 bytes -- the NVSwitch reduces, every rank receives n_nets * n floats instead of world times that.
+ * loss_guard [opt]: this rank's loss (device); a non-finite loss on ANY rank makes EVERY rank skip the update
+ * (train/trainer.py:713-716, made collective so the replicas stay identical). */
 int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                             const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr,
-                            float beta1, float beta2, float eps, int64_t t, float grad_scale, void* stream);
+                            float beta1, float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard, void* stream);
+
+/* Health of the peer-memory exchange above.  A rank waits NSB_PEER_TIMEOUT_S seconds (environment, default 600 -- a peer
+ * may be validating, checkpointing or stalled on data) for its peers' flags; when that expires the kernel skips the update,
+ * records the peer it was waiting for and returns normally (no trap: the CUDA context stays usable).  *code = 0 when every
+ * exchange so far completed, else 1 + the rank that never arrived.  Synchronises the device (a 4-byte read-back); the
+ * trainer calls it whenever it reads the step's scalars on the host.  No counterpart in the reference (single GPU). */
+int nsb_peer_status(int* code);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-path entry points (one host call per step / per ray tile)
@@ -182,13 +200,17 @@ size_t nsb_train_workspace_bytes(int64_t B, int Nc, int Nf, int mode);
  * params / m / v / packed: HOST arrays of two device pointers (coarse, fine); grads: [2 * NSB_N_PARAMS] (with world > 1 this
  * rank's buffer of the current epoch parity, i.e. capture one graph per parity); draws are always generated in-kernel.
  * lr_T_max > 0: the learning rate follows CosineAnnealingLR(T_max, eta_min) from base `lr` (make_scheduler, train/trainer.py:81-88),
- * evaluated on the device from the step count; lr_T_max <= 0: constant lr. */
+ * evaluated on the device from the step count; lr_T_max <= 0: constant lr.
+ * scalars[8]: {loss, psnr, mse_c, mse_f, squared gradient norm (when clipping), 3 spare}.  A non-finite loss skips the
+ * optimiser update (train/trainer.py:713-716; the counter still advances).  grad_clip_norm > 0: clip_grad_norm_ over both
+ * nets before Adam (:719-721) -- single rank only (world > 1 returns NSB_E_BADARG: the norm of the reduced gradient is not
+ * available inside the fused exchange; use the NCCL path + nsb_grad_clip). */
 int nsb_train_step(const float* rays_o, const float* rays_d, const float* ray_norm, const float* viewdirs,
                    const float* target, float* const* params, float* const* m, float* const* v, void* const* packed,
                    float* grads, float* scalars, float* comp_c, float* comp_f, void* ws, size_t ws_bytes, int64_t B,
                    int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
                    uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
-                   uint64_t* step_counter,
+                   float grad_clip_norm, uint64_t* step_counter,
                    const void* const* peer_grads, const void* mc_grads, void* const* peer_flags, int rank, int world, void* stream);
 
 /* Trainer._train_step + loss.backward(), train/trainer.py:876-1013 and :717.  Batch tensors as
@@ -243,10 +265,11 @@ int nsb_sample_pixel_batch(const float* images, int F, int H, int W, int C, cons
 /* Eval output path: what ValidationRenderer does with a rendered frame,
  * utils/validation_renderer.py:485-533 with save_rgb_png / save_gray_png (utils/render_utils.py:28-47) and _compute_psnr
  * (:171-196), without leaving the device: rgb8[n,3] / acc8[n] / depth8[n] = (clamp(x,0,1) * 255 + 0.5) truncated to uint8,
- * depth first mapped to clamp((depth - near) / (far - near + 1e-8)) (or used as is when use_ndc); any output may be NULL.
+ * depth first mapped to clamp((depth - fp32(near)) / fp32(far - near + 1e-8)) with a true division, bit for bit what torch computes
+ * from Python-double near/far (or used as is when use_ndc); any output may be NULL.
  * With gt_rgb[n,3] (and optional mask[n], 1 = valid): psnr_out[0] = -10 log10(max(mse, 1e-10)), psnr_out[1] = mse with
  * mse = sum(mask * diff^2) / max(3 * sum(mask), 1e-8) over clamped values; psnr_scratch = 2 doubles of device scratch. */
-int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, float depth_near, float depth_far,
+int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, double depth_near, double depth_far,
                      int use_ndc, uint8_t* rgb8, uint8_t* acc8, uint8_t* depth8, const float* gt_rgb, const float* mask,
                      double* psnr_scratch, float* psnr_out, void* stream);
 

@@ -5,6 +5,7 @@
 // [feat | gamma(d)] buffer of color_fc), dedicated warp-per-point kernels for the N=1/N=3 heads.
 // The tensor-core mode lives in field_tc.cu.
 #include <cstdio>
+#include <cstdlib>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -566,7 +567,10 @@ __device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, flo
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
-                            float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr, float eta_min, int64_t T_max) {
+                            float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr, float eta_min, int64_t T_max,
+                            const float* __restrict__ loss_guard) {
+    // non-finite loss: the reference skips the optimiser step (train/trainer.py:713-716)
+    if (loss_guard && !isfinite(*loss_guard)) return;
     if (t_dev) adam_bias_corrections(t_dev, lr, eta_min, T_max, b1, b2, lr_over_bc1, inv_sqrt_bc2);
     // 16-byte accesses when the buffers allow it (the flat parameter buffers do: 595,844 = 4 x 148,961)
     const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -613,7 +617,12 @@ struct AdamArParams {
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
     const uint64_t* t_dev; float lr, eta_min; int64_t T_max;       // graph replay: step count (and epoch) = *t_dev + 1
+    const float* loss_guard;                // this rank's loss (device), or null: a non-finite loss on ANY rank skips the update
+    uint64_t timeout_ns;                    // how long a rank waits for its peers' flags before it gives up (NSB_PEER_TIMEOUT_S)
 };
+// Set (1 + peer rank) by a rank that gave up waiting for `peer`; read by the host through nsb_peer_status().  A rank that
+// times out leaves the kernel WITHOUT applying the update and without killing the context -- the host raises.
+__device__ unsigned int g_peer_error = 0;
 __device__ __forceinline__ uint64_t ar_global_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // NVLS: one load returns the sum over every rank's copy, reduced inside the NVSwitch
 __device__ __forceinline__ float4 ld_reduce_mc(const float4* p) {
@@ -633,9 +642,17 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
     float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2;
     uint32_t epoch = a.epoch;
     if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.eta_min, a.T_max, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
+    __shared__ int s_abort;
+    // train/trainer.py:713-716: a non-finite loss skips the optimiser step.  Across ranks the decision must be common, so
+    // every rank publishes "my loss is bad" next to its epoch flag (one word per rank and epoch parity) and skips if any is.
+    const uint32_t bad = (a.loss_guard && !isfinite(*a.loss_guard)) ? 1u : 0u;
+    if (threadIdx.x == 0) s_abort = (world == 1 && bad) ? 1 : 0;
+    __syncthreads();
     if (world > 1 && threadIdx.x < world) {     // (a single rank has nobody to wait for)
         const int r = threadIdx.x;
+        const int bad_ofs = world * (1 + (int)(epoch & 1u));
         if (blockIdx.x == 0) {      // the gradient kernels of this stream have finished: publish that to rank r
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + bad_ofs + a.rank), "r"(bad) : "memory");
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(epoch) : "memory");
         }
@@ -646,13 +663,21 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
             if ((int32_t)(seen - epoch) >= 0) break;
             if (i & 0x3FFu) continue;
             if (t0 == 0) { t0 = ar_global_ns(); continue; }
-            if (ar_global_ns() - t0 > 5000000000ull) {      // 5 s: a peer never arrived -- trap instead of hanging the GPU
-                printf("nsb adam_allreduce: rank %d still waiting for rank %d at epoch %u\n", a.rank, r, epoch);
-                __trap();
+            if (ar_global_ns() - t0 > a.timeout_ns) {
+                // a peer never arrived (default: 10 min of skew -- validation, checkpointing or a data stall on one rank are
+                // ordinary): record who, skip the update, let the host raise.  No __trap: the context stays usable.
+                if (blockIdx.x == 0) printf("nsb adam_allreduce: rank %d gave up waiting for rank %d at epoch %u\n", a.rank, r, epoch);
+                atomicMax(&g_peer_error, 1u + (unsigned)r);
+                s_abort = 1;
+                break;
             }
         }
+        uint32_t peer_bad;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(peer_bad) : "l"(a.flags[a.rank] + bad_ofs + r) : "memory");
+        if (peer_bad) s_abort = 1;
     }
     __syncthreads();
+    if (s_abort) return;
     const int64_t n4 = a.n >> 2, total4 = n4 * a.n_nets;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i / n4);
@@ -694,7 +719,7 @@ namespace nsb {
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
                         float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max,
-                        const void* mc_grads, void* stream) {
+                        const void* mc_grads, const float* loss_guard, void* stream) {
     if (!params || !m || !v || !peer_grads || (!peer_flags && world > 1) || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 ||
         world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
@@ -712,25 +737,45 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
     a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr; a.eta_min = eta_min; a.T_max = T_max;
     a.mc_grads = static_cast<const float*>(mc_grads);
-    // every block spins on the flag exchange first, so the grid must be co-resident: at most four blocks of 256 per SM
+    a.loss_guard = loss_guard;
+    static const uint64_t timeout_ns = [] {
+        const char* e = getenv("NSB_PEER_TIMEOUT_S");
+        const double sec = e && atof(e) > 0 ? atof(e) : 600.0;
+        return (uint64_t)(sec * 1e9);
+    }();
+    a.timeout_ns = timeout_ns;
+    // every block spins on the flag exchange first, so the whole grid must be co-resident: cap it at what the occupancy
+    // calculator says fits (registers of the chosen instantiation included), at most four blocks per SM
+    void (*kern)(const AdamArParams) = world == 1 ? adam_allreduce_kernel<1> : world == 2 ? adam_allreduce_kernel<2>
+                                     : world == 4 ? adam_allreduce_kernel<4> : world == 8 ? adam_allreduce_kernel<8> : adam_allreduce_kernel<0>;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) return check_launch("occupancy(adam_allreduce_kernel)");
+    if (per_sm > 4) per_sm = 4;
     int grid = (int)cdiv((n >> 2) * n_nets, 256);
-    if (grid > 4 * num_sms()) grid = 4 * num_sms();
-    cudaStream_t st = as_stream(stream);
-    if (world == 1) adam_allreduce_kernel<1><<<grid, 256, 0, st>>>(a);
-    else if (world == 2) adam_allreduce_kernel<2><<<grid, 256, 0, st>>>(a);
-    else if (world == 4) adam_allreduce_kernel<4><<<grid, 256, 0, st>>>(a);
-    else if (world == 8) adam_allreduce_kernel<8><<<grid, 256, 0, st>>>(a);
-    else adam_allreduce_kernel<0><<<grid, 256, 0, st>>>(a);
+    if (grid > per_sm * num_sms()) grid = per_sm * num_sms();
+    kern<<<grid, 256, 0, as_stream(stream)>>>(a);
     NSB_LAUNCH_CHECK("adam_allreduce_kernel");
+    return NSB_OK;
+}
+int peer_status(int* code) {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_peer_error, sizeof(v)) != cudaSuccess) return check_launch("cudaMemcpyFromSymbol(g_peer_error)");
+    *code = (int)v;
     return NSB_OK;
 }
 }  // namespace nsb
 
 extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                                        const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n,
-                                       float lr, float beta1, float beta2, float eps, int64_t t, float grad_scale, void* stream) {
+                                       float lr, float beta1, float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard,
+                                       void* stream) {
     return adam_allreduce_impl(params, m, v, n_nets, peer_grads, peer_flags, rank, world, epoch, n, lr, beta1, beta2, eps, t, grad_scale,
-                               nullptr, 0.f, 0, mc_grads, stream);
+                               nullptr, 0.f, 0, mc_grads, loss_guard, stream);
+}
+
+extern "C" int nsb_peer_status(int* code) {
+    if (!code) return NSB_E_BADARG;
+    return peer_status(code);
 }
 
 extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream) {
@@ -744,17 +789,44 @@ extern "C" int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, i
 
 namespace nsb {
 int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int64_t t,
-              float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, void* stream) {
+              float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max, const float* loss_guard, void* stream) {
     if (!params || !grads || !m || !v || n < 1 || t < 1) return NSB_E_BADARG;
     const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
     adam_kernel<<<elem_grid(n), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
-                                                            (float)(1.0 / sqrt(bc2)), grad_scale, t_dev, lr, eta_min, T_max);
+                                                            (float)(1.0 / sqrt(bc2)), grad_scale, t_dev, lr, eta_min, T_max, loss_guard);
     NSB_LAUNCH_CHECK("adam_kernel");
     return NSB_OK;
 }
 }  // namespace nsb
 
 extern "C" int nsb_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
-                             float beta2, float eps, int64_t t, float grad_scale, void* stream) {
-    return adam_impl(params, grads, m, v, n, lr, beta1, beta2, eps, t, grad_scale, nullptr, 0.f, 0, stream);
+                             float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard, void* stream) {
+    return adam_impl(params, grads, m, v, n, lr, beta1, beta2, eps, t, grad_scale, nullptr, 0.f, 0, loss_guard, stream);
+}
+
+// ---- torch.nn.utils.clip_grad_norm_ (train/trainer.py:719-721) on the flat gradient buffer -------------------------------
+namespace nsb {
+__global__ void grad_sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ acc) {
+    float s = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+__global__ void grad_clip_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ acc, float max_norm, float pre_scale) {
+    // total_norm of (pre_scale * g); clip_coef = max_norm / (total_norm + 1e-6), clamped to 1 (torch semantics)
+    const float coef = fminf(max_norm / (sqrtf(*acc) * pre_scale + 1e-6f), 1.0f);
+    if (coef >= 1.0f) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= coef;
+}
+}  // namespace nsb
+
+extern "C" int nsb_grad_clip(float* grads, int64_t n, float max_norm, float pre_scale, float* scratch, void* stream) {
+    if (!grads || !scratch || n < 1 || !(max_norm > 0.f)) return NSB_E_BADARG;
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(scratch, 0, sizeof(float), st) != cudaSuccess) return NSB_E_CUDA;
+    grad_sumsq_kernel<<<elem_grid(n), 256, 0, st>>>(grads, n, scratch);
+    NSB_LAUNCH_CHECK("grad_sumsq_kernel");
+    grad_clip_kernel<<<elem_grid(n), 256, 0, st>>>(grads, n, scratch, max_norm, pre_scale);
+    NSB_LAUNCH_CHECK("grad_clip_kernel");
+    return NSB_OK;
 }

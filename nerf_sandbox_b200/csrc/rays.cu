@@ -109,7 +109,7 @@ __global__ void sample_pixel_batch_kernel(const float* __restrict__ images, int 
 // u8 = (clamp(x, 0, 1) * 255 + 0.5) truncated  (two roundings: this file is compiled with -fmad=false, like numpy)
 __device__ __forceinline__ uint8_t to_u8(float x) { return (uint8_t)(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f); }
 __global__ void frame_output_kernel(const float* __restrict__ rgb, const float* __restrict__ acc, const float* __restrict__ depth, int64_t n,
-                                    float near_, float inv_range, int use_ndc, uint8_t* __restrict__ rgb8, uint8_t* __restrict__ acc8,
+                                    float near_, float range, int use_ndc, uint8_t* __restrict__ rgb8, uint8_t* __restrict__ acc8,
                                     uint8_t* __restrict__ depth8, const float* __restrict__ gt, const float* __restrict__ mask,
                                     double* __restrict__ psnr_acc) {
     double se = 0.0, wsum = 0.0;
@@ -117,7 +117,8 @@ __global__ void frame_output_kernel(const float* __restrict__ rgb, const float* 
         const float r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
         if (rgb8) { rgb8[3 * i] = to_u8(r); rgb8[3 * i + 1] = to_u8(g); rgb8[3 * i + 2] = to_u8(b); }
         if (acc8 && acc) acc8[i] = to_u8(acc[i]);
-        if (depth8 && depth) depth8[i] = to_u8(use_ndc ? depth[i] : (depth[i] - near_) * inv_range);     // :491-492
+        // :491-492 -- a true IEEE division by fp32(far - near + 1e-8), as torch's `tensor / python_float` does: byte-exact
+        if (depth8 && depth) depth8[i] = to_u8(use_ndc ? depth[i] : (depth[i] - near_) / range);
         if (gt && psnr_acc) {                                                                           // _compute_psnr, :171-196
             const float m = mask ? mask[i] : 1.0f;
             float e = 0.0f;
@@ -147,7 +148,7 @@ __global__ void psnr_finish_kernel(const double* __restrict__ acc, float* __rest
 
 using namespace nsb;
 
-extern "C" int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, float depth_near, float depth_far,
+extern "C" int nsb_frame_output(const float* rgb, const float* acc, const float* depth, int64_t n, double depth_near, double depth_far,
                                 int use_ndc, uint8_t* rgb8, uint8_t* acc8, uint8_t* depth8, const float* gt_rgb, const float* mask,
                                 double* psnr_scratch, float* psnr_out, void* stream) {
     if (n == 0) return NSB_OK;
@@ -156,8 +157,9 @@ extern "C" int nsb_frame_output(const float* rgb, const float* acc, const float*
     cudaStream_t st = as_stream(stream);
     if (gt_rgb && cudaMemsetAsync(psnr_scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return NSB_E_CUDA;
     const int64_t want = cdiv(n, 256), cap = (int64_t)num_sms() * 8;
-    const float inv_range = 1.0f / (depth_far - depth_near + 1e-8f);
-    frame_output_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rgb, acc, depth, n, depth_near, inv_range, use_ndc, rgb8, acc8, depth8,
+    // Python evaluates `far - near + 1e-8` in double and torch rounds that scalar to the tensor's dtype
+    const float range = (float)(depth_far - depth_near + 1e-8);
+    frame_output_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(rgb, acc, depth, n, (float)depth_near, range, use_ndc, rgb8, acc8, depth8,
                                                                        gt_rgb, mask, gt_rgb ? psnr_scratch : nullptr);
     NSB_LAUNCH_CHECK("frame_output_kernel");
     if (gt_rgb) {

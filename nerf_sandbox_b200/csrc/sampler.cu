@@ -199,9 +199,11 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
             // below keeps the draw-then-sort form.
             const int cnt = (Nf + 1 + 31) >> 5;                       // draws per lane, a contiguous block
             const int s0 = lane * cnt;
+            // Philox blocks per lane: at least ceil(cnt / 4), so the lanes' counter ranges never overlap (8 up to Nf = 1023)
+            const uint64_t ctr_stride = (uint64_t)max(8, (cnt + 3) >> 2);
             float local = 0.f;
             for (int q = 0; q < cnt; q += 4) {
-                const uint4 r = philox4(seed, offset, ((uint64_t)b * 32 + lane) * 8 + (uint64_t)(q >> 2));
+                const uint4 r = philox4(seed, offset, ((uint64_t)b * 32 + lane) * ctr_stride + (uint64_t)(q >> 2));
                 const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {

@@ -93,9 +93,11 @@ def gather_shards(local: torch.Tensor, n_total: int, group=None, align: int = 1)
 
 @torch.no_grad()
 def render_image_sharded(rays_o, rays_d_unit, ray_norms, H, W, near, far, nerf_c, nerf_f, nc_eval, nf_eval, white_bkgd,
-                         eval_chunk=65536, *, viewdirs_world_unit=None, infinite_last_bin=False, group=None) -> dict:
+                         eval_chunk=65536, *, viewdirs_world_unit=None, infinite_last_bin=False, sigma_activation="relu",
+                         group=None, timings=None) -> dict:
     """render_image_chunked (utils/render_utils.py:285-424) with the H*W rays split into one contiguous pixel block per
-    rank; every rank returns the full frame."""
+    rank; every rank returns the full frame.  ``timings`` (optional dict) receives CUDA events around this rank's
+    compute and around the all-gather (keys "compute", "gather": (start, end) event pairs)."""
     from .render import render_rays
     rank, world = world_info(group)
     n = H * W
@@ -104,11 +106,20 @@ def render_image_sharded(rays_o, rays_d_unit, ray_norms, H, W, near, far, nerf_c
     vd = None if viewdirs_world_unit is None else viewdirs_world_unit.reshape(n, 3)[s:e]
     m = e - s
     out = torch.empty((m, 5), device=rays_o.device, dtype=torch.float32)       # rgb | acc | depth
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+    if ev:
+        ev[0].record()
     for a in range(0, m, eval_chunk):
         b = min(m, a + eval_chunk)
         rgb, acc, depth = render_rays(o[a:b].contiguous(), d[a:b].contiguous(), rn[a:b].contiguous(),
                                       None if vd is None else vd[a:b].contiguous(), nerf_c, nerf_f, near=near, far=far,
-                                      nc=nc_eval, nf=nf_eval, white_bkgd=white_bkgd, infinite_last_bin=infinite_last_bin)
+                                      nc=nc_eval, nf=nf_eval, white_bkgd=white_bkgd, infinite_last_bin=infinite_last_bin,
+                                      sigma_activation=sigma_activation)
         out[a:b, :3] = rgb; out[a:b, 3] = acc; out[a:b, 4] = depth
+    if ev:
+        ev[1].record(); ev[2].record()
     full = gather_shards(out, n, group, align=128)
+    if ev:
+        ev[3].record()
+        timings["compute"], timings["gather"] = (ev[0], ev[1]), (ev[2], ev[3])
     return {"rgb": full[:, :3].reshape(H, W, 3), "acc": full[:, 3].reshape(H, W, 1), "depth": full[:, 4].reshape(H, W, 1)}

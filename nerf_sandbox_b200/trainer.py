@@ -32,16 +32,22 @@ class _FusedStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tr, batch, draws, *params):
-        scal, comp_c, comp_f = tr._fwd_bwd(batch, draws, grad_scale=1.0)
+        # gradients go to a buffer of this call's own (never the trainer's shared / peer-visible buffers): a later
+        # _train_step(), step() or step_graph() before loss.backward() cannot change what backward() returns
+        grads = torch.empty(2 * _lib.N_PARAMS, device=tr.device, dtype=torch.float32)
+        scal, comp_c, comp_f = tr._fwd_bwd(batch, draws, grad_scale=1.0, grads=grads)
         ctx.tr = tr
+        ctx.save_for_backward(grads)
         ctx.mark_non_differentiable(comp_c, comp_f)
         return scal[0].clone(), scal[1].clone(), comp_c, comp_f
 
     @staticmethod
     def backward(ctx, g_loss, g_psnr, g_cc, g_cf):
         tr = ctx.tr
-        gc = tr.nerf_c.unflatten(tr.grads_c * g_loss)
-        gf = tr.nerf_f.unflatten(tr.grads_f * g_loss)
+        (grads,) = ctx.saved_tensors
+        n = _lib.N_PARAMS
+        gc = tr.nerf_c.unflatten(grads[:n] * g_loss)
+        gf = tr.nerf_f.unflatten(grads[n:] * g_loss)
         return (None, None, None) + tuple(gc) + tuple(gf)
 
 
@@ -67,17 +73,16 @@ class VanillaTrainer:
         sp = lr_scheduler_params or {}
         self.lr_T_max = int(sp["T_max"]) if name == "cosine" else 0
         self.lr_eta_min = float(sp.get("eta_min", 0.0)) if name == "cosine" else 0.0
-        if float(grad_clip_norm or 0.0) > 0:
-            raise NotImplementedError("grad_clip_norm is not on the fused step path (the reference default is 0 = off)")
+        self.grad_clip_norm = float(grad_clip_norm or 0.0)          # trainer.py:719-721 (0 = off, the reference default)
         self.mode = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}[mode]
         self.seed, self.global_step, self.adam_t = int(seed), 0, 0
         self.pg = process_group
-        gen_state = torch.random.get_rng_state()
-        torch.manual_seed(seed)
-        self.pos_enc, self.dir_enc = get_vanilla_nerf_encoders()
-        self.nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)      # trainer.py:326-341
-        self.nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)
-        torch.random.set_rng_state(gen_state)
+        # init draws come from a forked RNG: neither the caller's CPU generator nor this device's CUDA generator is reseeded
+        with torch.random.fork_rng(devices=[self.device] if self.device.type == "cuda" else []):
+            torch.manual_seed(seed)
+            self.pos_enc, self.dir_enc = get_vanilla_nerf_encoders()
+            self.nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)      # trainer.py:326-341
+            self.nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation=self.sigma_activation, mode=mode)
         if sigma_bias is not None:
             with torch.no_grad():
                 self.nerf_c.sigma_out.bias.fill_(sigma_bias); self.nerf_f.sigma_out.bias.fill_(sigma_bias)
@@ -92,6 +97,10 @@ class VanillaTrainer:
         world = world_info(process_group)[1]
         if allreduce not in ("auto", "p2p", "nccl"):
             raise ValueError("allreduce must be 'auto', 'p2p' or 'nccl'")
+        if world > 1 and self.grad_clip_norm > 0:
+            if allreduce == "p2p":
+                raise ValueError("grad_clip_norm needs the norm of the reduced gradient before Adam: use allreduce='nccl'")
+            allreduce = "nccl"
         if world > 1 and allreduce in ("auto", "p2p") and self.device.type == "cuda":
             try:
                 self.peer = PeerGrads(2 * n, self.device, process_group)
@@ -100,16 +109,18 @@ class VanillaTrainer:
                     raise
                 import warnings
                 warnings.warn(f"symmetric-memory gradient buffers unavailable ({exc!r}); using the NCCL all-reduce")
-        self.epoch = 0
+        # the exchange epoch of a step IS its Adam step count t (one counter on every path: step(), step_graph(), resume)
         if self.peer is not None:
             self.grads_all = self.peer.buffer(1)
         else:
             self.grads_all = torch.zeros(2 * n, device=self.device, dtype=torch.float32)   # one buffer -> one all-reduce
         self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self.m_c, self.v_c, self.m_f, self.v_f = z(), z(), z(), z()
-        self.scalars = torch.zeros(4, device=self.device, dtype=torch.float32)
+        self._scal8 = torch.zeros(8, device=self.device, dtype=torch.float32)     # [loss, psnr, mse_c, mse_f, |g|^2, spare x3]
+        self.scalars = self._scal8[:4]
         self._ws = None
         self._graphs = None
+        self._graph_key = None
         self.nerf_c.packed(); self.nerf_f.packed()
 
     def current_lr(self, sched_steps=None) -> float:
@@ -132,10 +143,12 @@ class VanillaTrainer:
         need = _lib.lib().nsb_train_workspace_bytes(B, self.nc, self.nf, self.mode)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._graphs = None                    # captured graphs hold the old workspace address: recapture on next use
         return self._ws, need
 
-    def _fwd_bwd(self, batch, draws=None, grad_scale=1.0):
-        """nsb_train_fwd_bwd: fills self.grads_c/grads_f and self.scalars; returns (scalars, comp_c, comp_f)."""
+    def _fwd_bwd(self, batch, draws=None, grad_scale=1.0, grads=None):
+        """nsb_train_fwd_bwd: fills `grads` (default: this step's self.grads_c/grads_f) and self.scalars; returns
+        (scalars, comp_c, comp_f)."""
         L = _lib.lib()
         o, d, rn, vd, tgt = (_lib.f32c(batch[k]) for k in BATCH_KEYS)
         B = o.shape[0]
@@ -143,9 +156,11 @@ class VanillaTrainer:
         comp_c = torch.empty((B, 3), device=self.device); comp_f = torch.empty((B, 3), device=self.device)
         draws = draws or {}
         g = lambda k: None if draws.get(k) is None else _lib.f32c(draws[k])
+        n = _lib.N_PARAMS
+        grads_c, grads_f = (self.grads_c, self.grads_f) if grads is None else (grads[:n], grads[n:])
         _lib.check(L.nsb_train_fwd_bwd(
             _lib.ptr(o), _lib.ptr(d), _lib.ptr(rn.reshape(B)), _lib.ptr(vd), _lib.ptr(tgt),
-            _lib.ptr(self.nerf_c.packed()), _lib.ptr(self.nerf_f.packed()), _lib.ptr(self.grads_c), _lib.ptr(self.grads_f),
+            _lib.ptr(self.nerf_c.packed()), _lib.ptr(self.nerf_f.packed()), _lib.ptr(grads_c), _lib.ptr(grads_f),
             _lib.ptr(self.scalars), _lib.ptr(comp_c), _lib.ptr(comp_f), _lib.ptr(ws), wsb, B, self.nc, self.nf,
             self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode,
             float(grad_scale), self.seed, self.global_step, _lib.ptr(g("U")), _lib.ptr(g("u_fine")),
@@ -166,9 +181,9 @@ class VanillaTrainer:
         [loss, psnr, mse_c, mse_f] of this rank's shard (no host sync)."""
         L = _lib.lib()
         n = _lib.N_PARAMS
-        self.epoch += 1
+        epoch = self.adam_t + 1                               # exchange epoch == Adam's t of this step (same as step_graph)
         if self.peer is not None:                             # this step's gradient buffer (double-buffered by epoch parity)
-            self.grads_all = self.peer.buffer(self.epoch)
+            self.grads_all = self.peer.buffer(epoch)
             self.grads_c, self.grads_f = self.grads_all[:n], self.grads_all[n:]
         self._fwd_bwd(batch, draws, grad_scale=1.0)
         lr = self.current_lr()                                # sched.step() follows opt.step(): t-1 scheduler steps so far
@@ -179,16 +194,23 @@ class VanillaTrainer:
             pr = self.peer
             arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
             _lib.check(L.nsb_adam_allreduce_step(arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]), arr([self.m_c, self.m_f]),
-                                                 arr([self.v_c, self.v_f]), 2, pr.pointers(self.epoch), pr.multicast(self.epoch), pr.flag_array, pr.rank, pr.world,
-                                                 self.epoch, n, lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
-                                                 1.0 / pr.world, _lib.stream()), "nsb_adam_allreduce_step")
+                                                 arr([self.v_c, self.v_f]), 2, pr.pointers(epoch), pr.multicast(epoch), pr.flag_array, pr.rank, pr.world,
+                                                 epoch, n, lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
+                                                 1.0 / pr.world, _lib.ptr(self.scalars), _lib.stream()), "nsb_adam_allreduce_step")
             NeRF.repack((self.nerf_c, self.nerf_f))
             return self.scalars
         world = allreduce_grads(self.grads_all, self.pg)     # ONE sum-allreduce of 2 x 595,844 fp32 over NCCL/NVLink
+        guard = self.scalars
+        if world > 1:                                         # the skip decision must be common: any rank's bad loss skips all
+            guard = self.scalars[:1].clone()
+            torch.distributed.all_reduce(guard, op=torch.distributed.ReduceOp.SUM, group=self.pg)     # inf/nan propagate
+        if self.grad_clip_norm > 0:                           # clip_grad_norm_ over both nets (trainer.py:719-721)
+            _lib.check(L.nsb_grad_clip(_lib.ptr(self.grads_all), 2 * n, self.grad_clip_norm, 1.0 / world, _lib.ptr(self._scal8[4:]),
+                                       _lib.stream()), "nsb_grad_clip")
         for nerf, g, m, v in ((self.nerf_c, self.grads_c, self.m_c, self.v_c), (self.nerf_f, self.grads_f, self.m_f, self.v_f)):
             flat = nerf.flat_params()
             _lib.check(L.nsb_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.N_PARAMS, lr,
-                                       self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.stream()),
+                                       self.betas[0], self.betas[1], self.eps, self.adam_t, 1.0 / world, _lib.ptr(guard), _lib.stream()),
                        "nsb_adam_step")
         NeRF.repack((self.nerf_c, self.nerf_f))
         return self.scalars
@@ -211,9 +233,10 @@ class VanillaTrainer:
             _lib.ptr(st["rays_o_marching"]), _lib.ptr(st["rays_d_marching_unit"]), _lib.ptr(st["rays_d_marching_norm"].reshape(B)),
             _lib.ptr(st["rays_d_world_unit"]), _lib.ptr(st["rgb"]), arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]),
             arr([self.m_c, self.m_f]), arr([self.v_c, self.v_f]), arr([self.nerf_c.packed(), self.nerf_f.packed()]), _lib.ptr(grads),
-            _lib.ptr(self.scalars), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
+            _lib.ptr(self._scal8), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
             self.nf, self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode, self.seed,
-            self.lr, self.lr_eta_min, self.lr_T_max, self.betas[0], self.betas[1], self.eps, _lib.ptr(self._step_dev), pg, mc, pf, rank,
+            self.lr, self.lr_eta_min, self.lr_T_max, self.betas[0], self.betas[1], self.eps, self.grad_clip_norm,
+            _lib.ptr(self._step_dev), pg, mc, pf, rank,
             world, _lib.stream()),
             "nsb_train_step")
 
@@ -228,14 +251,20 @@ class VanillaTrainer:
         if self.adam_t != self.global_step:
             raise RuntimeError("step_graph derives Philox streams and Adam's t from one counter: adam_t must equal global_step")
         B = batch["rays_o_marching"].shape[0]
-        if self._graphs is None or self._static["rays_o_marching"].shape[0] != B:
+        # everything whose ADDRESS a captured graph bakes in: a re-flattened / moved parameter buffer, re-allocated packed
+        # weights or a grown workspace (see _workspace) force a recapture instead of a replay into freed memory
+        key = (B, self.nerf_c.flat_params().data_ptr(), self.nerf_f.flat_params().data_ptr(), self.nerf_c.packed().data_ptr(),
+               self.nerf_f.packed().data_ptr(), self.nc, self.nf)
+        if self._graphs is None or self._graph_key != key:
             self._static = {k: torch.empty(tuple(batch[k].shape), dtype=torch.float32, device=self.device) for k in BATCH_KEYS}
             self._static_comp = (torch.empty((B, 3), device=self.device), torch.empty((B, 3), device=self.device))
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
             for k in BATCH_KEYS:
                 self._static[k].copy_(batch[k])
-            self._fwd_bwd(self._static)                      # eager warm-up of every kernel on the path (no state change)
-            self.nerf_c.packed(); self.nerf_f.packed()
+            # eager warm-up of every kernel on the path, into a PRIVATE gradient buffer: the symmetric buffers may still be
+            # read by peers finishing the previous step (no state change, no cross-rank traffic)
+            self._fwd_bwd(self._static, grads=torch.empty(2 * _lib.N_PARAMS, device=self.device, dtype=torch.float32))
+            self._workspace(B)                               # (sized before capture: growing it later invalidates the graphs)
             torch.cuda.synchronize(self.device)
             self._graphs, self._graph_launches = [], 0
             for parity in ((0, 1) if self.peer is not None else (0,)):
@@ -245,24 +274,82 @@ class VanillaTrainer:
                     self._launch_train_step(parity)
                 self._graph_launches = _lib.launch_count() - before
                 self._graphs.append(g)
+            self._graph_key = key
             self._step_host = -1
         if self._step_host != self.adam_t:                   # (re)synchronise the device counter with the host's step count
             self._step_dev.fill_(self.adam_t)
             self._step_host = self.adam_t
         for k in BATCH_KEYS:
             self._static[k].copy_(batch[k], non_blocking=True)
-        self.epoch += 1; self.adam_t += 1; self.global_step += 1; self._step_host += 1
+        self.adam_t += 1; self.global_step += 1; self._step_host += 1
         self._graphs[self.adam_t & 1 if self.peer is not None else 0].replay()
         return self.scalars
 
-    def state_dict(self):                                      # trainer.py:596-621 (hot-path subset)
-        return {"step": self.global_step, "nerf_c": self.nerf_c.state_dict(), "nerf_f": self.nerf_f.state_dict(),
-                "opt": {"t": self.adam_t, "m_c": self.m_c, "v_c": self.v_c, "m_f": self.m_f, "v_f": self.v_f}}
+    def check_peers(self):
+        """Raise if a peer-memory gradient exchange timed out (nsb_peer_status; synchronises the device).  Call it wherever
+        the step's scalars are read on the host."""
+        if self.peer is None:
+            return
+        code = C.c_int(0)
+        _lib.check(_lib.lib().nsb_peer_status(C.byref(code)), "nsb_peer_status")
+        if code.value:
+            raise RuntimeError(f"rank {self.peer.rank}: gradient exchange timed out waiting for rank {code.value - 1} "
+                               f"(NSB_PEER_TIMEOUT_S); the update of that step was skipped -- replicas may have diverged")
+
+    # ---- checkpoint: the reference's format (trainer.py:596-645) ----------------------------------------------
+    def _adam_param_group(self):
+        g = torch.optim.Adam([torch.zeros(1)], lr=self.lr, betas=tuple(self.betas), eps=self.eps).state_dict()["param_groups"][0]
+        g = dict(g); g["lr"] = self.current_lr(); g["initial_lr"] = self.lr; g["params"] = list(range(48))
+        return g
+
+    def state_dict(self):
+        """{step, nerf_c, nerf_f, opt, sched} as Trainer.save_checkpoint writes them: ``opt`` is a torch.optim.Adam
+        state_dict over list(nerf_c.parameters()) + list(nerf_f.parameters()) (trainer.py:383-386), so checkpoints move
+        between the reference trainer and this one in both directions.  Tensors are copies, not live views."""
+        state = {}
+        if self.adam_t > 0:
+            ms = self.nerf_c.unflatten(self.m_c) + self.nerf_f.unflatten(self.m_f)
+            vs = self.nerf_c.unflatten(self.v_c) + self.nerf_f.unflatten(self.v_f)
+            for i, (m, v) in enumerate(zip(ms, vs)):
+                state[i] = {"step": torch.tensor(float(self.adam_t)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        sched = None
+        if self.lr_T_max > 0:
+            sched = {"T_max": self.lr_T_max, "eta_min": self.lr_eta_min, "base_lrs": [self.lr], "last_epoch": self.adam_t,
+                     "_step_count": self.adam_t + 1, "_last_lr": [self.current_lr()]}
+        clone = lambda sd: {k: v.detach().clone() for k, v in sd.items()}
+        return {"step": self.global_step, "nerf_c": clone(self.nerf_c.state_dict()), "nerf_f": clone(self.nerf_f.state_dict()),
+                "opt": {"state": state, "param_groups": [self._adam_param_group()]}, "scaler": None, "sched": sched}
 
     def load_state_dict(self, sd):
-        self.global_step = int(sd["step"])
+        """Accepts what state_dict() writes, a reference checkpoint (torch Adam ``opt``, possibly None) and this package's
+        round-1 format ({"t", "m_c", ...})."""
+        self.global_step = int(sd.get("step", 0))
         self.nerf_c.load_state_dict(sd["nerf_c"]); self.nerf_f.load_state_dict(sd["nerf_f"])
-        self.adam_t = int(sd["opt"]["t"])
-        for k in ("m_c", "v_c", "m_f", "v_f"):
-            getattr(self, k).copy_(sd["opt"][k])
+        opt = sd.get("opt")
+        for buf in (self.m_c, self.v_c, self.m_f, self.v_f):
+            buf.zero_()
+        if opt is None:
+            self.adam_t = 0
+        elif "state" in opt:                                   # torch.optim.Adam.state_dict()
+            st = opt["state"]
+            self.adam_t = int(float(st[0]["step"])) if len(st) else 0
+            if len(st) not in (0, 48):
+                raise ValueError(f"optimizer state holds {len(st)} parameters, expected 48 (coarse + fine NeRF)")
+            ms = self.nerf_c.unflatten(self.m_c) + self.nerf_f.unflatten(self.m_f)
+            vs = self.nerf_c.unflatten(self.v_c) + self.nerf_f.unflatten(self.v_f)
+            for i in range(len(st)):
+                ms[i].copy_(st[i]["exp_avg"]); vs[i].copy_(st[i]["exp_avg_sq"])
+        else:                                                  # round-1 format
+            self.adam_t = int(opt["t"])
+            for k in ("m_c", "v_c", "m_f", "v_f"):
+                getattr(self, k).copy_(opt[k])
+        if self.peer is not None:
+            # the flag blocks may hold epochs beyond the restored step count: zero them between two barriers so no rank
+            # sees a stale "peer has arrived" for an epoch that has not happened yet
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.pg)
+            self.peer.flags.zero_()
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.pg)
+        self._step_host = -1                                   # step_graph re-synchronises the device counter
         self.nerf_c.packed(force=True); self.nerf_f.packed(force=True)

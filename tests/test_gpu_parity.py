@@ -437,9 +437,11 @@ def test_frame_outputs_match_reference_image_path():
     assert np.array_equal(out["rgb"].cpu().numpy(), u8(rgb))
     assert np.array_equal(out["opacity"].cpu().numpy(), u8(acc.squeeze(-1)))
     dn = ((depth.squeeze(-1) - 2.0) / (6.0 - 2.0 + 1e-8)).clamp(0, 1)
-    d8 = out["depth"].cpu().numpy().astype(np.int32)
-    assert np.abs(d8 - u8(dn).astype(np.int32)).max() <= 1          # (depth-near)*inv_range vs a division: last-bit ties
-    assert (d8 != u8(dn)).mean() < 0.01
+    assert np.array_equal(out["depth"].cpu().numpy(), u8(dn))            # byte-exact: the kernel divides like the reference
+    for near, far in ((0.1, 7.3), (1.2345, 3.21)):                       # near/far that are not fp32-representable doubles
+        o2 = nsb.frame_outputs({"rgb": rgb, "acc": acc, "depth": depth}, near=near, far=far)
+        dn2 = ((depth.squeeze(-1) - near) / (far - near + 1e-8)).clamp(0, 1)
+        assert np.array_equal(o2["depth"].cpu().numpy(), u8(dn2))
     pred, gtc = rgb.clamp(0, 1), gt.clamp(0, 1)
     mse = (((pred - gtc) ** 2) * mask).sum() / (mask.sum() * 3).clamp_min(1e-8)
     psnr = -10.0 * torch.log10(mse.clamp_min(1e-10))
