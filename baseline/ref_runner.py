@@ -1,0 +1,107 @@
+"""The reference's OWN implementation of the path, run unmodified on the host cores.
+
+`pip install --target baseline/_ref /root/reference` is refused by the reference's setup.py (:31-42 raises for any
+Python other than 3.8 / 3.10; this image has 3.12), so ``vendor()`` does what that install would have done for a
+pure-Python package: it copies the package tree ``nerf_sandbox/`` as it is into ``baseline/_ref/`` (git-ignored, not
+gpurun-ignored -- it travels to the GPU box with the snapshot; the sources never enter the history).  Nothing here
+is on the product path: ``bench.py --impl reference`` / the ``cpu_baseline`` leg time it, and the GPU drop-in tests
+(tests/test_gpu_dropin.py) drive the reference's own ``Trainer._train_step`` through ``install()`` with it.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+SRC = "/root/reference/nerf_sandbox"
+
+
+def vendor(verbose: bool = False) -> bool:
+    """Copy /root/reference/nerf_sandbox -> baseline/_ref/nerf_sandbox (build container only).  True if _ref exists."""
+    dst = os.path.join(REF_DIR, "nerf_sandbox")
+    if os.path.isdir(SRC):
+        if os.path.isdir(dst):
+            shutil.rmtree(dst)
+        os.makedirs(REF_DIR, exist_ok=True)
+        shutil.copytree(SRC, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+        if verbose:
+            print(f"vendored {SRC} -> {dst}")
+    return os.path.isdir(dst)
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "nerf_sandbox", "source", "train", "trainer.py"))
+
+
+def imageio_shim() -> None:
+    """utils/render_utils.py:20 imports imageio at module scope; it is not installed here (PNG/MP4 export only)."""
+    if "imageio" in sys.modules:
+        return
+    try:
+        __import__("imageio")
+    except ImportError:
+        m = types.ModuleType("imageio"); m.v2 = types.ModuleType("imageio.v2")
+
+        def _missing(*a, **k):
+            raise RuntimeError("imageio is not installed: image/video export is unavailable")
+        m.imread = m.imwrite = m.mimwrite = m.v2.imread = m.v2.imwrite = _missing
+        sys.modules["imageio"], sys.modules["imageio.v2"] = m, m.v2
+
+
+def import_reference():
+    """Put baseline/_ref on sys.path and return the reference's (trainer, render_utils) modules."""
+    if not available():
+        raise RuntimeError("baseline/_ref is missing: run __graft_entry__.build() in the build container")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    imageio_shim()
+    from nerf_sandbox.source.train import trainer as TR
+    from nerf_sandbox.source.utils import render_utils as RU
+    return TR, RU
+
+
+def make_namespace(TR, device, nerf_c, nerf_f, pos_enc, dir_enc, *, nc=64, nf=128, near=2.0, far=6.0, use_ndc=False,
+                   amp=False, global_step=1):
+    """The attributes Trainer._train_step reads from ``self`` (train/trainer.py:876-1013), with the values the vanilla
+    profile gives them (trainer.py:277-291, :411-416; train_nerf.py:275, 281)."""
+    from types import SimpleNamespace
+    return SimpleNamespace(use_ndc=use_ndc, global_step=global_step, device=device, amp=amp, nc=nc, nf=nf, det_fine=False,
+                           samp_near=near, samp_far=far, pos_enc=pos_enc, dir_enc=dir_enc, nerf_c=nerf_c, nerf_f=nerf_f,
+                           white_bkgd=True, sigma_activation="relu", raw_noise_std=1.0, train_mlp_chunk=0,
+                           infinite_last_bin=True)
+
+
+def make_cpu_step(batch_fn, *, nc=64, nf=128, threads=None, seed=0):
+    """Returns (step, info): ``step()`` runs one full optimisation step of the reference on the CPU in fp32 --
+    Trainer._train_step (unbound, on a namespace) + loss.backward() + torch.optim.Adam.step(), i.e. the loop body
+    train/trainer.py:702-725 with amp off (what the reference does on a CPU device, trainer.py:396-397) -- on the batch
+    ``batch_fn(step_index)`` returns (dict of numpy arrays with the trainer's batch keys)."""
+    import torch
+    TR, _ = import_reference()
+    from nerf_sandbox.source.models.encoders import get_vanilla_nerf_encoders
+    from nerf_sandbox.source.models.mlps import NeRF
+    threads = int(threads or os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    pos_enc, dir_enc = get_vanilla_nerf_encoders()
+    nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu")          # trainer.py:326-341
+    nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu")
+    with torch.no_grad():                      # random-init density is degenerate: same bias as our arm
+        nerf_c.sigma_out.bias.fill_(0.3); nerf_f.sigma_out.bias.fill_(0.3)
+    opt = torch.optim.Adam(list(nerf_c.parameters()) + list(nerf_f.parameters()), lr=5e-4)      # trainer.py:383-386
+    ns = make_namespace(TR, torch.device("cpu"), nerf_c, nerf_f, pos_enc, dir_enc, nc=nc, nf=nf)
+    state = {"i": 0}
+
+    def step():
+        b = {k: torch.from_numpy(v) for k, v in batch_fn(state["i"]).items()}
+        state["i"] += 1
+        ns.global_step = state["i"] if state["i"] % 500 else state["i"] + 1     # skip the every-500-steps diagnostics
+        opt.zero_grad(set_to_none=True)
+        out = TR.Trainer._train_step(ns, b)
+        out["loss"].backward()
+        opt.step()
+        return float(out["loss"].detach())
+    return step, {"threads": torch.get_num_threads(), "torch": torch.__version__}

@@ -102,11 +102,29 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """Threads the CPU arm uses: every host core, set explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_step_fn(rays_per_step):
-    """The reference's CPU implementation of the step, as restated by the oracle (numpy, all host threads
-    through the BLAS pool).  Returns a callable running one full step (fwd+bwd+Adam) on `rays_per_step` rays."""
-    from oracle import nerf_oracle as O
+    """One full optimisation step (fwd+bwd+Adam) of the path on the host cores, on `rays_per_step` rays of the bench
+    workload.  Preferred: the reference's OWN code from baseline/_ref (unbound Trainer._train_step + backward + torch Adam,
+    fp32, amp off as the reference runs on a CPU device) -> kind "reference".  Only when baseline/_ref is absent: the numpy
+    oracle port -> kind "port".  Returns (step callable, kind, threads actually used, description)."""
+    threads = host_threads()
     rng = np.random.default_rng(0)
+    from baseline import ref_runner
+    if ref_runner.available():
+        step, info = ref_runner.make_cpu_step(lambda i: blender_rays(rng, rays_per_step, i), nc=NC, nf=NF, threads=threads)
+        return step, "reference", info["threads"], (f"reference Trainer._train_step + backward + torch.optim.Adam (baseline/_ref, unmodified), "
+                                                    f"torch {info['torch']} CPU fp32, torch threads={info['threads']}")
+    from threadpoolctl import threadpool_limits
+    from oracle import nerf_oracle as O
+    threadpool_limits(limits=threads)
     st = dict(pc=O.init_params(rng, 0.3), pf=O.init_params(rng, 0.3), t=0)
     st["Pc"], st["Pf"] = O.flatten_params(st["pc"]), O.flatten_params(st["pf"])
     st["m"] = [np.zeros_like(st["Pc"]) for _ in range(4)]
@@ -122,31 +140,34 @@ def cpu_reference_step_fn(rays_per_step):
         st["Pf"], st["m"][2], st["m"][3] = O.adam_step(st["Pf"], O.flatten_params(out["grads_f"]), st["m"][2], st["m"][3], st["t"])
         st["pc"], st["pf"] = O.unflatten_params(st["Pc"]), O.unflatten_params(st["Pf"])
         return float(out["loss"])
-    return step
+    return step, "port", threads, f"numpy fp32 oracle port (baseline/_ref absent), BLAS threads={threads}"
+
+
+WORKLOAD = ("vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step/GPU, 64 coarse + 128 fine, "
+            "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])")
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step on the host cores -- always the bench workload
+    (1024 rays/step), every host thread, rank 0 only (the CPU arm does not depend on the number of GPUs)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    rays = RAYS if (args.steps + args.warmup) <= 24 else 256
-    step = cpu_reference_step_fn(rays)
+    step, kind, threads, what = cpu_reference_step_fn(RAYS)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    v = rays * args.steps / dt
-    sample = f"{args.steps} full steps (fwd+bwd+Adam) of {rays} rays x (64+192) samples, numpy fp32, BLAS threads={cores}"
+    v = RAYS * args.steps / dt
+    sample = f"{args.steps} full steps (fwd+bwd+Adam) of {RAYS} rays x (64+192) samples after {args.warmup} warm-up: {what}"
     print(json.dumps({
         "impl": "reference", "metric": "train_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step, 64 coarse + 128 fine, "
-                               "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])", "rays_per_step": rays},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": RAYS, "host_threads": threads},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -325,14 +346,14 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ---------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        stepf = cpu_reference_step_fn(RAYS)
+        stepf, kind, threads, what = cpu_reference_step_fn(RAYS)
         stepf()
         t0 = time.perf_counter(); n = 0
-        while n < 2:
+        while n < 4:
             stepf(); n += 1
         dt = time.perf_counter() - t0
-        cpu = {"value": RAYS * n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{n} full steps (fwd+bwd+Adam) of {RAYS} rays after 1 warm-up, numpy fp32 oracle, BLAS threads={os.cpu_count()}"}
+        cpu = {"value": RAYS * n / dt, "unit": "rays/s", "cores": threads, "kind": kind,
+               "sample": f"{n} full steps (fwd+bwd+Adam) of {RAYS} rays x (64+192) samples after 1 warm-up: {what}"}
 
     if rank == 0:
         ws_gb = L.nsb_train_workspace_bytes(RAYS, NC, NF, tr.mode) / 1e9
@@ -340,8 +361,7 @@ def main():
             "metric": "train_rays_per_s", "value": world * RAYS * K / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": K,
             "warmup": W_, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "vanilla NeRF Blender-shape training 800x800 white bkgd precrop, 1024 rays/step/GPU, 64 coarse + 128 fine, "
-                                   "8x256 MLP x2 fwd+bwd+Adam, random-init (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "rays_per_step_per_gpu": RAYS, "parallelism": f"ray-sharded dp{world}, {exchange} of 2x595,844 fp32 grads",
                        "mode": args.mode, "step": "one CUDA-graph replay (nsb_train_step)" if use_graph else "eager launches",
                        "l2": f"no flush: per-step working set {ws_gb:.2f} GB exceeds the 126 MB L2"},

@@ -34,8 +34,9 @@ _BINDINGS = {
 
 
 def _imageio_shim():
-    """render_utils.py:20 imports imageio at module scope; provide a stub when it is not installed
-    (PNG/MP4 export is outside the hot path)."""
+    """render_utils.py:20 and the loaders import imageio at module scope; when it is not installed provide a stand-in:
+    PNG read/write through PIL when that is present (enough for the Blender loader and the validation PNGs), video export
+    unavailable.  Image IO is outside the hot path."""
     if "imageio" in sys.modules:
         return
     try:
@@ -45,12 +46,32 @@ def _imageio_shim():
 
         def _missing(*a, **k):
             raise RuntimeError("imageio is not installed: image/video export is unavailable")
-        m.imread = m.imwrite = m.mimwrite = m.v2.imread = m.v2.imwrite = _missing
+        imread = imwrite = _missing
+        try:
+            import numpy as np
+            from PIL import Image
+
+            def imread(path, *a, **k):
+                return np.array(Image.open(path))
+
+            def imwrite(path, arr, *a, **k):
+                Image.fromarray(np.asarray(arr)).save(str(path))
+        except ImportError:
+            pass
+        m.imread = m.v2.imread = imread
+        m.imwrite = m.v2.imwrite = imwrite
+        m.mimwrite = m.v2.mimwrite = m.get_writer = m.v2.get_writer = _missing
         sys.modules["imageio"], sys.modules["imageio.v2"] = m, m.v2
 
 
-def install(verbose: bool = False) -> dict:
-    """Rebind the reference's names; returns {module: [names rebound]}.  The reference package must be importable."""
+def install(verbose: bool = False, mode: str | None = None) -> dict:
+    """Rebind the reference's names; returns {module: [names rebound]}.  The reference package must be importable.
+
+    ``mode`` ("bf16" = tcgen05 tensor cores, "fp32" = FFMA parity kernels; default: NSB_MODE, else "fp32") becomes the
+    arithmetic mode of every ``NeRF`` the reference builds afterwards -- its Trainer passes no mode (train/trainer.py:326-341),
+    so this is how ``train_nerf.py --vanilla`` reaches the tensor-core path."""
+    if mode is not None:
+        mlps.set_default_mode(mode)
     _imageio_shim()
     done = {}
     for modname, names in _BINDINGS.items():

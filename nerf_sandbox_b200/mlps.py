@@ -29,6 +29,27 @@ def log_nerf_arch(nerf, pos_enc=None, dir_enc=None, logger=print, name="NeRF"):
             logger(f"[{name}] {attr}: {head.in_features} → {head.out_features}")
 
 
+# Arithmetic mode of NeRF modules built without an explicit ``mode=`` -- which is how the reference's Trainer builds them
+# (train/trainer.py:326-341 passes no such argument).  install(mode=...) / set_default_mode() / NSB_MODE select it:
+# "bf16" = tcgen05 tensor-core kernels, "fp32" = FFMA parity kernels.
+import os as _os
+_DEFAULT_MODE = _os.environ.get("NSB_MODE", "fp32").lower()
+
+
+def set_default_mode(mode: str) -> str:
+    """Mode used by ``NeRF(...)`` when the caller passes none; returns the previous default."""
+    global _DEFAULT_MODE
+    mode = str(mode).lower()
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(f"mode must be 'fp32' or 'bf16', got {mode!r}")
+    prev, _DEFAULT_MODE = _DEFAULT_MODE, mode
+    return prev
+
+
+def get_default_mode() -> str:
+    return _DEFAULT_MODE
+
+
 class _Workspace:
     """Grow-only device scratch owned by PyTorch (the library never allocates)."""
 
@@ -70,11 +91,12 @@ class _FieldEncFn(torch.autograd.Function):
 
 class NeRF(nn.Module):
     """8x256 trunk with the skip concat at the input of layer ``skip_pos``, raw [r,g,b,sigma] output
-    (models/mlps.py:41-134, :192-278).  ``mode``: "fp32" (FFMA, parity) or "bf16" (tcgen05)."""
+    (models/mlps.py:41-134, :192-278).  ``mode``: "fp32" (FFMA, parity) or "bf16" (tcgen05); None = the package default
+    (set_default_mode / install(mode=...) / NSB_MODE), so the reference's own constructor call selects it."""
 
     def __init__(self, enc_pos_dim: int, enc_dir_dim: int, n_layers: int = 8, hidden_dim: int = 256, skip_pos: int = 4,
                  near: float = 2.0, far: float = 6.0, initial_acc_opacity: float | None = None,
-                 sigma_activation: str = "softplus", mode: str = "fp32") -> None:
+                 sigma_activation: str = "softplus", mode: str | None = None) -> None:
         super().__init__()
         self.enc_pos_dim, self.enc_dir_dim = enc_pos_dim, enc_dir_dim
         self.n_layers, self.hidden_dim, self.skip_pos = n_layers, hidden_dim, skip_pos
@@ -99,6 +121,10 @@ class NeRF(nn.Module):
             nn.init.kaiming_uniform_(m.weight, nonlinearity="relu"); nn.init.zeros_(m.bias)
         nn.init.kaiming_uniform_(self.feature.weight, nonlinearity="linear"); nn.init.zeros_(self.feature.bias)
         nn.init.kaiming_uniform_(self.color_fc.weight, nonlinearity="relu"); nn.init.zeros_(self.color_fc.bias)
+        if mode is None:
+            mode = _DEFAULT_MODE
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(f"mode must be 'fp32' or 'bf16', got {mode!r}")
         self.mode = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}[mode]
         self._vanilla = (enc_pos_dim, enc_dir_dim, n_layers, hidden_dim, skip_pos) == (63, 27, 8, 256, 4)
         self._flat = None

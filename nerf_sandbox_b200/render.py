@@ -11,7 +11,7 @@ from typing import Tuple
 import torch
 import torch.nn.functional as F
 
-from . import _lib
+from . import _hooks, _lib
 from .encoders import PositionalEncoder
 from .mlps import NeRF
 from .sampling import sample_pdf  # noqa: F401  (re-exported like render_utils.py:24)
@@ -142,6 +142,8 @@ def nerf_forward_pass(rays_o: torch.Tensor, rays_d_unit: torch.Tensor, z_vals: t
         rn = None if ray_norms is None else _lib.f32c(ray_norms).reshape(B)
         vd = None if viewdirs_world_unit is None else _lib.f32c(viewdirs_world_unit)
         use_noise = training and raw_noise_std > 0.0
+        if use_noise and raw_noise is None and _hooks.normal is not None:
+            raw_noise = _hooks.normal(B * N, z.device)
         noise = _lib.f32c(raw_noise).reshape(-1) if (use_noise and raw_noise is not None) else None
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (use_noise and noise is None) else 0

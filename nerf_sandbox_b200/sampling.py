@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _hooks, _lib
 
 
 @torch.no_grad()
@@ -23,6 +23,8 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, *, det
     b, w = _lib.f32c(bins), _lib.f32c(weights)
     out = torch.empty((B, n_samples), device=b.device, dtype=torch.float32)
     inds = torch.empty((B, n_samples), device=b.device, dtype=torch.int64) if return_inds else None
+    if u is None and not deterministic and _hooks.uniform is not None:
+        u = _hooks.uniform(B, int(n_samples), b.device)
     uu = None if (u is None or deterministic) else _lib.f32c(u)
     cc = None if cdf is None else _lib.f32c(cdf)
     if uu is not None and tuple(uu.shape) != (B, n_samples):

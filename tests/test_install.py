@@ -4,16 +4,20 @@ import sys
 
 import pytest
 
-REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")          # the unmodified reference package, vendored by __graft_entry__.build()
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "nerf_sandbox")), reason="baseline/_ref not vendored")
 def test_install_rebinds_reference_names():
     sys.path.insert(0, REF)
     try:
         import nerf_sandbox_b200 as nsb
         from nerf_sandbox_b200.install import install
-        done = install()
+        done = install(mode="bf16")
+        from nerf_sandbox_b200 import mlps
+        assert mlps.get_default_mode() == "bf16"
+        mlps.set_default_mode("fp32")
         import nerf_sandbox.source.train.trainer as T
         import nerf_sandbox.source.utils.render_utils as RU
         import nerf_sandbox.source.utils.validation_renderer as VR
