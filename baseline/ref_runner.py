@@ -81,6 +81,9 @@ def make_cpu_step(batch_fn, *, nc=64, nf=128, threads=None, seed=0):
     ``batch_fn(step_index)`` returns (dict of numpy arrays with the trainer's batch keys)."""
     import torch
     TR, _ = import_reference()
+    inst = sys.modules.get("nerf_sandbox_b200.install")
+    if inst is not None:
+        inst.uninstall()                       # this arm times the reference's OWN callables, never the rebound ones
     from nerf_sandbox.source.models.encoders import get_vanilla_nerf_encoders
     from nerf_sandbox.source.models.mlps import NeRF
     threads = int(threads or os.cpu_count() or 1)

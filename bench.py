@@ -60,6 +60,72 @@ def frame_rays(rng):
     return f32(np.broadcast_to(c, d.shape)), f32(d / nrm), f32(nrm[:, 0])
 
 
+def llff_ndc_rays(rng, n):
+    """BASELINE configs[3] batch: LLFF fern shape (504x378 = 4032x3024 / 8, f = 3260 / 8), forward-facing NDC marching rays
+    (utils/ray_utils.py:92-126: o, d warped to the near plane, z in [0,1], ray_norms = |d_ndc|), world-space view directions."""
+    Hh, Ww, f = 378, 504, 407.6
+    px = np.stack([rng.integers(0, Ww, n), rng.integers(0, Hh, n)], -1).astype(np.float64) + 0.5
+    d = np.stack([(px[:, 0] - Ww / 2) / f, -(px[:, 1] - Hh / 2) / f, -np.ones(n)], -1)        # OpenGL camera, c2w ~ identity + shift
+    o = np.broadcast_to(np.array([0.05, -0.03, 0.02]), d.shape)
+    near = 1.0
+    t = -(near + o[:, 2]) / d[:, 2]
+    o = o + t[:, None] * d
+    o0 = -f / (Ww / 2) * o[:, 0] / o[:, 2]; o1 = -f / (Hh / 2) * o[:, 1] / o[:, 2]; o2 = 1.0 + 2.0 * near / o[:, 2]
+    d0 = -f / (Ww / 2) * (d[:, 0] / d[:, 2] - o[:, 0] / o[:, 2]); d1 = -f / (Hh / 2) * (d[:, 1] / d[:, 2] - o[:, 1] / o[:, 2])
+    d2 = -2.0 * near / o[:, 2]
+    on, dn = np.stack([o0, o1, o2], -1), np.stack([d0, d1, d2], -1)
+    nrm = np.linalg.norm(dn, axis=-1, keepdims=True)
+    dw = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(rays_o_marching=f32(on), rays_d_marching_unit=f32(dn / nrm), rays_d_marching_norm=f32(nrm), rays_d_world_unit=f32(dw),
+                rgb=f32(rng.uniform(0, 1, (n, 3))))
+
+
+def dropin_rays_per_s(mode, dev, batches, steps=20):
+    """rays/s of the loop body train/trainer.py:702-725 executed by the REFERENCE'S code (baseline/_ref) on this package's
+    kernels: install(mode) rebinds its by-name imports, then its unbound Trainer._train_step, autograd backward and
+    torch.optim.Adam run unmodified (amp off: the arithmetic mode is the kernels')."""
+    import torch
+    from baseline import ref_runner
+    from nerf_sandbox_b200.install import install, uninstall
+    TR, _ = ref_runner.import_reference()
+    install(mode=mode)
+    try:
+        return _dropin_timed(TR, ref_runner, mode, dev, batches, steps)
+    finally:
+        uninstall()                                   # the CPU baseline leg below times the reference's OWN callables
+
+
+def _dropin_timed(TR, ref_runner, mode, dev, batches, steps):
+    import torch
+    with torch.random.fork_rng(devices=[dev]):
+        torch.manual_seed(0)
+        pos_enc, dir_enc = TR.get_vanilla_nerf_encoders()
+        nc_, nf_ = TR.NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu").to(dev), TR.NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu").to(dev)
+    with torch.no_grad():
+        nc_.sigma_out.bias.fill_(0.3); nf_.sigma_out.bias.fill_(0.3)
+    opt = torch.optim.Adam(list(nc_.parameters()) + list(nf_.parameters()), lr=5e-4)
+    ns = ref_runner.make_namespace(TR, dev, nc_, nf_, pos_enc.to(dev), dir_enc.to(dev), nc=NC, nf=NF)
+
+    def step(b):
+        opt.zero_grad(set_to_none=True)
+        out = TR.Trainer._train_step(ns, b)
+        out["loss"].backward()
+        opt.step()
+        return out["loss"]
+    for i in range(3):
+        step(batches[i % len(batches)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(batches[i % len(batches)])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"path": "reference Trainer._train_step + loss.backward() + torch.optim.Adam after nerf_sandbox_b200.install(mode)", "mode": mode,
+            "ms_per_step": ms, "train_rays_per_s": RAYS / (ms * 1e-3), "steps": steps, "loss_after": float(loss.detach())}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -181,6 +247,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("NSB_BENCH_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph (N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -245,6 +313,16 @@ def main():
     else:
         launches = _lib.launch_count() - l0 + (K if world > 1 and tr.peer is None else 0)      # + one NCCL all-reduce kernel per step
     loss_dev = float(tr.scalars[0])
+    # spread: four more blocks of K steps, same bracketing (the line's value stays the first block)
+    repeats = [ms_total / K]
+    for _ in range(4):
+        barrier()
+        e0.record()
+        for i in range(K):
+            do_step(devb[i % pool_n])
+        e1.record()
+        barrier()
+        repeats.append(max_over_ranks(e0.elapsed_time(e1)) / K)
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------------------
     # one pinned host buffer per batch, [o | d | norm | viewdir | rgb] field-major, so a step is ONE H2D copy
@@ -325,23 +403,63 @@ def main():
         roofline["hbm"] = {"achieved": traffic / (ms_field * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                            "frac": traffic / (ms_field * 1e-3) / 1e9 / hbm_peak}
 
-    # ---- secondary metric: 800x800 eval frame (configs[2]) -----------------------------------------------
-    extra = {}
-    if not args.no_frame and rank == 0:
+    # ---- secondary metric: 800x800 eval frame (configs[2]), pixel rows split over the N ranks + one all-gather ----------
+    extra = {"repeat_ms_per_step": [round(x, 5) for x in repeats]}
+    if not args.no_frame:
+        from nerf_sandbox_b200.dist import render_image_sharded
         o, d, rn = (torch.from_numpy(a).to(dev) for a in frame_rays(rng))
         chunk = 65536
-        nrays = H * W if args.mode == "bf16" else 2 * chunk            # fp32 mode: bounded sample, extrapolated
-        pe, de = tr.pos_enc, tr.dir_enc
+        full = args.mode == "bf16"
+        Hf = H if full else 164                                              # fp32 mode: a bounded band of rows, extrapolated
+        nrays = Hf * W
+        tim = {}
         def frame():
-            for s in range(0, nrays, chunk):
-                e = min(nrays, s + chunk)
-                nsb.render_rays(o[s:e], d[s:e], rn[s:e], d[s:e], tr.nerf_c, tr.nerf_f, near=2.0, far=6.0, nc=NC, nf=NF, white_bkgd=True)
-        frame(); torch.cuda.synchronize()
-        e0.record(); frame(); e1.record(); torch.cuda.synchronize()
-        ms_frame = e0.elapsed_time(e1) * (H * W / nrays)
-        extra = {"render_800x800_frames_per_s": 1e3 / ms_frame, "render_ms_per_frame": ms_frame, "render_rays_timed": nrays,
-                 "render_eval_chunk": chunk,
-                 "render_mlp_tflops": H * W * POINTS_PER_RAY * FLOP_FWD_PER_POINT / (ms_frame * 1e-3) / 1e12}
+            return render_image_sharded(o[:nrays], d[:nrays], rn[:nrays], Hf, W, 2.0, 6.0, tr.nerf_c, tr.nerf_f, NC, NF, True, eval_chunk=chunk,
+                                        viewdirs_world_unit=d[:nrays], timings=tim)
+        frame(); barrier()
+        e0.record(); img = frame(); e1.record(); barrier()
+        ms_frame = max_over_ranks(e0.elapsed_time(e1)) * (H * W / nrays)
+        ms_comp = max_over_ranks(tim["compute"][0].elapsed_time(tim["compute"][1])) * (H * W / nrays)
+        ms_gather = max_over_ranks(tim["gather"][0].elapsed_time(tim["gather"][1]))
+        extra.update({"render_800x800_frames_per_s": 1e3 / ms_frame, "render_ms_per_frame": ms_frame, "render_rays_timed": nrays,
+                      "render_eval_chunk": chunk, "render_n_gpus": world, "render_ms_compute_max_rank": ms_comp,
+                      "render_ms_allgather": ms_gather if world > 1 else 0.0,
+                      "render_mlp_tflops": H * W * POINTS_PER_RAY * FLOP_FWD_PER_POINT / (ms_frame * 1e-3) / 1e12,
+                      "render_checksum": float(img["rgb"].double().mean())})
+        del o, d, rn, img
+
+    # ---- BASELINE configs[3]: LLFF fern-shape NDC training, ray-sharded 8,192 rays/GPU, same exchange as the headline ------
+    if not args.no_cfg4 and args.mode == "bf16":
+        B4 = 8192
+        rng4 = np.random.default_rng(2000 + rank)
+        tr4 = nsb.VanillaTrainer(dev, rays_per_batch=B4, nc=NC, nf=NF, near=0.0, far=1.0, mode=args.mode, seed=0, sigma_bias=2.0,
+                                 allreduce=os.environ.get("NSB_ALLREDUCE", "auto"))
+        pool4 = [{k: torch.from_numpy(v).to(dev) for k, v in llff_ndc_rays(rng4, B4).items()} for _ in range(4)]
+        step4 = tr4.step_graph if use_graph else tr4.step
+        for i in range(3):
+            step4(pool4[i % 4])
+        barrier()
+        K4 = 10
+        e0.record()
+        for i in range(K4):
+            step4(pool4[i % 4])
+        e1.record()
+        barrier()
+        ms4 = max_over_ranks(e0.elapsed_time(e1)) / K4
+        extra["cfg4"] = {"workload": "LLFF fern-shape NDC (504x378, f=407.6, z in [0,1]) training, 8192 rays/step/GPU, 64+128 (BASELINE configs[3])",
+                         "rays_per_step_per_gpu": B4, "n_gpus": world, "ms_per_step": ms4, "train_rays_per_s": world * B4 / (ms4 * 1e-3),
+                         "steps": K4, "loss_after": float(tr4.scalars[0]),
+                         "mlp_tflops_per_gpu": B4 * POINTS_PER_RAY * FLOP_TRAIN_PER_POINT / (ms4 * 1e-3) / 1e12}
+        tr4.check_peers()
+        del tr4, pool4
+        torch.cuda.empty_cache()
+
+    # ---- the drop-in seam: the REFERENCE'S OWN Trainer._train_step + backward + torch Adam after install(mode) (N=1) -------
+    if rank == 0 and world == 1 and not args.no_dropin:
+        try:
+            extra["dropin"] = dropin_rays_per_s(args.mode, dev, devb)
+        except Exception as exc:                      # baseline/_ref absent, ...: report, do not fail the bench
+            extra["dropin"] = {"unavailable": repr(exc)[:200]}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ---------------
     cpu = None
@@ -371,6 +489,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
             "loss_after": loss_dev, "loss_e2e_last": float(loss_host[0]),
         }))
+    tr.check_peers()
     if world > 1:
         dist.destroy_process_group()
 

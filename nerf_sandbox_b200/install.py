@@ -33,6 +33,18 @@ _BINDINGS = {
 }
 
 
+_ORIGINALS = {}          # (module, name) -> the reference's own object, for uninstall()
+
+
+def uninstall() -> None:
+    """Put the reference's own callables back (e.g. to time its CPU path in the same process after a drop-in run)."""
+    for (modname, n), obj in _ORIGINALS.items():
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, n, obj)
+    _ORIGINALS.clear()
+
+
 def _imageio_shim():
     """render_utils.py:20 and the loaders import imageio at module scope; when it is not installed provide a stand-in:
     PNG read/write through PIL when that is present (enough for the Blender loader and the validation PNGs), video export
@@ -77,6 +89,8 @@ def install(verbose: bool = False, mode: str | None = None) -> dict:
     for modname, names in _BINDINGS.items():
         mod = importlib.import_module(modname)
         for n, obj in names.items():
+            if (modname, n) not in _ORIGINALS and hasattr(mod, n):
+                _ORIGINALS[(modname, n)] = getattr(mod, n)
             setattr(mod, n, obj)
         done[modname] = sorted(names)
         if verbose:

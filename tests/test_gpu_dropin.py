@@ -37,7 +37,9 @@ def ref():
     if not ref_runner.available():
         pytest.skip("baseline/_ref missing (run __graft_entry__.build() in the build container)")
     TR, RU = ref_runner.import_reference()
-    return ref_runner, TR, RU
+    yield ref_runner, TR, RU
+    from nerf_sandbox_b200.install import uninstall
+    uninstall()
 
 
 def test_reference_train_step_through_install_matches_golden_fp32(ref):

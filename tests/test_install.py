@@ -13,7 +13,7 @@ def test_install_rebinds_reference_names():
     sys.path.insert(0, REF)
     try:
         import nerf_sandbox_b200 as nsb
-        from nerf_sandbox_b200.install import install
+        from nerf_sandbox_b200.install import install, uninstall
         done = install(mode="bf16")
         from nerf_sandbox_b200 import mlps
         assert mlps.get_default_mode() == "bf16"
@@ -28,6 +28,9 @@ def test_install_rebinds_reference_names():
         # the reference Trainer's constructor probes (trainer.py:367-380) work on our NeRF
         m = T.NeRF(63, 27, 8, 256, skip_pos=4)
         T.log_nerf_arch(m, logger=lambda s: None); m._debug_dump_arch_once(); m.enable_debug(3, lambda s: None)
+        orig = T.NeRF
+        uninstall()
+        assert T.NeRF is not orig and T.NeRF.__module__.startswith("nerf_sandbox.source")      # the reference's own class is back
     finally:
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k.startswith("nerf_sandbox.")]:
