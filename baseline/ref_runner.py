@@ -37,7 +37,8 @@ def available() -> bool:
 
 
 def imageio_shim() -> None:
-    """utils/render_utils.py:20 imports imageio at module scope; it is not installed here (PNG/MP4 export only)."""
+    """utils/render_utils.py:20 and the loaders import imageio at module scope; it is not installed here.  Stand-in: PNG
+    read/write through PIL (what the Blender loader and the validation PNGs need); video export unavailable."""
     if "imageio" in sys.modules:
         return
     try:
@@ -47,7 +48,21 @@ def imageio_shim() -> None:
 
         def _missing(*a, **k):
             raise RuntimeError("imageio is not installed: image/video export is unavailable")
-        m.imread = m.imwrite = m.mimwrite = m.v2.imread = m.v2.imwrite = _missing
+        imread = imwrite = _missing
+        try:
+            import numpy as np
+            from PIL import Image
+
+            def imread(path, *a, **k):
+                return np.array(Image.open(path))
+
+            def imwrite(path, arr, *a, **k):
+                Image.fromarray(np.asarray(arr)).save(str(path))
+        except ImportError:
+            pass
+        m.imread = m.v2.imread = imread
+        m.imwrite = m.v2.imwrite = imwrite
+        m.mimwrite = m.v2.mimwrite = m.get_writer = m.v2.get_writer = _missing
         sys.modules["imageio"], sys.modules["imageio.v2"] = m, m.v2
 
 

@@ -203,6 +203,10 @@ def test_trained_scene_psnr_delta_bf16_vs_fp32(nsb):
     steps = int(os.environ.get("NSB_TEST_TRAIN_STEPS", "600"))
     res = train_and_eval(nsb, steps)
     print("trained-scene PSNR (dB):", res)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):                                    # kept as evidence (copied to profiles/ by hand)
+        import json
+        json.dump(res, open(os.path.join(out_dir, "trained_scene_psnr.json"), "w"))
     assert res["trained_bf16_rendered_bf16"] > 20.0, res                          # the scene is actually learnt
     # north_star's bf16 bar on identical inputs: the same trained weights rendered in the two modes
     assert abs(res["trained_bf16_rendered_bf16"] - res["trained_bf16_rendered_fp32"]) <= 0.05, res
