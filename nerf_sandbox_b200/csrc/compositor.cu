@@ -4,6 +4,7 @@
 // The exclusive cumprod transmittance is a multiplicative warp scan carried across 32-sample chunks;
 // rgb/depth/acc reductions ride the same pass.  The backward recomputes T (never reads it from HBM),
 // stages alpha/T per warp in shared memory and walks the ray in reverse with a suffix-sum scan.
+#include <cstdlib>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -238,6 +239,285 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
     }
 }
 
+// =====================================================================================================================
+// Run layout (N <= 256 samples per ray -- every vanilla shape: 64 coarse, 192 merged): lane l of the ray's warp owns the
+// CONTIGUOUS run [l R, l R + R) of samples, R = ceil(N / 32) <= 8, all in registers.  The exclusive cumprod is a serial
+// product inside the run plus ONE multiplicative warp scan over the 32 run products per ray (instead of one scan per 32
+// samples), the loads of a run are issued up front (R independent 16-byte loads per lane in flight), and the backward keeps
+// alpha / T / rgb / pre-activations of its run in registers between the two passes: no shared memory, no recompute of the
+// activations.  Head activations use MUFU-based fast paths (ex2 / rcp: relative error ~2e-7, far inside the 1e-4 bar).
+// The strided kernels above remain for N > 256.
+// =====================================================================================================================
+constexpr int kRunWarps = 4;
+// NSB_K3_STRIDED=1 forces the strided kernels for every N (A/B timing and debugging)
+static const int kRunMaxN = [] { const char* e = getenv("NSB_K3_STRIDED"); return (e && e[0] == '1') ? 0 : 256; }();
+
+// 1 / (1 + 2^(-x log2 e)): FMUL + MUFU.EX2 + FADD + MUFU.RCP (relative error ~4e-7; saturates to 0 / 1, NaN propagates)
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+
+template <bool RAW, int R>
+struct RunSamples {
+    float r[R], g[R], b[R], sigma[R], pre[R], z[R], delta[R], alpha[R], Tl[R];
+};
+
+// Loads + activations + alpha + in-run exclusive products for this lane's run; returns the run's product of (1 - alpha + eps).
+// FULL: N == 32 R, every lane owns exactly R samples (64 / 192 / 256 samples per ray): no per-sample validity predicates.
+// In-kernel noise is drawn in pairs (one hash + Box-Muller -> cos and sin branches) for samples (k, k+1) of the run, k even;
+// forward and backward call this same function, so they regenerate identical draws.
+template <bool RAW, int R, bool FULL>
+__device__ __forceinline__ float run_forward(RunSamples<RAW, R>& s, const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
+                                             const float* __restrict__ noise, float noise_std, bool add_noise, bool softplus,
+                                             uint64_t seed, uint64_t offset, const float* __restrict__ zrow, int64_t q0, int start, int cnt,
+                                             int N, bool inf_last, float rn, bool has_rn, float eps) {
+    float4 v[R];
+    float nz[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {              // every load of the run in flight before the first use
+        s.z[k] = 0.f; nz[k] = 0.f; v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FULL || k < cnt) {
+            s.z[k] = __ldg(zrow + start + k);
+            if (RAW) {
+                v[k] = __ldg(reinterpret_cast<const float4*>(rgb_or_raw) + q0 + k);
+                if (add_noise && noise) nz[k] = __ldg(noise + q0 + k);
+            } else {
+                v[k].x = __ldg(rgb_or_raw + (q0 + k) * 3); v[k].y = __ldg(rgb_or_raw + (q0 + k) * 3 + 1);
+                v[k].z = __ldg(rgb_or_raw + (q0 + k) * 3 + 2); v[k].w = __ldg(sigma + q0 + k);
+            }
+        }
+    }
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, s.z[0], 1);      // first z of the next lane's run
+    if (RAW && add_noise && !noise) {
+        const uint32_t key = hash_key(seed, offset, (uint64_t)q0);
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+            float n0, n1;
+            hash_normal_pair(key, (uint32_t)(q0 + k), n0, n1);
+            nz[k] = n0;
+            if (k + 1 < R) nz[k + 1] = n1;
+        }
+    }
+    float prod = 1.0f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        s.alpha[k] = 0.f; s.Tl[k] = prod; s.r[k] = s.g[k] = s.b[k] = s.sigma[k] = s.pre[k] = s.delta[k] = 0.f;
+        if (FULL || k < cnt) {
+            if (RAW) {
+                s.r[k] = fast_sigmoid(v[k].x); s.g[k] = fast_sigmoid(v[k].y); s.b[k] = fast_sigmoid(v[k].z);       // :236
+                float pre = v[k].w;
+                if (add_noise) pre = fmaf(nz[k], noise_std, pre);                                                   // :239-241
+                s.pre[k] = pre;
+                s.sigma[k] = softplus ? (pre > 20.0f ? pre : log1pf(__expf(pre))) : fmaxf(pre, 0.0f);              // :243-246
+            } else {
+                s.r[k] = v[k].x; s.g[k] = v[k].y; s.b[k] = v[k].z; s.sigma[k] = v[k].w;
+            }
+            const int i = start + k;
+            float zn = z_next_lane;
+            if (k + 1 < R) zn = (FULL || k + 1 < cnt) ? s.z[k + 1] : z_next_lane;
+            float d = (i == N - 1) ? (inf_last ? 1e10f : 0.0f) : (zn - s.z[k]);                                    // :131-136
+            if (has_rn) d *= rn;                                                                                   // :139-141
+            s.delta[k] = d;
+            const float sdt = fminf(fmaxf(s.sigma[k] * d, 0.0f), 60.0f);                                           // :144
+            // :145 -- the accurate expf: for small sigma*delta, alpha inherits the ABSOLUTE error of exp (a 2^-22 MUFU error is a
+            // 1e-4 relative error of alpha = 1e-3), which is what the 1e-4 parity bar on the composite cannot afford
+            s.alpha[k] = 1.0f - expf(-sdt);
+            prod *= (1.0f - s.alpha[k]) + eps;                                                                     // :149
+        }
+    }
+    return prod;
+}
+
+template <bool RAW, int R, bool FULL>
+__global__ void __launch_bounds__(kRunWarps * 32)
+composite_fwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
+                         float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, float* __restrict__ comp,
+                         float* __restrict__ weights, float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N,
+                         uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
+    const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
+    const bool has_rn = ray_norm != nullptr;
+    const int start = lane * R;
+    const int cnt = FULL ? R : max(0, min(R, N - start));
+    for (int64_t b = blockIdx.x * (int64_t)kRunWarps + warp; b < B; b += (int64_t)gridDim.x * kRunWarps) {
+        const float rn = has_rn ? __ldg(ray_norm + b) : 1.0f;
+        const int64_t q0 = b * N + start;
+        RunSamples<RAW, R> s;
+        const float prod = run_forward<RAW, R, FULL>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
+                                               cnt, N, inf_last, rn, has_rn, eps);
+        const float incl = warp_scan_mul(prod, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);                   // product over all earlier lanes' runs
+        if (lane == 0) excl = 1.0f;
+        float sw = 0.f, swz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (FULL || k < cnt) {
+                float w = (excl * s.Tl[k]) * s.alpha[k];                     // :148-153 exclusive cumprod, weights
+                if (!isfinite(w)) w = 0.0f;                                  // :154
+                if (weights) weights[q0 + k] = w;
+                sw += w; swz = fmaf(w, s.z[k], swz); sr = fmaf(w, s.r[k], sr); sg = fmaf(w, s.g[k], sg); sb = fmaf(w, s.b[k], sb);
+            }
+        }
+        sw = warp_sum(sw); swz = warp_sum(swz); sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+        if (lane == 0) {
+            const float acc = fminf(fmaxf(sw, 0.0f), 1.0f);                  // :156
+            const float bg = white ? (1.0f - acc) : 0.0f;                    // :161-162
+            comp[b * 3 + 0] = finalize_color(sr + bg);
+            comp[b * 3 + 1] = finalize_color(sg + bg);
+            comp[b * 3 + 2] = finalize_color(sb + bg);
+            if (acc_out) acc_out[b] = acc;
+            if (depth_out) depth_out[b] = swz / (acc + eps);                 // :157
+        }
+    }
+}
+
+template <bool RAW, int R, bool FULL>
+__global__ void __launch_bounds__(kRunWarps * 32)
+composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
+                         float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
+                         const float* __restrict__ g_weights, const float* __restrict__ g_acc, const float* __restrict__ g_depth,
+                         float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma, int64_t B, int N, uint32_t flags, float eps,
+                         uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    if (step_dev) offset += 8 * *step_dev;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
+    const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
+    const bool has_rn = ray_norm != nullptr;
+    const int start = lane * R;
+    const int cnt = FULL ? R : max(0, min(R, N - start));
+    for (int64_t b = blockIdx.x * (int64_t)kRunWarps + warp; b < B; b += (int64_t)gridDim.x * kRunWarps) {
+        const float rn = has_rn ? __ldg(ray_norm + b) : 1.0f;
+        const int64_t q0 = b * N + start;
+        // ---- pass 1: forward recompute, everything about this lane's run stays in registers
+        RunSamples<RAW, R> s;
+        const float prod = run_forward<RAW, R, FULL>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
+                                               cnt, N, inf_last, rn, has_rn, eps);
+        float gwv[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) gwv[k] = (g_weights && (FULL || k < cnt)) ? __ldg(g_weights + q0 + k) : 0.0f;
+        const float incl = warp_scan_mul(prod, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        float sw = 0.f, swz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+        float T[R], w[R];
+        bool fin[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            T[k] = excl * s.Tl[k];
+            const float wraw = T[k] * s.alpha[k];
+            fin[k] = isfinite(wraw);
+            w[k] = ((FULL || k < cnt) && fin[k]) ? wraw : 0.0f;
+            sw += w[k]; swz = fmaf(w[k], s.z[k], swz); sr = fmaf(w[k], s.r[k], sr); sg = fmaf(w[k], s.g[k], sg); sb = fmaf(w[k], s.b[k], sb);
+        }
+        sw = warp_sum(sw); swz = warp_sum(swz); sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+        const float acc = fminf(fmaxf(sw, 0.0f), 1.0f);
+        const float bg = white ? (1.0f - acc) : 0.0f;
+        float gc[3];                                   // clamp / nan_to_num masks on the composite (:165)
+        {
+            const float craw[3] = {sr + bg, sg + bg, sb + bg};
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? __ldg(g_comp + b * 3 + c) : 0.0f;
+        }
+        const float inv = 1.0f / (acc + eps);
+        const float gd = g_depth ? __ldg(g_depth + b) : 0.0f;
+        float g_accv = g_acc ? __ldg(g_acc + b) : 0.0f;
+        if (white) g_accv -= gc[0] + gc[1] + gc[2];
+        g_accv -= gd * swz * inv * inv;                                      // depth = swz / (acc + eps)
+        const float g_s = (sw >= 0.0f && sw <= 1.0f) ? g_accv : 0.0f;        // clamp(0,1) mask at :156
+        // ---- pass 2: G_i, suffix sums of G_j w_j (serial inside the run + one reverse warp scan per ray)
+        float G[R], lane_total = 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            G[k] = 0.f;
+            if ((FULL || k < cnt) && fin[k])                                 // (nan_to_num backward: no gradient through a non-finite weight)
+                G[k] = gwv[k] + g_s + s.r[k] * gc[0] + s.g[k] * gc[1] + s.b[k] * gc[2] + gd * s.z[k] * inv;
+            lane_total = fmaf(G[k], w[k], lane_total);
+        }
+        float sfx = lane_total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_down_sync(0xffffffffu, sfx, d);
+            if (lane + d < 32) sfx += t;
+        }
+        float suffix = sfx - lane_total;                                     // sum over all later lanes' runs
+#pragma unroll
+        for (int k = R - 1; k >= 0; --k) {
+            if (FULL || k < cnt) {
+                const float f = (1.0f - s.alpha[k]) + eps;
+                const float d_alpha = G[k] * T[k] - suffix * rcp_approx(f);  // cumprod_backward, division form (f in [1e-10, 1])
+                suffix = fmaf(G[k], w[k], suffix);
+                const float d_sdt = d_alpha * (1.0f - s.alpha[k]);           // d/dsdt (1 - exp(-sdt)) = exp(-sdt)
+                const float sd = s.sigma[k] * s.delta[k];
+                const float ds = (sd >= 0.0f && sd <= 60.0f) ? d_sdt * s.delta[k] : 0.0f;     // clamp masks :144
+                if (RAW) {
+                    float4 o;
+                    o.x = w[k] * gc[0] * s.r[k] * (1.0f - s.r[k]);
+                    o.y = w[k] * gc[1] * s.g[k] * (1.0f - s.g[k]);
+                    o.z = w[k] * gc[2] * s.b[k] * (1.0f - s.b[k]);
+                    o.w = softplus ? (s.pre[k] > 20.0f ? ds : ds * fast_sigmoid(s.pre[k])) : (s.pre[k] > 0.0f ? ds : 0.0f);
+                    reinterpret_cast<float4*>(d_rgb_or_raw)[q0 + k] = o;
+                } else {
+                    d_rgb_or_raw[(q0 + k) * 3 + 0] = w[k] * gc[0];
+                    d_rgb_or_raw[(q0 + k) * 3 + 1] = w[k] * gc[1];
+                    d_rgb_or_raw[(q0 + k) * 3 + 2] = w[k] * gc[2];
+                    d_sigma[q0 + k] = ds;
+                }
+            }
+        }
+    }
+}
+
+static int run_grid(int64_t B) {
+    const int64_t want = cdiv(B, kRunWarps);
+    const int64_t cap = (int64_t)num_sms() * 32;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <bool RAW>
+static int launch_fwd_run(const float* a, const float* sigma, const float* noise, float noise_std, const float* z, const float* rn,
+                          float* comp, float* weights, float* acc, float* depth, int64_t B, int N, uint32_t flags, float eps, uint64_t seed,
+                          uint64_t off, void* stream) {
+    const int R = (N + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+    const int grid = run_grid(B);
+#define NSB_RUN_FWD(RR)                                                                                                              \
+    case RR:                                                                                                                         \
+        if (N == 32 * RR) composite_fwd_run_kernel<RAW, RR, true><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, \
+                                                                                                    acc, depth, B, N, flags, eps, seed, off, g_step_dev); \
+        else composite_fwd_run_kernel<RAW, RR, false><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, \
+                                                                                        B, N, flags, eps, seed, off, g_step_dev);                 \
+        break;
+    switch (R) { NSB_RUN_FWD(1) NSB_RUN_FWD(2) NSB_RUN_FWD(3) NSB_RUN_FWD(4) NSB_RUN_FWD(5) NSB_RUN_FWD(6) NSB_RUN_FWD(7) NSB_RUN_FWD(8)
+        default: return NSB_E_BADARG; }
+#undef NSB_RUN_FWD
+    NSB_LAUNCH_CHECK("composite_fwd_run_kernel");
+    return NSB_OK;
+}
+
+template <bool RAW>
+static int launch_bwd_run(const float* a, const float* sigma, const float* noise, float noise_std, const float* z, const float* rn,
+                          const float* g_comp, const float* g_w, const float* g_a, const float* g_d, float* d0, float* d1, int64_t B, int N,
+                          uint32_t flags, float eps, uint64_t seed, uint64_t off, void* stream) {
+    const int R = (N + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+    const int grid = run_grid(B);
+#define NSB_RUN_BWD(RR)                                                                                                             \
+    case RR:                                                                                                                         \
+        if (N == 32 * RR) composite_bwd_run_kernel<RAW, RR, true><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, \
+                                                                                                    g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev); \
+        else composite_bwd_run_kernel<RAW, RR, false><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, \
+                                                                                        B, N, flags, eps, seed, off, g_step_dev);                  \
+        break;
+    switch (R) { NSB_RUN_BWD(1) NSB_RUN_BWD(2) NSB_RUN_BWD(3) NSB_RUN_BWD(4) NSB_RUN_BWD(5) NSB_RUN_BWD(6) NSB_RUN_BWD(7) NSB_RUN_BWD(8)
+        default: return NSB_E_BADARG; }
+#undef NSB_RUN_BWD
+    NSB_LAUNCH_CHECK("composite_bwd_run_kernel");
+    return NSB_OK;
+}
+
 static int comp_grid(int64_t B) {
     const int64_t want = cdiv(B, kCompWarps);
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -338,6 +618,7 @@ extern "C" int nsb_composite_fwd(const float* rgb, const float* sigma, const flo
                                  uint32_t flags, float eps, void* stream) {
     if (B == 0) return NSB_OK;
     if (!rgb || !sigma || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
+    if (N <= kRunMaxN) return launch_fwd_run<false>(rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, stream);
     composite_fwd_kernel<false><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
         rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, nullptr);
     NSB_LAUNCH_CHECK("composite_fwd_kernel");
@@ -350,6 +631,9 @@ extern "C" int nsb_composite_bwd(const float* rgb, const float* sigma, const flo
                                  void* stream) {
     if (B == 0) return NSB_OK;
     if (!rgb || !sigma || !z || !g_comp || !d_rgb || !d_sigma || N < 1 || B < 0) return NSB_E_BADARG;
+    if (N <= kRunMaxN)
+        return launch_bwd_run<false>(rgb, sigma, nullptr, 0.f, z, ray_norm, g_comp, g_weights, g_acc, g_depth, d_rgb, d_sigma, B, N, flags, eps,
+                                     0, 0, stream);
     return launch_bwd<false>(rgb, sigma, nullptr, 0.f, z, ray_norm, g_comp, g_weights, g_acc, g_depth, d_rgb, d_sigma,
                              B, N, flags, eps, 0, 0, stream);
 }
@@ -359,6 +643,8 @@ extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float
                                      int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
     if (B == 0) return NSB_OK;
     if (!raw || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
+    if (N <= kRunMaxN)
+        return launch_fwd_run<true>(raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, stream);
     composite_fwd_kernel<true><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
         raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, g_step_dev);
     NSB_LAUNCH_CHECK("composite_raw_fwd_kernel");
@@ -370,6 +656,9 @@ extern "C" int nsb_composite_raw_bwd(const float* raw, const float* noise, float
                                      uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
     if (B == 0) return NSB_OK;
     if (!raw || !z || !g_comp || !d_raw || N < 1 || B < 0) return NSB_E_BADARG;
+    if (N <= kRunMaxN)
+        return launch_bwd_run<true>(raw, nullptr, noise, noise_std, z, ray_norm, g_comp, nullptr, nullptr, nullptr, d_raw, nullptr, B, N, flags,
+                                    1e-10f, seed, offset, stream);
     return launch_bwd<true>(raw, nullptr, noise, noise_std, z, ray_norm, g_comp, nullptr, nullptr, nullptr, d_raw,
                             nullptr, B, N, flags, 1e-10f, seed, offset, stream);
 }

