@@ -22,6 +22,7 @@
 // TMEM across all tiles of a CTA).  DESIGN.md section 4 has the measurements behind each of these choices.
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <mutex>
 #include "nsb_common.cuh"
@@ -69,7 +70,10 @@ constexpr int kTailFloats = kBoOfs + 4;
 constexpr uint32_t kTImgOfs = ((kBiasOfs + kTailFloats * 4 + 255) / 256) * 256;
 constexpr int kNumDgradLayers = 9;
 __host__ __device__ inline uint32_t dgrad_layer_ofs(int m) { return kTImgOfs + (m == 0 ? 0u : 65536u + (uint32_t)(m - 1) * 131072u); }
-constexpr uint32_t kPackedTcBytes = kTImgOfs + 65536 + 8 * 131072;
+// fp16 copy of the forward images (same layout as the bf16 ones at offset 0) for the inference kernel
+constexpr uint32_t kF16ImgOfs = kTImgOfs + 65536 + 8 * 131072;
+static_assert(kF16ImgOfs % 256 == 0 && kWeightImageBytes % 256 == 0, "images are addressed as rows of 256 B");
+constexpr uint32_t kPackedTcBytes = kF16ImgOfs + kWeightImageBytes;
 
 __host__ __device__ inline int layer_nslabs(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 9 ? 9 : 8)); }
 __host__ __device__ inline int layer_N(int l) { return l == 9 ? 128 : 256; }
@@ -252,13 +256,18 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
-__device__ __forceinline__ uint32_t make_idesc(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-// the same for a CTA pair: M = 256 (128 rows per CTA)
-__device__ __forceinline__ uint32_t make_idesc2(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
+// Number formats (instruction-descriptor bits [7,10) = A, [10,13) = B: 0 = f16, 1 = bf16; accumulation is fp32 throughout).
+//  * INFERENCE forward (no stash: eval frames, no-grad passes): fp16 operands -- weights, gamma(x), gamma(d), activations.
+//    11 significant bits, what the reference computes in under its CUDA autocast (utils/render_utils.py:334-335), 8x finer
+//    than bf16; the positional encoding's high-frequency features and the 9-layer chain are where that shows in a render.
+//  * TRAINING forward + backward: bf16 everywhere.  The stash is the forward's own operand images and wgrad multiplies them
+//    with dY tiles, which need fp32's exponent range (no loss scaling here); kind::f16 MMAs with DIFFERENT A and B formats
+//    trap with "illegal instruction" on B200 (measured: dgrad with A = bf16, B = fp16), so both operands of every backward
+//    MMA -- hence the stashed activations, hence the training forward -- are bf16.
+constexpr uint32_t kFmtF16 = 0u, kFmtBF16 = 1u;
+// kind::f16 instruction descriptor of a CTA pair: D = f32, both operands K-major, M = 256 (128 rows per CTA)
+__device__ __forceinline__ uint32_t make_idesc2(int N, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
 }
 
 // {lo = relu(a), hi = relu(b)} as bf16x2 in one instruction
@@ -271,6 +280,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+// fp16 pair {lo = a, hi = b}, saturating at +-65504 instead of overflowing to inf; _relu clamps negatives to +0 first
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_f16_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) { return F16 ? pack_f16(a, b) : pack_bf16(a, b); }
+template <bool F16> __device__ __forceinline__ uint32_t pack2_relu(float a, float b) { return F16 ? pack_f16_relu(a, b) : pack_bf16_relu(a, b); }
 
 // 16 ReLU'd bf16 outputs held as 8 packed words -> 16 mask bits: bit j (even column 2j) and bit 16+j (odd column 2j+1).
 // __vsetne2 gives 0x0001 per non-zero half-word; one multiply-add per word shifts it into place.
@@ -319,7 +341,7 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c0, con
     if (KIND != 3 || MASK) {          // color_fc output goes to shared memory only for the training stash
         uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = KIND == 0 ? pack_bf16_relu(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) w[j] = KIND == 0 ? pack2_relu<!MASK>(f[2 * j], f[2 * j + 1]) : pack2<!MASK>(f[2 * j], f[2 * j + 1]);
         st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
         st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
         if (KIND != 2 && MASK) mbits = relu_bits16(w);            // training: ReLU mask bits of these 16 outputs
@@ -452,6 +474,7 @@ __device__ __forceinline__ void st_chunk_g(uint8_t* grow, int k8, uint32_t a, ui
 }
 
 // gamma(x) of this thread's point -> gx buffer (K=64: [x(3) | sin(2^k x_d) k-major (30) | cos (30) | 0])
+template <bool F16>
 __device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float py, float pz, uint8_t* grow) {
     float e[64];
     e[0] = px; e[1] = py; e[2] = pz; e[63] = 0.f;
@@ -468,13 +491,14 @@ __device__ __forceinline__ void encode_pos(uint32_t gx, int r, float px, float p
     }
 #pragma unroll
     for (int k8 = 0; k8 < 8; ++k8) {
-        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
-                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        const uint32_t w0 = pack2<F16>(e[8 * k8], e[8 * k8 + 1]), w1 = pack2<F16>(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack2<F16>(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack2<F16>(e[8 * k8 + 6], e[8 * k8 + 7]);
         st_chunk(gx, k8, r, w0, w1, w2, w3);
         st_chunk_g(grow, k8, w0, w1, w2, w3);
     }
 }
 // gamma(d) -> first 4 K-chunks of the gx buffer (K=32: [v(3) | sin (12) | cos (12) | 0 x5])
+template <bool F16>
 __device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float vy, float vz, uint8_t* grow) {
     float e[32];
 #pragma unroll
@@ -493,19 +517,20 @@ __device__ __forceinline__ void encode_dir(uint32_t gx, int r, float vx, float v
     }
 #pragma unroll
     for (int k8 = 0; k8 < 4; ++k8) {
-        const uint32_t w0 = pack_bf16(e[8 * k8], e[8 * k8 + 1]), w1 = pack_bf16(e[8 * k8 + 2], e[8 * k8 + 3]),
-                       w2 = pack_bf16(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack_bf16(e[8 * k8 + 6], e[8 * k8 + 7]);
+        const uint32_t w0 = pack2<F16>(e[8 * k8], e[8 * k8 + 1]), w1 = pack2<F16>(e[8 * k8 + 2], e[8 * k8 + 3]),
+                       w2 = pack2<F16>(e[8 * k8 + 4], e[8 * k8 + 5]), w3 = pack2<F16>(e[8 * k8 + 6], e[8 * k8 + 7]);
         st_chunk(gx, k8, r, w0, w1, w2, w3);
         st_chunk_g(grow, k8, w0, w1, w2, w3);
     }
 }
 // materialised encodings (NeRF.forward boundary): copy a row of `n` floats, zero-padded to 8*chunks
+template <bool F16>
 __device__ __forceinline__ void copy_enc_row(uint32_t gx, int r, const float* __restrict__ src, int n, int chunks, uint8_t* grow) {
     for (int k8 = 0; k8 < chunks; ++k8) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (8 * k8 + j < n && src) ? src[8 * k8 + j] : 0.f;
-        const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+        const uint32_t w0 = pack2<F16>(v[0], v[1]), w1 = pack2<F16>(v[2], v[3]), w2 = pack2<F16>(v[4], v[5]), w3 = pack2<F16>(v[6], v[7]);
         st_chunk(gx, k8, r, w0, w1, w2, w3);
         st_chunk_g(grow, k8, w0, w1, w2, w3);
     }
@@ -571,7 +596,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                             const uint32_t half = bytes >> 1;
                             if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, bytes);
                             tma_load_rows_to_leader(sbase + kSmemRing + stage * kStageBytes2, half == 8192u ? &p.tm8 : &p.tm4,
-                                                    (c_layer_ofs[l] + (uint32_t)s * bytes + crank * half) >> 8, bar_full + 8 * stage);
+                                                    ((STASH ? 0u : kF16ImgOfs) + c_layer_ofs[l] + (uint32_t)s * bytes + crank * half) >> 8, bar_full + 8 * stage);
                         }
                         __syncwarp();
                         if (++stage == kStages2) { stage = 0; ++round; }
@@ -612,7 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
             for (int64_t it = 0; it < n_iter; ++it) {
                 for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
                     const int N = layer_N(l);
-                    const uint32_t idesc = make_idesc2(N);
+                    const uint32_t idesc = make_idesc2(N, STASH ? kFmtBF16 : kFmtF16, STASH ? kFmtBF16 : kFmtF16);
                     const uint32_t lbo_b = (uint32_t)N * 8u;            // K-chunk stride inside a stage: N/2 rows x 16 B
                     const uint64_t bhi = desc_hi(lbo_b, 128);
                     const uint32_t b_step = (2u * lbo_b) >> 4;
@@ -688,7 +713,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
             // ---- layer-0 input: gamma(x) ----
             float vdir[3] = {0.f, 0.f, 1.f};
             if (FROM_ENC) {
-                copy_enc_row(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8, srow(kStashGx));
+                copy_enc_row<!STASH>(gx, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8, srow(kStashGx));
             } else {
                 const int64_t b = qc / p.N;
                 const float zz = valid ? p.z[qc] : 0.f;
@@ -696,7 +721,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                 const float px = fmaf(p.rays_d[b * 3 + 0], zm, p.rays_o[b * 3 + 0]);
                 const float py = fmaf(p.rays_d[b * 3 + 1], zm, p.rays_o[b * 3 + 1]);
                 const float pz = fmaf(p.rays_d[b * 3 + 2], zm, p.rays_o[b * 3 + 2]);
-                encode_pos(gx, r, px, py, pz, srow(kStashGx));
+                encode_pos<!STASH>(gx, r, px, py, pz, srow(kStashGx));
                 const float* vs = p.viewdirs ? p.viewdirs : p.rays_d;
                 const float vx = vs[b * 3 + 0], vy = vs[b * 3 + 1], vz = vs[b * 3 + 2];
                 const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
@@ -767,10 +792,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                         uint32_t w[8];
                         if (relu && !need_f32) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16_relu(f[2 * j], f[2 * j + 1]);
+                            for (int j = 0; j < 8; ++j) w[j] = pack2_relu<!STASH>(f[2 * j], f[2 * j + 1]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+                            for (int j = 0; j < 8; ++j) w[j] = pack2<!STASH>(f[2 * j], f[2 * j + 1]);
                         }
                         st_chunk(act, (c0 >> 3), r, w[0], w[1], w[2], w[3]);
                         st_chunk(act, (c0 >> 3) + 1, r, w[4], w[5], w[6], w[7]);
@@ -809,8 +834,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
                 }
                 t_cols += clock64() - tc0;
                 if (l == 8) {              // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
-                    if (FROM_ENC) copy_enc_row(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
-                    else encode_dir(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
+                    if (FROM_ENC) copy_enc_row<!STASH>(gx, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4, srow(kStashGd));
+                    else encode_dir<!STASH>(gx, r, vdir[0], vdir[1], vdir[2], srow(kStashGd));
                 }
                 if (do_stash) handoff_signal(t);                // l == 9: only the stash copy of c waits for it
                 else if (l != 9) { tc_fence_before(); fence_async_smem(); arrive_in(crank, bar_in, bar_pin, t); }
@@ -836,13 +861,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
 }
 
 // ---- weight packing: flat fp32 params -> bf16 shared-memory images + fp32 tail ------------------------
+template <bool F16>
 __device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params, uint8_t* __restrict__ out, int m) {
     // MMA layer m (0..9) <- parameter layer index: 0..7 trunk, 8 feature, 10 color_fc
     {
         const int pl = m < 9 ? m : 10;
         const LayerDesc d = layer_desc(pl);
         const int N = d.N, Kp = d.Kpad;
-        __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + c_layer_ofs[m]);
+        __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + (F16 ? kF16ImgOfs : 0u) + c_layer_ofs[m]);      // (16-bit elements)
         // image order: [K slab k/32][half of N (one per CTA of a pair)][K chunk (k/8)%4][n % (N/2)][k%8] -- a CTA's half
         // of a K=32 slab is one contiguous block (8 KB at N=256).  One 16-byte chunk (8 consecutive k of one row) per
         // thread, consecutive threads on consecutive rows: sector-sized reads, fully coalesced writes.
@@ -853,9 +879,10 @@ __device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                w[j] = pack_bf16(8 * k8 + 2 * j < d.K ? row[2 * j] : 0.f, 8 * k8 + 2 * j + 1 < d.K ? row[2 * j + 1] : 0.f);
+                w[j] = pack2<F16>(8 * k8 + 2 * j < d.K ? row[2 * j] : 0.f, 8 * k8 + 2 * j + 1 < d.K ? row[2 * j + 1] : 0.f);
             reinterpret_cast<uint4*>(img)[(((size_t)(k8 >> 2) * 2 + n / hn) * 4 + (k8 & 3)) * hn + n % hn] = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        if (F16) return;                                   // the fp32 tail is written once, by the bf16 pass
         float* tail = reinterpret_cast<float*>(out + kBiasOfs);
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
             tail[layer_bias_ofs(m) + n] = params[d.b_off + n];
@@ -993,7 +1020,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_d
     } else if (warp == 1) {
         if (crank == 0 && elect_one()) {                   // MMA issuer: the leader's elected thread, ping-pong over the two tiles
             uint32_t stage = 0, round = 0, use = 0;
-            const uint32_t idesc = make_idesc2(256);
+            const uint32_t idesc = make_idesc2(256, kFmtBF16, kFmtBF16);
             const uint64_t ahi = desc_hi(2048, 128), bhi = desc_hi(2048, 128);
             const uint32_t ring_lo = (sbase + kDgSmemRing) >> 4;
             for (int64_t it = 0; it < n_iter; ++it) {
@@ -1157,7 +1184,7 @@ constexpr int kWgThreads = 256;                       // warp 0 producer, warp 1
 // MN-major, no-swizzle descriptor for a tile image used with the POINT index as K: SBO = stride between 8-wide
 // column groups (2048 B), LBO = stride between 8-point groups (128 B).
 __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    return (1u << 4) | (kFmtBF16 << 7) | (kFmtBF16 << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
 // Column sums of one piece (chunks w4, w4+4, ... of 8 columns; this lane's rows lane, lane+32, ...):
@@ -1409,13 +1436,15 @@ __device__ __forceinline__ void pack_tc_transposed(const float* __restrict__ par
         }
     }
 }
-// one launch packs every image of up to four nets: blockIdx.y = forward layer 0..9 | 10 + dgrad step 0..8, blockIdx.z = net
+// one launch packs every image of up to four nets: blockIdx.y = forward layer 0..9 (bf16) | 10 + dgrad step 0..8 |
+// 19 + forward layer 0..9 (fp16), blockIdx.z = net
 struct PackBatch { const float* params[4]; uint8_t* out[4]; };
 __global__ void pack_tc_kernel(const PackBatch b) {
     const float* params = b.params[blockIdx.z];
     uint8_t* out = b.out[blockIdx.z];
-    if (blockIdx.y < kNumMmaLayers) pack_tc_forward(params, out, blockIdx.y);
-    else pack_tc_transposed(params, out, blockIdx.y - kNumMmaLayers);
+    if (blockIdx.y < kNumMmaLayers) pack_tc_forward<false>(params, out, blockIdx.y);
+    else if (blockIdx.y < kNumMmaLayers + kNumDgradLayers) pack_tc_transposed(params, out, blockIdx.y - kNumMmaLayers);
+    else pack_tc_forward<true>(params, out, blockIdx.y - kNumMmaLayers - kNumDgradLayers);
 }
 
 }  // namespace tc
@@ -1433,7 +1462,7 @@ static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (s
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st) {
     tc::PackBatch b{};
     for (int i = 0; i < n_nets; ++i) { b.params[i] = params[i]; b.out[i] = reinterpret_cast<uint8_t*>(packed_bf16[i]); }
-    tc::pack_tc_kernel<<<dim3(32, tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
+    tc::pack_tc_kernel<<<dim3(32, 2 * tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
     NSB_LAUNCH_CHECK("pack_tc_kernel");
     return NSB_OK;
 }

@@ -99,14 +99,15 @@ def _check_step(nsb, batch, draws, *, near, far, nc, nf, sigma_bias, modes):
             # gradients: fp32 summation-order noise over 10^5..10^6 points (measured against an fp64 oracle run in round 1: 5e-3)
             assert rel(gc, ref["grads_c"]) <= 5e-3 and rel(gf, ref["grads_f"]) <= 2e-2, (rel(gc, ref["grads_c"]), rel(gf, ref["grads_f"]))
         else:
-            assert abs(loss - ref["loss"]) <= 2e-2 * ref["loss"], (loss, ref["loss"])
+            # bars = ~10x what scripts/tc_precision.py measures at this size (profiles/r2_tc_precision.json: loss 1.5e-4,
+            # composite 52.7 dB, gradient cosine 0.99996, |g| ratio 1.0005) -- the training kernels compute in bf16
+            assert abs(loss - ref["loss"]) <= 2e-3 * ref["loss"], (loss, ref["loss"])
             assert float(np.abs(N(out["comp_f"]) - ref["comp_f"]).max()) <= 4e-2
             mse = float(np.mean((N(out["comp_f"]) - ref["comp_f"]) ** 2))
-            assert -10 * np.log10(max(mse, 1e-12)) >= 45.0                                               # bf16 vs reference render
-            # bf16 forward flips ReLU masks of near-zero activations: per-net gradient direction within a few percent
+            assert -10 * np.log10(max(mse, 1e-12)) >= 48.0                                               # bf16 vs reference render
             cos = lambda a, b: float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-            assert cos(gc, ref["grads_c"]) >= 0.99 and cos(gf, ref["grads_f"]) >= 0.98, (cos(gc, ref["grads_c"]), cos(gf, ref["grads_f"]))
-            assert abs(np.linalg.norm(gf) / np.linalg.norm(ref["grads_f"]) - 1) <= 5e-2
+            assert cos(gc, ref["grads_c"]) >= 0.9995 and cos(gf, ref["grads_f"]) >= 0.9995, (cos(gc, ref["grads_c"]), cos(gf, ref["grads_f"]))
+            assert abs(np.linalg.norm(gf) / np.linalg.norm(ref["grads_f"]) - 1) <= 1e-2
 
 
 def test_train_step_1024_rays_matches_oracle(nsb):
@@ -148,7 +149,7 @@ def test_eval_tile_65536_rays_matches_oracle(nsb):
     sl = slice(s0, s0 + 65536)
     o, d, rn = rays[0][sl], rays[1][sl], rays[2][sl]
     sub = np.arange(0, 65536, 16)
-    for mode, tol in (("fp32", None), ("bf16", 4e-2)):
+    for mode, tol in (("fp32", None), ("bf16", 5e-3)):
         tr = nsb.VanillaTrainer(DEV, mode=mode, seed=7, sigma_bias=1.0)
         rgb, acc, depth = nsb.render_rays(T(o), T(d), T(rn).reshape(-1), T(d), tr.nerf_c, tr.nerf_f, near=2.0, far=6.0, nc=64, nf=128,
                                           white_bkgd=True)
@@ -160,10 +161,10 @@ def test_eval_tile_65536_rays_matches_oracle(nsb):
             np.testing.assert_allclose(N(acc)[sub], ref["acc"].reshape(-1), rtol=1e-4, atol=2e-6)
             # depth = sum(w z) / (acc + 1e-10): where acc ~ 0 it is a ratio of rounding noise, so the bar applies to acc * depth
             np.testing.assert_allclose(N(depth)[sub] * N(acc)[sub], ref["depth"].reshape(-1) * ref["acc"].reshape(-1), rtol=2e-4, atol=2e-5)
-        else:
+        else:            # the inference kernel computes on fp16 operands: measured 79 dB against the fp32 render
             assert float(np.abs(N(rgb)[sub] - ref["rgb"]).max()) <= tol
             mse = float(np.mean((N(rgb)[sub] - ref["rgb"]) ** 2))
-            assert -10 * np.log10(max(mse, 1e-12)) >= 45.0
+            assert -10 * np.log10(max(mse, 1e-12)) >= 65.0
 
 
 # ---------------------------------------------------------------------------------------------------- trained scene
@@ -222,6 +223,6 @@ def test_trained_scene_psnr_delta_bf16_vs_fp32(nsb):
     assert res["trained_bf16_rendered_bf16"] > 20.0, res                          # the scene is actually learnt
     # north_star's bf16 bar on identical inputs: the same trained weights rendered in the two modes
     assert abs(res["trained_bf16_rendered_bf16"] - res["trained_bf16_rendered_fp32"]) <= 0.05, res
-    # and training IN bf16 reaches the same quality as training in fp32 (same init, batches and Philox draws; the two
-    # trajectories differ only by arithmetic -- the allowance covers their chaotic divergence, measured in profiles/)
-    assert abs(res["trained_bf16_rendered_bf16"] - res["trained_fp32_rendered_fp32"]) <= 0.25, res
+    # and training IN bf16 reaches the quality of training in fp32 (same init, batches and draws; the trajectories differ
+    # only by arithmetic and diverge chaotically: four measured runs gave bf16 - fp32 = +0.12 .. +0.24 dB, never negative)
+    assert res["trained_bf16_rendered_bf16"] - res["trained_fp32_rendered_fp32"] >= -0.25, res
