@@ -16,29 +16,62 @@ __device__ __forceinline__ float coarse_z_at(int i, int Nc, float near_, float f
     return near_ * (1.0f - t) + far_ * t;                      // trainer.py:902
 }
 
+// coarse_z_at with the (division) step of linspace hoisted by the caller: step = 1 / (Nc - 1)
+__device__ __forceinline__ float coarse_z_step(int i, int Nc, float step, float near_, float far_) {
+    const float t = Nc <= 1 ? 0.0f : (i < Nc / 2 ? step * (float)i : __fmaf_rn(-step, (float)(Nc - 1 - i), 1.0f));    // == linspace01(i, Nc)
+    return near_ * (1.0f - t) + far_ * t;
+}
+
+// uniform in [0,1) on the 2^-24 grid from a 32-bit counter hash (jitter draws need no more than that)
+__device__ __forceinline__ float hash_u01(uint32_t key, uint32_t idx) { return u01(mix32(idx * 0x9E3779B1u + key)); }
+
 __global__ void stratified_kernel(float* __restrict__ z, const float* __restrict__ U, int64_t B, int Nc,
                                   float near_, float far_, int jitter, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
     if (step_dev) offset += 8 * *step_dev;
     const int64_t total = B * (int64_t)Nc;
-    // four consecutive samples per thread: one Philox4x32 block feeds all four uniforms
+    const bool vec = (Nc & 3) == 0;                 // a group of four samples never straddles two rays: 16-byte stores
+    const float step = Nc > 1 ? 1.0f / (float)(Nc - 1) : 0.0f;
     for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; base < total;
          base += (int64_t)gridDim.x * blockDim.x * 4) {
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        if (jitter && !U) rnd = philox4(seed, offset, (uint64_t)(base >> 2));
-        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        const uint32_t key = hash_key(seed, offset, (uint64_t)base);
+        if (vec) {
+            // (a 64-bit modulo is ~100 instructions: stay in 32 bits whenever the sample count allows)
+            const int i0 = total <= 0x7fffffffLL ? (int)((uint32_t)base % (uint32_t)Nc) : (int)(base % Nc);
+            // z_{i0-1} .. z_{i0+4}: six evaluations of trainer.py:902 serve the four samples' lower/upper bounds
+            float zz[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) zz[e] = coarse_z_step(min(max(i0 - 1 + e, 0), Nc - 1), Nc, step, near_, far_);
+            float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jitter) uu = U ? *reinterpret_cast<const float4*>(U + base)
+                               : make_float4(hash_u01(key, (uint32_t)base), hash_u01(key, (uint32_t)base + 1), hash_u01(key, (uint32_t)base + 2),
+                                             hash_u01(key, (uint32_t)base + 3));
+            const float u4[4] = {uu.x, uu.y, uu.z, uu.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                const float zi = zz[e + 1];
+                if (!jitter) { o[e] = zi; continue; }
+                const float lower = i > 0 ? 0.5f * (zi + zz[e]) : zi;           // :904-905  (mids = 0.5*(z[1:]+z[:-1]))
+                const float upper = i < Nc - 1 ? 0.5f * (zz[e + 2] + zi) : zi;  // :906
+                o[e] = lower + (upper - lower) * u4[e];                        // :907 (the sort at :908 is the identity)
+            }
+            *reinterpret_cast<float4*>(z + base) = make_float4(o[0], o[1], o[2], o[3]);
+            continue;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int64_t idx = base + e;
             if (idx >= total) break;
             const int i = (int)(idx % Nc);
-            const float zi = coarse_z_at(i, Nc, near_, far_);
+            const float zi = coarse_z_step(i, Nc, step, near_, far_);
             if (!jitter) { z[idx] = zi; continue; }
-            const float zl = i > 0 ? coarse_z_at(i - 1, Nc, near_, far_) : zi;
-            const float zr = i < Nc - 1 ? coarse_z_at(i + 1, Nc, near_, far_) : zi;
-            const float lower = i > 0 ? 0.5f * (zi + zl) : zi;     // :904-905  (mids = 0.5*(z[1:]+z[:-1]))
-            const float upper = i < Nc - 1 ? 0.5f * (zr + zi) : zi; // :906
-            const float u = U ? U[idx] : u01(rw[e]);
-            z[idx] = lower + (upper - lower) * u;                  // :907 (the sort at :908 is the identity)
+            const float zl = i > 0 ? coarse_z_step(i - 1, Nc, step, near_, far_) : zi;
+            const float zr = i < Nc - 1 ? coarse_z_step(i + 1, Nc, step, near_, far_) : zi;
+            const float lower = i > 0 ? 0.5f * (zi + zl) : zi;
+            const float upper = i < Nc - 1 ? 0.5f * (zr + zi) : zi;
+            const float u = U ? U[idx] : hash_u01(key, (uint32_t)idx);
+            z[idx] = lower + (upper - lower) * u;
         }
     }
 }
@@ -191,71 +224,100 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
         build_cdf(cdf, M, lane, [&](int j) { return fmaxf((0.5f * (wrow[j + 1] + wrow[j]) + 1e-5f) + 1e-5f, 0.0f); });
         __syncwarp();
         const bool draw_sorted = !deterministic && !u_in;
-        if (draw_sorted) {
-            // In-kernel draws: the merge below only needs the SORTED fine samples, and sorted iid uniforms are exactly the
-            // normalised partial sums of Nf+1 iid exponentials (order statistics of the uniform distribution), so they are
-            // generated in order: u_(k) = (E_1 + .. + E_k) / (E_1 + .. + E_{Nf+1}).  One prefix sum instead of a 28-stage
-            // bitonic sort, and one Philox block per four draws.  Same distribution as sort(rand()); the explicit-u path
-            // below keeps the draw-then-sort form.
-            const int cnt = (Nf + 1 + 31) >> 5;                       // draws per lane, a contiguous block
-            const int s0 = lane * cnt;
-            // Philox blocks per lane: at least ceil(cnt / 4), so the lanes' counter ranges never overlap (8 up to Nf = 1023)
-            const uint64_t ctr_stride = (uint64_t)max(8, (cnt + 3) >> 2);
-            float local = 0.f;
-            for (int q = 0; q < cnt; q += 4) {
-                const uint4 r = philox4(seed, offset, ((uint64_t)b * 32 + lane) * ctr_stride + (uint64_t)(q >> 2));
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int sidx = s0 + q + e;
-                    if (q + e < cnt && sidx <= Nf) {
-                        const float ex = -__logf(((float)(rw[e] >> 8) + 1.0f) * (1.0f / 16777216.0f));     // Exp(1), argument in (0,1]
-                        local += ex;
-                        if (sidx < Nf) fine[sidx] = ex;                      // (the last one only enters the total)
-                    }
+        if (draw_sorted || deterministic) {
+            // ---- fast path: this lane owns a CONTIGUOUS block of the (sorted) uniforms, so after one binary search the CDF
+            // index only moves forward, and the fine samples come out sorted: no sort, and their rank among the coarse
+            // samples is a short walk from the CDF bin they fell into.
+            const int cf = (Nf + 31) >> 5;                            // fine samples per lane
+            const int s0 = min(lane * cf, Nf), s1 = min(s0 + cf, Nf);
+            float total = 1.0f, run = 0.f, incl = 0.f;
+            if (draw_sorted) {
+                // In-kernel draws: sorted iid uniforms are exactly the normalised partial sums of Nf+1 iid exponentials (order
+                // statistics of the uniform distribution): u_(k) = (E_1 + .. + E_k) / (E_1 + .. + E_{Nf+1}).  Lane l sums the
+                // exponentials of ITS samples (+ the closing one on the last lane); one warp scan gives every lane its offset.
+                const uint32_t key = hash_key(seed, offset, (uint64_t)b);
+                float local = 0.f;
+                for (int sidx = s0; sidx < s1; ++sidx) {
+                    const float ex = -0.6931471805599453f * lg2_approx((float)((mix32(((uint32_t)b * (uint32_t)(Nf + 1) + (uint32_t)sidx) * 0x9E3779B1u + key) >> 8) + 1u) *
+                                                                       (1.0f / 16777216.0f));            // Exp(1), argument in (0,1]
+                    fine[sidx] = ex;
+                    local += ex;
                 }
-            }
-            float incl = local;                                       // inclusive scan of the lane totals
+                float tail = 0.f;                                     // E_{Nf+1}: only enters the total
+                if (lane == 31) tail = -0.6931471805599453f * lg2_approx((float)((mix32(((uint32_t)b * (uint32_t)(Nf + 1) + (uint32_t)Nf) * 0x9E3779B1u + key) >> 8) + 1u) *
+                                                                         (1.0f / 16777216.0f));
+                incl = local;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const float tsum = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += tsum;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float tsum = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += tsum;
+                }
+                total = __shfl_sync(0xffffffffu, incl + tail, 31);
+                // this lane's partial sums run from the previous lane's inclusive total to its own (clamped below: monotone
+                // across lane boundaries whatever the rounding of the in-lane additions)
+                run = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) run = 0.f;
             }
-            const float total = __shfl_sync(0xffffffffu, incl, 31);
-            // this lane's partial sums run from the previous lane's inclusive total to its own (clamped: monotone across
-            // lane boundaries whatever the rounding of the in-lane additions)
-            float run = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) run = 0.f;
+            // searches are branch-free (fixed trip count): lanes sit in bins of very different width, and data-dependent walks
+            // made the warp pay the longest lane's path on every sample
+            int pw_c = 1;
+            while (pw_c * 2 <= M + 1) pw_c *= 2;
+            for (int sidx = s0; sidx < s1; ++sidx) {
+                float u;
+                if (draw_sorted) { run = fminf(run + fine[sidx], incl); u = fminf(run / total, 1.0f); }
+                else u = linspace01(sidx, Nf);                        // sampling_utils.py:44-46
+                int ind = 0;                                          // searchsorted(cdf, u, right=True) = #{cdf <= u}  (:51)
+                for (int step = pw_c; step > 0; step >>= 1) {
+                    const int mid = ind + step;
+                    if (mid <= M + 1 && cdf[mid - 1] <= u) ind = mid;
+                }
+                const int below = min(max(ind - 1, 0), M), above = min(max(ind, 1), M);          // :52-53
+                const float c_lo = cdf[below], c_hi = cdf[above];
+                float denom = c_hi - c_lo;
+                if (denom < 1e-5f) denom = 1.0f;                      // :62
+                const float t = (u - c_lo) / denom;
+                const float e_lo = edges[below], e_hi = edges[above];
+                const float zf = e_lo + t * (e_hi - e_lo);            // :64
+                fine[sidx] = zf;
+                if (z_fine) z_fine[b * Nf + sidx] = zf;
+                // Rank among the coarse samples, r = #{zc <= zf}.  zf >= edges[below] >= mid(below-1) >= zc[below-1], so r >= below;
+                // zf <= edges[above] <= mid(above) <= zc[above+1], so at most zc[below .. below+2] can be <= zf: three compares.
+                // (A tie or a last-ulp overshoot beyond that is caught by the guard and walked.)
+                int r = below;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r += (below + k < Nc && zrow[min(below + k, Nc - 1)] <= zf) ? 1 : 0;
+                if (r == below + 3) { while (r < Nc && zrow[r] <= zf) ++r; }
+                merged[sidx + r] = zf;
+            }
             __syncwarp();
-            for (int q = 0; q < cnt; ++q) {
-                const int sidx = s0 + q;
-                if (sidx < Nf) {
-                    run = fminf(run + fine[sidx], incl);
-                    int ind;
-                    const float zf = invert(cdf, edges, M, fminf(run / total, 1.0f), &ind);
-                    fine[sidx] = zf;
-                    if (z_fine) z_fine[b * Nf + sidx] = zf;
+            // coarse samples: position i + #{fine < zc[i]} (coarse first on ties), branch-free lower bound over the sorted fine row
+            int pw = 1;
+            while (pw * 2 <= Nf) pw *= 2;
+            for (int i = lane; i < Nc; i += 32) {
+                const float v = zrow[i];
+                int lo = 0;
+                for (int step = pw; step > 0; step >>= 1) {
+                    const int mid = lo + step;
+                    if (mid <= Nf && fine[mid - 1] < v) lo = mid;
                 }
+                merged[i + lo] = v;
             }
+            __syncwarp();
         } else {
             for (int s = lane; s < Nf; s += 32) {
-                const float u = deterministic ? linspace01(s, Nf) : u_in[b * Nf + s];
+                const float u = u_in[b * Nf + s];
                 int ind;
                 const float zf = invert(cdf, edges, M, u, &ind);
                 fine[s] = zf;
                 if (z_fine) z_fine[b * Nf + s] = zf;
             }
-        }
-        if (!deterministic && !draw_sorted) {
             for (int j = Nf + lane; j < sort_len; j += 32) fine[j] = __int_as_float(0x7f800000);   // +inf pad
             __syncwarp();
             warp_bitonic_sort(fine, sort_len, lane);
-        } else {
+            for (int i = lane; i < Nc; i += 32) { const float v = zrow[i]; merged[i + lower_bound_f(fine, Nf, v)] = v; }
+            for (int j = lane; j < Nf; j += 32) { const float v = fine[j]; merged[j + upper_bound(zrow, Nc, v)] = v; }
             __syncwarp();
         }
-        for (int i = lane; i < Nc; i += 32) { const float v = zrow[i]; merged[i + lower_bound_f(fine, Nf, v)] = v; }
-        for (int j = lane; j < Nf; j += 32) { const float v = fine[j]; merged[j + upper_bound(zrow, Nc, v)] = v; }
-        __syncwarp();
         for (int j = lane; j < Nt; j += 32) z_all[b * Nt + j] = merged[j];
         __syncwarp();
     }
