@@ -565,6 +565,16 @@ __device__ __forceinline__ void adam_bias_corrections(const uint64_t* t_dev, flo
     __syncthreads();
     lr_over_bc1 = s_bc[0]; inv_sqrt_bc2 = s_bc[1];
 }
+// One Adam element update with every rounding spelled out (no compiler-chosen FMA contraction): the plain kernel and the
+// fused all-reduce kernel must produce bit-identical parameters from the same gradient (tests/test_gpu_dist.py).
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float grad_scale, float b1, float b2, float eps,
+                                            float lr_over_bc1, float inv_sqrt_bc2) {
+    const float gi = __fmul_rn(g, grad_scale);
+    m = __fmaf_rn(b1, m, __fmul_rn(1.0f - b1, gi));
+    v = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.0f - b2, gi), gi));
+    p = __fsub_rn(p, __fmul_rn(lr_over_bc1, __fdiv_rn(m, __fmaf_rn(__fsqrt_rn(v), inv_sqrt_bc2, eps))));
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float b1, float b2, float eps,
                             float inv_sqrt_bc2, float grad_scale, const uint64_t* t_dev, float lr, float eta_min, int64_t T_max,
@@ -581,22 +591,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
             float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
             const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x; float* pp = &p4.x;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float gi = gg[c] * grad_scale;
-                mm[c] = b1 * mm[c] + (1.0f - b1) * gi;
-                vv[c] = b2 * vv[c] + (1.0f - b2) * gi * gi;
-                pp[c] -= lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * inv_sqrt_bc2 + eps));
-            }
+            for (int c = 0; c < 4; ++c) adam_update(pp[c], mm[c], vv[c], gg[c], grad_scale, b1, b2, eps, lr_over_bc1, inv_sqrt_bc2);
             reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; reinterpret_cast<float4*>(p)[i] = p4;
         }
         return;
     }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * grad_scale;
-        const float mi = b1 * m[i] + (1.0f - b1) * gi;
-        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        p[i] -= lr_over_bc1 * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_update(pi, mi, vi, g[i], grad_scale, b1, b2, eps, lr_over_bc1, inv_sqrt_bc2);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 
@@ -701,12 +704,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
         float4 pm = reinterpret_cast<float4*>(a.m[k])[j], pv = reinterpret_cast<float4*>(a.v[k])[j], pp = reinterpret_cast<float4*>(a.p[k])[j];
         float* gg = &g.x; float* mm = &pm.x; float* vv = &pv.x; float* pq = &pp.x;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float gi = gg[c] * a.grad_scale;
-            mm[c] = a.b1 * mm[c] + (1.0f - a.b1) * gi;
-            vv[c] = a.b2 * vv[c] + (1.0f - a.b2) * gi * gi;
-            pq[c] -= lr_over_bc1 * (mm[c] / (sqrtf(vv[c]) * inv_sqrt_bc2 + a.eps));
-        }
+        for (int c = 0; c < 4; ++c) adam_update(pq[c], mm[c], vv[c], gg[c], a.grad_scale, a.b1, a.b2, a.eps, lr_over_bc1, inv_sqrt_bc2);
         reinterpret_cast<float4*>(a.m[k])[j] = pm; reinterpret_cast<float4*>(a.v[k])[j] = pv; reinterpret_cast<float4*>(a.p[k])[j] = pp;
     }
 }

@@ -79,16 +79,19 @@ class PeerGrads:
 
 
 def gather_shards(local: torch.Tensor, n_total: int, group=None, align: int = 1) -> torch.Tensor:
-    """All-gather row shards produced with shard_range(n_total, rank, world, align) back into [n_total, ...]."""
+    """All-gather row shards produced with shard_range(n_total, rank, world, align) back into [n_total, ...]: one
+    all_gather_into_tensor into a single buffer of world equal slots (the last shard is padded), no per-rank copies."""
     rank, world = world_info(group)
     if world == 1:
         return local
     per = shard_range(n_total, 0, world, align)[1]
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return torch.cat(out, 0)[:n_total]
+    if local.shape[0] != per:                                   # only the last rank's shard can be short
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        local = pad
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out[:n_total]
 
 
 @torch.no_grad()

@@ -157,6 +157,19 @@ class NeRF(nn.Module):
             self._flat, self._packed_version = flat, -1
         return self._flat
 
+    def storage_key(self):
+        """Cheap identity of everything a captured CUDA graph bakes in for this net: the flat parameter buffer (first and last
+        parameter still alias it -- .to() / load into new tensors breaks that) and the packed-weights buffer."""
+        ps = self._param_ends if getattr(self, "_param_ends", None) else None
+        if ps is None:
+            allp = self.ordered_params()
+            ps = self._param_ends = (allp[0], allp[-1], sum(p.numel() for p in allp[:-1]))
+        f, pk = self._flat, self._packed
+        if f is None or pk is None or ps[0].data.data_ptr() != f.data_ptr() or ps[1].data.data_ptr() != f.data_ptr() + 4 * ps[2]:
+            self.flat_params(); self.packed()
+            f, pk = self._flat, self._packed
+        return (f.data_ptr(), pk.data_ptr())
+
     def unflatten(self, flat: torch.Tensor):
         out, off = [], 0
         for p in self.ordered_params():

@@ -253,8 +253,7 @@ class VanillaTrainer:
         B = batch["rays_o_marching"].shape[0]
         # everything whose ADDRESS a captured graph bakes in: a re-flattened / moved parameter buffer, re-allocated packed
         # weights or a grown workspace (see _workspace) force a recapture instead of a replay into freed memory
-        key = (B, self.nerf_c.flat_params().data_ptr(), self.nerf_f.flat_params().data_ptr(), self.nerf_c.packed().data_ptr(),
-               self.nerf_f.packed().data_ptr(), self.nc, self.nf)
+        key = (B, self.nerf_c.storage_key(), self.nerf_f.storage_key(), self.nc, self.nf)
         if self._graphs is None or self._graph_key != key:
             self._static = {k: torch.empty(tuple(batch[k].shape), dtype=torch.float32, device=self.device) for k in BATCH_KEYS}
             self._static_comp = (torch.empty((B, 3), device=self.device), torch.empty((B, 3), device=self.device))

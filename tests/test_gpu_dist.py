@@ -55,17 +55,40 @@ for epoch in range(1, 4):
     mc = pg.multicast(epoch) if os.environ.get("NSB_NVLS") == "1" else None      # NVLS variant: multimem.ld_reduce
     _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
                                          pg.pointers(epoch), mc, pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
-                                         1.0 / world, _lib.stream()), "fused")
+                                         1.0 / world, None, _lib.stream()), "fused")
     red = grads.clone(); dist.all_reduce(red)
     for k in range(2):
         _lib.check(L.nsb_adam_step(_lib.ptr(st[2 + k][0]), _lib.ptr(red[k * n:(k + 1) * n]), _lib.ptr(st[2 + k][1]), _lib.ptr(st[2 + k][2]),
-                                   n, 5e-4, 0.9, 0.999, 1e-8, epoch, 1.0 / world, _lib.stream()), "adam")
+                                   n, 5e-4, 0.9, 0.999, 1e-8, epoch, 1.0 / world, None, _lib.stream()), "adam")
     for k in range(2):
         for a, b in zip(st[k], st[2 + k]):
             if world == 2:
                 assert torch.equal(a, b), (epoch, k, float((a - b).abs().max()))
             else:
                 torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+# a non-finite loss on ONE rank makes EVERY rank skip the update (the reference's skip, trainer.py:713-716, made collective)
+before = [t.clone() for t in st[0]]
+for epoch, bad_rank in ((4, 1), (5, None)):
+    loss = torch.tensor([float("nan") if rank == bad_rank else 0.5], device=dev)
+    pg.buffer(epoch).copy_(torch.ones(2 * n, device=dev))
+    _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
+                                         pg.pointers(epoch), None, pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
+                                         1.0 / world, _lib.ptr(loss), _lib.stream()), "fused+guard")
+    torch.cuda.synchronize()
+    same = all(torch.equal(a, b) for a, b in zip(st[0], before))
+    assert same == (bad_rank is not None), (epoch, rank, same)
+# resume: load_state_dict on a trainer whose flag blocks are ahead of the restored step count, then keep training in lockstep
+sd = tr.state_dict()
+for step in range(9, 12):
+    tr.step_graph({k: T(v) for k, v in O.synthetic_rays(np.random.default_rng(100 * step + rank), 256).items()})
+tr.load_state_dict(sd)                      # back to t = 9 while the flags say 12
+assert tr.adam_t == 9
+for step in range(9, 12):
+    f = tr.step if step % 2 else tr.step_graph
+    f({k: T(v) for k, v in O.synthetic_rays(np.random.default_rng(100 * step + rank), 256).items()})
+tr.check_peers()
+flat = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()]); ref = flat.clone(); dist.broadcast(ref, 0)
+assert torch.equal(flat, ref), "replicas diverged after resume"
 H, W = 20, 31
 rays = O.synthetic_rays(np.random.default_rng(7), H * W)
 args = (T(rays["rays_o_marching"]), T(rays["rays_d_marching_unit"]), T(rays["rays_d_marching_norm"]).reshape(-1))
