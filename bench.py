@@ -284,11 +284,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def max_over_ranks(ms, op=None):
         if world == 1:
             return ms
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
         return float(t.item())
 
     # ---- device-resident timing ("value") --------------------------------------------------------------
@@ -420,9 +420,11 @@ def main():
         e0.record(); img = frame(); e1.record(); barrier()
         ms_frame = max_over_ranks(e0.elapsed_time(e1)) * (H * W / nrays)
         ms_comp = max_over_ranks(tim["compute"][0].elapsed_time(tim["compute"][1])) * (H * W / nrays)
-        ms_gather = max_over_ranks(tim["gather"][0].elapsed_time(tim["gather"][1]))
+        # the all-gather as seen by the LAST rank to arrive (min over ranks): on the others the interval is mostly waiting for it
+        ms_gather = max_over_ranks(tim["gather"][0].elapsed_time(tim["gather"][1]), dist.ReduceOp.MIN if world > 1 else None)
+        ms_comp_min = max_over_ranks(tim["compute"][0].elapsed_time(tim["compute"][1]), dist.ReduceOp.MIN if world > 1 else None) * (H * W / nrays)
         extra.update({"render_800x800_frames_per_s": 1e3 / ms_frame, "render_ms_per_frame": ms_frame, "render_rays_timed": nrays,
-                      "render_eval_chunk": chunk, "render_n_gpus": world, "render_ms_compute_max_rank": ms_comp,
+                      "render_eval_chunk": chunk, "render_n_gpus": world, "render_ms_compute_max_rank": ms_comp, "render_ms_compute_min_rank": ms_comp_min,
                       "render_ms_allgather": ms_gather if world > 1 else 0.0,
                       "render_mlp_tflops": H * W * POINTS_PER_RAY * FLOP_FWD_PER_POINT / (ms_frame * 1e-3) / 1e12,
                       "render_checksum": float(img["rgb"].double().mean())})
