@@ -3,6 +3,7 @@
 // (utils/render_utils.py:337-417) as back-to-back launches on one stream -- no host syncs, no
 // allocation, so a caller can capture a step in a CUDA graph.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "nsb_common.cuh"
 
@@ -48,6 +49,16 @@ int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* pac
                      int stash, cudaStream_t st);
 int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws, int64_t Q, cudaStream_t st);
 
+int tc_field_fwd_rays_split(const float*, const float*, const float*, const float*, const float*, const void* packed, float* raw,
+                            int64_t B, int N, cudaStream_t st);
+int tc_field_fwd_enc_split(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, int64_t Q, cudaStream_t st);
+// The fp32 parity mode's INFERENCE forward (no stash) runs on the tensor cores with fp16-split operands (field_tc.cu:
+// field_fwd_split_kernel, fp32-accurate); NSB_FP32_EVAL=ffma keeps it on the FFMA kernels (A/B and debugging).
+static bool fp32_eval_on_tc() {
+    static const bool on = [] { const char* e = getenv("NSB_FP32_EVAL"); return !(e && e[0] == 'f'); }();
+    return on;
+}
+
 int tc_debug_layer(const float*, const float*, const float*, const float*, const float*, const void*, float*, float*, int,
                    int64_t, int, cudaStream_t);
 
@@ -82,7 +93,8 @@ extern "C" int nsb_pack_weights_batch(const float* const* params, void* const* p
         bf16[i] = reinterpret_cast<char*>(packed[i]) + packed_layout().bf16_off;
         if (mode != NSB_MODE_BF16) NSB_TRY(pack_fp32(params[i], packed[i], as_stream(stream)));
     }
-    if (mode != NSB_MODE_FP32) NSB_TRY(tc_pack(params, bf16, n_nets, as_stream(stream)));     // one launch for all nets and images
+    // one launch for all nets and images; the fp32 mode needs the tensor-core images too (split-operand inference forward)
+    if (mode != NSB_MODE_FP32 || fp32_eval_on_tc()) NSB_TRY(tc_pack(params, bf16, n_nets, as_stream(stream)));
     return NSB_OK;
 }
 
@@ -100,6 +112,8 @@ extern "C" int nsb_field_fwd_enc(const float* enc_pos, const float* enc_dir, con
     if (mode == NSB_MODE_BF16)
         return tc_field_fwd_enc(enc_pos, enc_dir, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw,
                                 ws, Q, stash, as_stream(stream));
+    if (!stash && fp32_eval_on_tc())
+        return tc_field_fwd_enc_split(enc_pos, enc_dir, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw, Q, as_stream(stream));
     NSB_TRY(fp32_prepare_enc(enc_pos, enc_dir, ws, Q, stash, as_stream(stream)));
     return fp32_mlp_fwd(packed, raw, ws, Q, stash, as_stream(stream));
 }
@@ -115,6 +129,9 @@ extern "C" int nsb_field_fwd_rays(const float* rays_o, const float* rays_d, cons
         return tc_field_fwd_rays(rays_o, rays_d, z, ray_norm, viewdirs,
                                  reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw, ws, B, N, stash,
                                  as_stream(stream));
+    if (!stash && fp32_eval_on_tc())
+        return tc_field_fwd_rays_split(rays_o, rays_d, z, ray_norm, viewdirs, reinterpret_cast<const char*>(packed) + packed_layout().bf16_off, raw,
+                                       B, N, as_stream(stream));
     NSB_TRY(fp32_prepare_rays(rays_o, rays_d, z, ray_norm, viewdirs, ws, B, N, stash, as_stream(stream)));
     return fp32_mlp_fwd(packed, raw, ws, Q, stash, as_stream(stream));
 }

@@ -472,7 +472,10 @@ static int gemm_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx,
     dim3 grid((unsigned)cdiv(n_out, BM), (unsigned)cdiv(Kpad, BN), (unsigned)splits);
     sgemm_kernel<true, true, EPI_WGRAD><<<grid, 256, 0, st>>>(g);
     NSB_LAUNCH_CHECK("sgemm_wgrad");
-    const int64_t rpb = 2048;
+    // enough blocks to fill the GPU (4 per SM): at 2048 rows per block a 196,608-point pass launched 96 blocks -- less than
+    // one wave -- and the bias grads cost more than any SGEMM of the step
+    int64_t rpb = cdiv(Q, (int64_t)num_sms() * 4);
+    rpb = rpb < 64 ? 64 : rpb;
     colsum_kernel<<<(unsigned)cdiv(Q, rpb), 256, 0, st>>>(dY, ldy, gb, Q, n_out, rpb);
     NSB_LAUNCH_CHECK("colsum_kernel");
     return NSB_OK;

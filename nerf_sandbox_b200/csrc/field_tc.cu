@@ -73,7 +73,9 @@ __host__ __device__ inline uint32_t dgrad_layer_ofs(int m) { return kTImgOfs + (
 // fp16 copy of the forward images (same layout as the bf16 ones at offset 0) for the inference kernel
 constexpr uint32_t kF16ImgOfs = kTImgOfs + 65536 + 8 * 131072;
 static_assert(kF16ImgOfs % 256 == 0 && kWeightImageBytes % 256 == 0, "images are addressed as rows of 256 B");
-constexpr uint32_t kPackedTcBytes = kF16ImgOfs + kWeightImageBytes;
+// low halves of the fp16 SPLIT  w = hi + lo  (hi = the fp16 image above, lo = fp16(w - hi)) for the fp32-accurate forward
+constexpr uint32_t kF16LoImgOfs = kF16ImgOfs + kWeightImageBytes;
+constexpr uint32_t kPackedTcBytes = kF16LoImgOfs + kWeightImageBytes;
 
 __host__ __device__ inline int layer_nslabs(int l) { return l == 0 ? 2 : (l == 4 ? 10 : (l == 9 ? 9 : 8)); }
 __host__ __device__ inline int layer_N(int l) { return l == 9 ? 128 : 256; }
@@ -281,14 +283,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 // fp16 pair {lo = a, hi = b}, saturating at +-65504 instead of overflowing to inf; _relu clamps negatives to +0 first
+#ifndef NSB_F16_SAT
+#define NSB_F16_SAT 1
+#endif
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
     uint32_t d;
+#if NSB_F16_SAT
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#endif
     return d;
 }
 __device__ __forceinline__ uint32_t pack_f16_relu(float a, float b) {
     uint32_t d;
+#if NSB_F16_SAT
     asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#else
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#endif
     return d;
 }
 template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) { return F16 ? pack_f16(a, b) : pack_bf16(a, b); }
@@ -860,15 +873,290 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_f
     }
 }
 
+// =======================================================================================================
+// fp32-ACCURATE forward on the tensor cores (inference; the eval path of the fp32 parity mode).  Every operand is split into
+// two fp16 terms, x = hi + 2^-11 lo with hi = fp16(x), lo = fp16(2^11 (x - hi)) -- the residual is scaled into fp16's NORMAL
+// range (unscaled, the residual of a weight of magnitude 0.05 is a subnormal with 2^-21 relative resolution) -- 22 significant
+// bits together, and every layer is
+//     acc = A_hi W_hi  +  2^-11 (A_hi W_lo + A_lo W_hi)            (the dropped lo*lo term is 2^-22 relative)
+// -- three kind::f16 MMAs per K = 16 step: the main term into TMEM columns [0,256), the two cross terms into [256,512); the
+// epilogue combines them.  fp16 products are exact in fp32, so what is left against an fp32 FFMA chain is accumulation order
+// and that last term.  Same CTA-pair machinery as the kernel above; the second activation
+// tile's shared memory holds the LOW halves, so a CTA works on ONE 128-point tile at a time (no ping-pong): the weight ring
+// streams a hi and a lo half-slab per K = 32 slab, warps 4-7 own rows and columns [0,128), warps 8-11 the same rows and
+// columns [128,256) (both warp groups can read the tile's TMEM lanes), heads as in the kernel above.
+// =======================================================================================================
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+// 8 consecutive K elements of row r -> one 16-byte chunk in the hi image and one in the lo image
+template <bool RELU>
+__device__ __forceinline__ void st_split8(uint32_t img_hi, uint32_t img_lo, int k8, int r, const float* v) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = RELU ? fmaxf(v[2 * j], 0.f) : v[2 * j], b = RELU ? fmaxf(v[2 * j + 1], 0.f) : v[2 * j + 1];
+        hi[j] = pack_f16(a, b);
+        const float2 h = f16x2_to_f32(hi[j]);
+        lo[j] = pack_f16((a - h.x) * 2048.0f, (b - h.y) * 2048.0f);
+    }
+    st_chunk(img_hi, k8, r, hi[0], hi[1], hi[2], hi[3]);
+    st_chunk(img_lo, k8, r, lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void encode_pos_split(uint32_t gx_hi, uint32_t gx_lo, int r, float px, float py, float pz) {
+    float e[64];
+    e[0] = px; e[1] = py; e[2] = pz; e[63] = 0.f;
+    float s[3], c[3];
+    sincosf(px, &s[0], &c[0]); sincosf(py, &s[1], &c[1]); sincosf(pz, &s[2], &c[2]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            e[3 + 3 * k + d] = s[d]; e[33 + 3 * k + d] = c[d];
+            if (k < 9) {      // exact argument doubling would accumulate rounding over 9 octaves at the 1e-4 bar: re-evaluate
+                const float a = ldexpf(d == 0 ? px : (d == 1 ? py : pz), k + 1);
+                sincosf(a, &s[d], &c[d]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) st_split8<false>(gx_hi, gx_lo, k8, r, e + 8 * k8);
+}
+__device__ __forceinline__ void encode_dir_split(uint32_t gx_hi, uint32_t gx_lo, int r, float vx, float vy, float vz) {
+    float e[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) e[i] = 0.f;
+    e[0] = vx; e[1] = vy; e[2] = vz;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float v3[3] = {ldexpf(vx, k), ldexpf(vy, k), ldexpf(vz, k)};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sincosf(v3[d], &e[3 + 3 * k + d], &e[15 + 3 * k + d]);
+    }
+#pragma unroll
+    for (int k8 = 0; k8 < 4; ++k8) st_split8<false>(gx_hi, gx_lo, k8, r, e + 8 * k8);
+}
+__device__ __forceinline__ void copy_enc_row_split(uint32_t gx_hi, uint32_t gx_lo, int r, const float* __restrict__ src, int n, int chunks) {
+    for (int k8 = 0; k8 < chunks; ++k8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (8 * k8 + j < n && src) ? src[8 * k8 + j] : 0.f;
+        st_split8<false>(gx_hi, gx_lo, k8, r, v);
+    }
+}
+
+template <bool FROM_ENC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_fwd_split_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages2, bar_in = bar_empty + 8 * kStages2,
+                   bar_acc = bar_in + 16, bar_pin = bar_acc + 16 + 8 * kStages2;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 8 * (3 * kStages2 + 6));
+    const uint32_t act_hi = sbase + kSmemAct, act_lo = act_hi + kActBytes, gx_hi = sbase + kSmemGx, gx_lo = gx_hi + kGxBytes;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_in, 256); mbar_init(bar_acc, 1); mbar_init(bar_pin, 256);      // both epilogue warp groups arrive
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // one tile per CTA and iteration: the pair covers tiles (2 i, 2 i + 1)
+    const int64_t num_pairs = (p.num_tiles + 1) / 2;
+    const int64_t first_pair = (int64_t)(blockIdx.x >> 1);
+    const int64_t pair_stride = gridDim.x >> 1;
+    const int64_t n_iter = first_pair < num_pairs ? (num_pairs - first_pair + pair_stride - 1) / pair_stride : 0;
+    const float* tail = reinterpret_cast<const float*>(p.packed + kBiasOfs);
+
+    if (warp == 0) {
+        // ---- TMA producer: per K = 32 slab a hi half-slab and a lo half-slab into two consecutive ring stages ----
+        uint32_t stage = 0, round = 0;
+        for (int64_t it = 0; it < n_iter; ++it) {
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+                const uint32_t bytes = 32u * (uint32_t)layer_N(l) * 2u, half = bytes >> 1;
+                const int ns = layer_nslabs(l);
+                for (int s2 = 0; s2 < 2 * ns; ++s2) {
+                    const int s = s2 >> 1;
+                    const uint32_t img = (s2 & 1) ? kF16LoImgOfs : kF16ImgOfs;
+                    mbar_wait(bar_empty + 8 * stage, (round & 1) ^ 1);
+                    if (elect_one()) {
+                        if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        tma_load_rows_to_leader(sbase + kSmemRing + stage * kStageBytes2, half == 8192u ? &p.tm8 : &p.tm4,
+                                                (img + c_layer_ofs[l] + (uint32_t)s * bytes + crank * half) >> 8, bar_full + 8 * stage);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages2) { stage = 0; ++round; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer (leader's elected thread): three MMAs per K = 16 step ----
+        if (crank == 0 && elect_one()) {
+            uint32_t stage = 0, round = 0, use = 0;
+            const uint64_t ahi = desc_hi(2048, 128);
+            const uint32_t ring_lo = (sbase + kSmemRing) >> 4;
+            for (int64_t it = 0; it < n_iter; ++it) {
+                for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
+                    const int N = layer_N(l);
+                    const uint32_t idesc = make_idesc2(N, kFmtF16, kFmtF16);
+                    const uint32_t lbo_b = (uint32_t)N * 8u;
+                    const uint64_t bhi = desc_hi(lbo_b, 128);
+                    const uint32_t b_step = (2u * lbo_b) >> 4;
+                    const int n_act = l == 0 ? 0 : 8;
+                    const int n_gx = l == 0 ? 2 : (l == 4 ? 2 : (l == 9 ? 1 : 0));
+                    mbar_wait(bar_in, use & 1);
+                    mbar_wait_cl(bar_pin, use & 1);
+                    tc_fence_after();
+                    bool first = true;
+                    const uint32_t d_main = tmem_base, d_cross = tmem_base + 256u;
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int n = seg == 0 ? n_act : n_gx;
+                        uint32_t a_h = (seg == 0 ? act_hi : gx_hi) >> 4, a_l = (seg == 0 ? act_lo : gx_lo) >> 4;
+                        for (int s = 0; s < n; ++s, a_h += 512u, a_l += 512u) {
+                            const uint32_t st_h = stage, rd = round;
+                            if (++stage == kStages2) { stage = 0; ++round; }
+                            const uint32_t st_l = stage, rd_l = round;
+                            if (++stage == kStages2) { stage = 0; ++round; }
+                            mbar_wait(bar_full + 8 * st_h, rd & 1);
+                            mbar_wait(bar_full + 8 * st_l, rd_l & 1);
+                            tc_fence_after();
+                            const uint32_t w_h = ring_lo + st_h * (kStageBytes2 >> 4), w_l = ring_lo + st_l * (kStageBytes2 >> 4);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t ao = (uint32_t)h * 256u, bo = (uint32_t)h * b_step;
+                                tc_mma2(d_main, ahi | (uint64_t)(a_h + ao), bhi | (uint64_t)(w_h + bo), idesc, first ? 0u : 1u);
+                                tc_mma2(d_cross, ahi | (uint64_t)(a_h + ao), bhi | (uint64_t)(w_l + bo), idesc, first ? 0u : 1u);
+                                tc_mma2(d_cross, ahi | (uint64_t)(a_l + ao), bhi | (uint64_t)(w_h + bo), idesc, 1u);
+                                first = false;
+                            }
+                            const bool last = (seg == 1 || n_gx == 0) && s == n - 1;
+                            if (last) tc_commit2(bar_acc);
+                            tc_commit2(bar_empty + 8 * st_h);
+                            tc_commit2(bar_empty + 8 * st_l);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: thread = (row r, column half g) ----
+        const int g = (warp - 4) >> 2;                   // 0: columns [0,128), 1: [128,256)
+        const int r = ((warp & 3) << 5) + lane;          // accumulator row == TMEM lane == point within the tile
+        const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        float* sbias = reinterpret_cast<float*>(smem + kSmemBias);          // 256 fp32: the current layer's bias
+        float* shead = sbias;      // 128 x 4 fp32 (the whole 2 KB block): head partial sums of group 1, after the last layer
+        uint32_t use = 0;
+        for (int64_t it = 0, pair = first_pair; it < n_iter; ++it, pair += pair_stride) {
+            const int64_t tile = pair * 2 + crank;
+            const int64_t q = tile * TILE_M + r;
+            const bool valid = tile < p.num_tiles && q < p.Q;
+            const int64_t qc = valid ? q : 0;
+            if (g == 0) {                                // (the encodings are this row's work once: group 0 writes them)
+                if (FROM_ENC) {
+                    copy_enc_row_split(gx_hi, gx_lo, r, valid ? p.enc_pos + qc * kPosDim : nullptr, kPosDim, 8);
+                } else {
+                    const int64_t b = qc / p.N;
+                    const float zz = valid ? p.z[qc] : 0.f;
+                    const float zm = p.ray_norm ? zz * p.ray_norm[b] : zz;
+                    encode_pos_split(gx_hi, gx_lo, r, fmaf(p.rays_d[b * 3 + 0], zm, p.rays_o[b * 3 + 0]), fmaf(p.rays_d[b * 3 + 1], zm, p.rays_o[b * 3 + 1]),
+                                     fmaf(p.rays_d[b * 3 + 2], zm, p.rays_o[b * 3 + 2]));
+                }
+            }
+            fence_async_smem(); arrive_in(crank, bar_in, bar_pin, 0);
+            float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f};
+            for (int l = 0; l < kNumMmaLayers; ++l, ++use) {
+                const int N = layer_N(l);
+                const int c_begin = g * (N >> 1), c_end = c_begin + (N >> 1);
+                mbar_wait(bar_acc, use & 1);
+                tc_fence_after();
+                named_bar_sync(1, 256);                  // everyone is past the previous layer's reads of sbias / shead
+                if (threadIdx.x - 128 < (unsigned)N) sbias[threadIdx.x - 128] = __ldg(tail + layer_bias_ofs(l) + (threadIdx.x - 128));
+                named_bar_sync(1, 256);
+                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                    uint32_t v[16], vc[16];
+                    tc_ld16(tmem_row + (uint32_t)c0, v);
+                    tc_ld16(tmem_row + 256u + (uint32_t)c0, vc);
+                    tc_wait_ld();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(vc[j]), 1.0f / 2048.0f, __uint_as_float(v[j])) + sbias[c0 + j];
+                    if (l != 8) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (l == 7) {                        // sigma_out on the fp32 activations (mlps.py:265)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sig = fmaf(f[j], __ldg(tail + kWsigOfs + c0 + j), sig);
+                    }
+                    if (l == 9) {                        // color_out on the fp32 color_fc activations (mlps.py:273)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            rgb[0] = fmaf(f[j], __ldg(tail + kWoOfs + c0 + j), rgb[0]);
+                            rgb[1] = fmaf(f[j], __ldg(tail + kWoOfs + 128 + c0 + j), rgb[1]);
+                            rgb[2] = fmaf(f[j], __ldg(tail + kWoOfs + 256 + c0 + j), rgb[2]);
+                        }
+                    }
+                    if (p.dbg && l == p.dbg_layer && valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) p.dbg[q * 256 + c0 + j] = f[j];
+                    }
+                    if (l != 9) {                        // next layer's A operand (hi and lo images), in place
+                        st_split8<false>(act_hi, act_lo, (c0 >> 3), r, f);
+                        st_split8<false>(act_hi, act_lo, (c0 >> 3) + 1, r, f + 8);
+                    }
+                }
+                if (l == 8 && g == 1) {                  // gamma(d) for color_fc replaces gamma(x) (layer 4 has retired)
+                    if (FROM_ENC) copy_enc_row_split(gx_hi, gx_lo, r, valid ? p.enc_dir + qc * kDirDim : nullptr, kDirDim, 4);
+                    else {
+                        const int64_t b = qc / p.N;
+                        const float* vs = p.viewdirs ? p.viewdirs : p.rays_d;
+                        const float vx = vs[b * 3 + 0], vy = vs[b * 3 + 1], vz = vs[b * 3 + 2];
+                        const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+                        encode_dir_split(gx_hi, gx_lo, r, vx * inv, vy * inv, vz * inv);
+                    }
+                }
+                if (l != 9) { tc_fence_before(); fence_async_smem(); arrive_in(crank, bar_in, bar_pin, 0); }
+            }
+            // combine the two column halves of the head sums: group 1 hands its partials to group 0 through shared memory
+            named_bar_sync(1, 256);
+            if (g == 1) { shead[4 * r + 0] = rgb[0]; shead[4 * r + 1] = rgb[1]; shead[4 * r + 2] = rgb[2]; shead[4 * r + 3] = sig; }
+            named_bar_sync(1, 256);
+            if (g == 0 && valid)
+                reinterpret_cast<float4*>(p.raw)[q] = make_float4(rgb[0] + shead[4 * r + 0] + tail[kBoOfs], rgb[1] + shead[4 * r + 1] + tail[kBoOfs + 1],
+                                                                   rgb[2] + shead[4 * r + 2] + tail[kBoOfs + 2], sig + shead[4 * r + 3] + tail[kBsigOfs]);
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- weight packing: flat fp32 params -> bf16 shared-memory images + fp32 tail ------------------------
-template <bool F16>
+__device__ __forceinline__ float f16_residual(float x) {      // 2^11 (x - fp16(x)): exact in fp32, in fp16's normal range
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+    return (x - __half2float(h)) * 2048.0f;
+}
+// FMT 0: bf16 image   1: fp16 image (= the high halves of the split)   2: low halves of the split
+template <int FMT>
 __device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params, uint8_t* __restrict__ out, int m) {
+    constexpr bool F16 = FMT != 0;
     // MMA layer m (0..9) <- parameter layer index: 0..7 trunk, 8 feature, 10 color_fc
     {
         const int pl = m < 9 ? m : 10;
         const LayerDesc d = layer_desc(pl);
         const int N = d.N, Kp = d.Kpad;
-        __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + (F16 ? kF16ImgOfs : 0u) + c_layer_ofs[m]);      // (16-bit elements)
+        __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(out + (FMT == 2 ? kF16LoImgOfs : FMT == 1 ? kF16ImgOfs : 0u) + c_layer_ofs[m]);   // (16-bit elements)
         // image order: [K slab k/32][half of N (one per CTA of a pair)][K chunk (k/8)%4][n % (N/2)][k%8] -- a CTA's half
         // of a K=32 slab is one contiguous block (8 KB at N=256).  One 16-byte chunk (8 consecutive k of one row) per
         // thread, consecutive threads on consecutive rows: sector-sized reads, fully coalesced writes.
@@ -878,11 +1166,14 @@ __device__ __forceinline__ void pack_tc_forward(const float* __restrict__ params
             const float* row = params + d.w_off + (int64_t)n * d.K + 8 * k8;
             uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                w[j] = pack2<F16>(8 * k8 + 2 * j < d.K ? row[2 * j] : 0.f, 8 * k8 + 2 * j + 1 < d.K ? row[2 * j + 1] : 0.f);
+            for (int j = 0; j < 4; ++j) {
+                float a = 8 * k8 + 2 * j < d.K ? row[2 * j] : 0.f, b = 8 * k8 + 2 * j + 1 < d.K ? row[2 * j + 1] : 0.f;
+                if (FMT == 2) { a = f16_residual(a); b = f16_residual(b); }
+                w[j] = pack2<F16>(a, b);
+            }
             reinterpret_cast<uint4*>(img)[(((size_t)(k8 >> 2) * 2 + n / hn) * 4 + (k8 & 3)) * hn + n % hn] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if (F16) return;                                   // the fp32 tail is written once, by the bf16 pass
+        if (FMT != 0) return;                              // the fp32 tail is written once, by the bf16 pass
         float* tail = reinterpret_cast<float*>(out + kBiasOfs);
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
             tail[layer_bias_ofs(m) + n] = params[d.b_off + n];
@@ -1437,14 +1728,15 @@ __device__ __forceinline__ void pack_tc_transposed(const float* __restrict__ par
     }
 }
 // one launch packs every image of up to four nets: blockIdx.y = forward layer 0..9 (bf16) | 10 + dgrad step 0..8 |
-// 19 + forward layer 0..9 (fp16), blockIdx.z = net
+// 19 + forward layer 0..9 (fp16 = split high halves) | 29 + forward layer 0..9 (split low halves), blockIdx.z = net
 struct PackBatch { const float* params[4]; uint8_t* out[4]; };
 __global__ void pack_tc_kernel(const PackBatch b) {
     const float* params = b.params[blockIdx.z];
     uint8_t* out = b.out[blockIdx.z];
-    if (blockIdx.y < kNumMmaLayers) pack_tc_forward<false>(params, out, blockIdx.y);
+    if (blockIdx.y < kNumMmaLayers) pack_tc_forward<0>(params, out, blockIdx.y);
     else if (blockIdx.y < kNumMmaLayers + kNumDgradLayers) pack_tc_transposed(params, out, blockIdx.y - kNumMmaLayers);
-    else pack_tc_forward<true>(params, out, blockIdx.y - kNumMmaLayers - kNumDgradLayers);
+    else if (blockIdx.y < 2 * kNumMmaLayers + kNumDgradLayers) pack_tc_forward<1>(params, out, blockIdx.y - kNumMmaLayers - kNumDgradLayers);
+    else pack_tc_forward<2>(params, out, blockIdx.y - 2 * kNumMmaLayers - kNumDgradLayers);
 }
 
 }  // namespace tc
@@ -1462,7 +1754,7 @@ static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (s
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st) {
     tc::PackBatch b{};
     for (int i = 0; i < n_nets; ++i) { b.params[i] = params[i]; b.out[i] = reinterpret_cast<uint8_t*>(packed_bf16[i]); }
-    tc::pack_tc_kernel<<<dim3(32, 2 * tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
+    tc::pack_tc_kernel<<<dim3(32, 3 * tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
     NSB_LAUNCH_CHECK("pack_tc_kernel");
     return NSB_OK;
 }
@@ -1536,6 +1828,42 @@ static int launch_fwd(tc::FwdParams& p, cudaStream_t st) {
     else tc::field_fwd_kernel<FROM_ENC, false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     NSB_LAUNCH_CHECK("field_fwd_kernel");
     return NSB_OK;
+}
+
+template <bool FROM_ENC>
+static int launch_fwd_split(tc::FwdParams& p, cudaStream_t st) {
+    NSB_TRY(check_arch());
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tc::field_fwd_split_kernel<FROM_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(field_fwd_split_kernel)");
+        attr_set = true;
+    }
+    p.num_tiles = cdiv(p.Q, tc::TILE_M);
+    NSB_TRY(packed_maps(p.packed, &p.tm8, &p.tm4));
+    const int64_t pairs = (p.num_tiles + 1) / 2;              // a CTA pair takes two tiles per iteration (one per CTA)
+    const int64_t max_pairs = num_sms() / 2;
+    const int grid = 2 * (int)(pairs < max_pairs ? pairs : max_pairs);
+    tc::field_fwd_split_kernel<FROM_ENC><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    NSB_LAUNCH_CHECK("field_fwd_split_kernel");
+    return NSB_OK;
+}
+
+// fp32-accurate forward on the tensor cores (fp16 split operands): the inference path of the fp32 parity mode
+int tc_field_fwd_rays_split(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,
+                            const void* packed, float* raw, int64_t B, int N, cudaStream_t st) {
+    tc::FwdParams p{};
+    p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.ray_norm = ray_norm; p.viewdirs = viewdirs;
+    p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw;
+    p.Q = B * (int64_t)N; p.N = N;
+    return launch_fwd_split<false>(p, st);
+}
+int tc_field_fwd_enc_split(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, int64_t Q, cudaStream_t st) {
+    tc::FwdParams p{};
+    p.enc_pos = enc_pos; p.enc_dir = enc_dir;
+    p.packed = reinterpret_cast<const uint8_t*>(packed); p.raw = raw;
+    p.Q = Q; p.N = 1;
+    return launch_fwd_split<true>(p, st);
 }
 
 int tc_field_fwd_rays(const float* rays_o, const float* rays_d, const float* z, const float* ray_norm, const float* viewdirs,

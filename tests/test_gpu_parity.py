@@ -176,8 +176,8 @@ def test_mlp_forward_backward_fp32(nsb):
     assert np.abs(N(flat)[g["grad_idx"]] - ref).max() <= 2e-4 * np.abs(ref).max()
     norms = np.array([float(q.grad.norm()) for q in net.parameters()])
     close(norms, g["grad_norms"], 2e-4, 1e-6)
-    with torch.no_grad():                                              # eval path (no stash) gives the same numbers
-        close(N(net(T(g["enc_pos"]), T(g["enc_dir"]))), N(out), 0, 0)
+    with torch.no_grad():       # eval path (no stash): the fp16-split tensor-core forward, fp32-accurate, same bar vs the reference
+        close(N(net(T(g["enc_pos"]), T(g["enc_dir"]))), g["out"], 1e-4, 2e-5)
     with pytest.raises(RuntimeError):
         net(T(g["enc_pos"])[:, :60], T(g["enc_dir"]))
 
