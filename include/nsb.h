@@ -118,11 +118,15 @@ int nsb_mse_loss(const float* comp_c, const float* comp_f, const float* target, 
  * order [x | sin(2^k x_d) k-major | cos(...)]. */
 int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_input, void* stream);
 
-/* Packed weights of one NeRF: fp32 padded rows for the FFMA path and a bf16 image in tcgen05 operand
- * layout for the tensor path.  Sizes in bytes. */
+/* Packed weights of one NeRF: fp32 padded rows for the FFMA path, and images in tcgen05 operand layout for the tensor
+ * paths -- bf16 (training forward), transposed bf16 (dgrad), fp16 (inference forward) and the fp16 low halves of the
+ * split used by the fp32-accurate inference forward.  Sizes in bytes. */
 size_t nsb_packed_weights_bytes(void);
 /* params: flat fp32 [NSB_N_PARAMS] in state_dict order -> packed (call after every optimiser step).
- * mode selects which section is refreshed: NSB_MODE_FP32, NSB_MODE_BF16, or -1 for both. */
+ * mode selects which section is refreshed: NSB_MODE_FP32, NSB_MODE_BF16, or -1 for both; OR-ing NSB_PACK_TRAIN_ONLY into it
+ * skips the two inference-only fp16 images (what a training loop does between evaluations: re-pack fully before the next
+ * inference call). */
+#define NSB_PACK_TRAIN_ONLY 0x100
 int nsb_pack_weights(const float* params, void* packed, int mode, void* stream);
 
 /* The same for up to four nets in one call (training re-packs coarse + fine after every optimiser step: one kernel launch in

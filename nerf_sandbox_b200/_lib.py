@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libnsb.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MODE_FP32, MODE_BF16 = 0, 1
+PACK_TRAIN_ONLY = 0x100
 WHITE_BKGD, INFINITE_LAST_BIN, TRAINING, SIGMA_SOFTPLUS = 1, 2, 4, 8
 N_PARAMS = 595844
 

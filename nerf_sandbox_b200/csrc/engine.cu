@@ -42,7 +42,7 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 size_t tc_workspace_bytes(int64_t Q, int stash);
 size_t tc_stash_tile_bytes();
 thread_local const uint64_t* g_step_dev = nullptr;
-int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st);
+int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, bool train_only, cudaStream_t st);
 int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
                       float* raw, void* ws, int64_t B, int N, int stash, cudaStream_t st);
 int tc_field_fwd_enc(const float* enc_pos, const float* enc_dir, const void* packed, float* raw, void* ws, int64_t Q,
@@ -86,6 +86,8 @@ extern "C" int64_t nsb_launch_count(void) { return g_launches; }
 
 extern "C" size_t nsb_packed_weights_bytes(void) { return packed_layout().total; }
 extern "C" int nsb_pack_weights_batch(const float* const* params, void* const* packed, int n_nets, int mode, void* stream) {
+    bool train_only = false;
+    if (mode >= 0 && (mode & NSB_PACK_TRAIN_ONLY)) { train_only = true; mode &= ~NSB_PACK_TRAIN_ONLY; }
     if (!params || !packed || n_nets < 1 || n_nets > 4 || mode < -1 || mode > NSB_MODE_BF16) return NSB_E_BADARG;
     void* bf16[4];
     for (int i = 0; i < n_nets; ++i) {
@@ -94,7 +96,8 @@ extern "C" int nsb_pack_weights_batch(const float* const* params, void* const* p
         if (mode != NSB_MODE_BF16) NSB_TRY(pack_fp32(params[i], packed[i], as_stream(stream)));
     }
     // one launch for all nets and images; the fp32 mode needs the tensor-core images too (split-operand inference forward)
-    if (mode != NSB_MODE_FP32 || fp32_eval_on_tc()) NSB_TRY(tc_pack(params, bf16, n_nets, as_stream(stream)));
+    if (mode != NSB_MODE_FP32) NSB_TRY(tc_pack(params, bf16, n_nets, train_only, as_stream(stream)));
+    else if (fp32_eval_on_tc() && !train_only) NSB_TRY(tc_pack(params, bf16, n_nets, false, as_stream(stream)));
     return NSB_OK;
 }
 
@@ -334,7 +337,7 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
                                     lr_eta_min, lr_T_max, nullptr, scalars, stream));
     }
     const float* cparams[2] = {params[0], params[1]};
-    NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode, stream));
+    NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode | NSB_PACK_TRAIN_ONLY, stream));      // inference images: on demand
     counter_inc_kernel<<<1, 32, 0, as_stream(stream)>>>(step_counter);
     NSB_LAUNCH_CHECK("counter_inc_kernel");
     return NSB_OK;

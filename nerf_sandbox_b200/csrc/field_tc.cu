@@ -1751,10 +1751,12 @@ size_t tc_stash_tile_bytes() { return tc::kStashTile; }      // a field workspac
 static inline uint8_t* ws_stash(void* ws) { return reinterpret_cast<uint8_t*>(ws) + 256; }
 static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (size_t)cdiv(Q, tc::TILE_M) * tc::kStashTile; }
 
-int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, cudaStream_t st) {
+int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, bool train_only, cudaStream_t st) {
     tc::PackBatch b{};
     for (int i = 0; i < n_nets; ++i) { b.params[i] = params[i]; b.out[i] = reinterpret_cast<uint8_t*>(packed_bf16[i]); }
-    tc::pack_tc_kernel<<<dim3(32, 3 * tc::kNumMmaLayers + tc::kNumDgradLayers, n_nets), 256, 0, st>>>(b);
+    // blockIdx.y: [0,19) = the training images (bf16 forward + transposed), [19,39) = the inference-only fp16 hi / lo images
+    const int ny = train_only ? tc::kNumMmaLayers + tc::kNumDgradLayers : 3 * tc::kNumMmaLayers + tc::kNumDgradLayers;
+    tc::pack_tc_kernel<<<dim3(32, ny, n_nets), 256, 0, st>>>(b);
     NSB_LAUNCH_CHECK("pack_tc_kernel");
     return NSB_OK;
 }

@@ -166,7 +166,7 @@ class NeRF(nn.Module):
             ps = self._param_ends = (allp[0], allp[-1], sum(p.numel() for p in allp[:-1]))
         f, pk = self._flat, self._packed
         if f is None or pk is None or ps[0].data.data_ptr() != f.data_ptr() or ps[1].data.data_ptr() != f.data_ptr() + 4 * ps[2]:
-            self.flat_params(); self.packed()
+            self.flat_params(); self.packed(for_inference=False)
             f, pk = self._flat, self._packed
         return (f.data_ptr(), pk.data_ptr())
 
@@ -176,8 +176,10 @@ class NeRF(nn.Module):
             out.append(flat[off:off + p.numel()].view(p.shape)); off += p.numel()
         return out
 
-    def packed(self, force: bool = False) -> torch.Tensor:
-        """Kernel-format weights (nsb_pack_weights), refreshed when any parameter changed in place."""
+    def packed(self, force: bool = False, for_inference: bool = True) -> torch.Tensor:
+        """Kernel-format weights (nsb_pack_weights), refreshed when any parameter changed in place.  A training loop re-packs
+        only the training images after each optimiser step (``repack``) and marks the inference-only fp16 images stale; they
+        are refreshed here the next time anything but the trainer asks (``for_inference=True``, the default)."""
         if not self._vanilla:
             raise NotImplementedError("libnsb kernels are specialised to NeRF(63,27,8,256,skip_pos=4)")
         flat = self.flat_params()
@@ -188,9 +190,10 @@ class NeRF(nn.Module):
             self._packed = torch.empty(L.nsb_packed_weights_bytes(), dtype=torch.uint8, device=flat.device)
             self._packed_version = -1
         version = sum(p._version for p in self.ordered_params())     # in-place updates (optimizer, load_state_dict)
-        if force or self._packed_version != version:
+        if force or self._packed_version != version or (for_inference and getattr(self, "_infer_stale", False)):
             _lib.check(L.nsb_pack_weights(_lib.ptr(flat), _lib.ptr(self._packed), self.mode, _lib.stream()), "nsb_pack_weights")
             self._packed_version = version
+            self._infer_stale = False
         return self._packed
 
     @staticmethod
@@ -201,10 +204,11 @@ class NeRF(nn.Module):
         nets = list(nets)
         bufs = [n.packed() if n._packed is None else n._packed for n in nets]
         arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
-        _lib.check(_lib.lib().nsb_pack_weights_batch(arr([n.flat_params() for n in nets]), arr(bufs), len(nets), nets[0].mode,
-                                                     _lib.stream()), "nsb_pack_weights_batch")
+        _lib.check(_lib.lib().nsb_pack_weights_batch(arr([n.flat_params() for n in nets]), arr(bufs), len(nets),
+                                                     nets[0].mode | _lib.PACK_TRAIN_ONLY, _lib.stream()), "nsb_pack_weights_batch")
         for n in nets:
             n._packed_version = sum(p._version for p in n.ordered_params())
+            n._infer_stale = True                  # the fp16 inference images are refreshed by the next packed() for inference
 
     # ---- forward ------------------------------------------------------------------------------------
     def forward(self, enc_pos: torch.Tensor, enc_dir: torch.Tensor) -> torch.Tensor:

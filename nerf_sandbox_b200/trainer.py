@@ -160,7 +160,7 @@ class VanillaTrainer:
         grads_c, grads_f = (self.grads_c, self.grads_f) if grads is None else (grads[:n], grads[n:])
         _lib.check(L.nsb_train_fwd_bwd(
             _lib.ptr(o), _lib.ptr(d), _lib.ptr(rn.reshape(B)), _lib.ptr(vd), _lib.ptr(tgt),
-            _lib.ptr(self.nerf_c.packed()), _lib.ptr(self.nerf_f.packed()), _lib.ptr(grads_c), _lib.ptr(grads_f),
+            _lib.ptr(self.nerf_c.packed(for_inference=False)), _lib.ptr(self.nerf_f.packed(for_inference=False)), _lib.ptr(grads_c), _lib.ptr(grads_f),
             _lib.ptr(self.scalars), _lib.ptr(comp_c), _lib.ptr(comp_f), _lib.ptr(ws), wsb, B, self.nc, self.nf,
             self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode,
             float(grad_scale), self.seed, self.global_step, _lib.ptr(g("U")), _lib.ptr(g("u_fine")),
@@ -232,7 +232,7 @@ class VanillaTrainer:
         _lib.check(L.nsb_train_step(
             _lib.ptr(st["rays_o_marching"]), _lib.ptr(st["rays_d_marching_unit"]), _lib.ptr(st["rays_d_marching_norm"].reshape(B)),
             _lib.ptr(st["rays_d_world_unit"]), _lib.ptr(st["rgb"]), arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]),
-            arr([self.m_c, self.m_f]), arr([self.v_c, self.v_f]), arr([self.nerf_c.packed(), self.nerf_f.packed()]), _lib.ptr(grads),
+            arr([self.m_c, self.m_f]), arr([self.v_c, self.v_f]), arr([self.nerf_c.packed(for_inference=False), self.nerf_f.packed(for_inference=False)]), _lib.ptr(grads),
             _lib.ptr(self._scal8), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
             self.nf, self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode, self.seed,
             self.lr, self.lr_eta_min, self.lr_T_max, self.betas[0], self.betas[1], self.eps, self.grad_clip_norm,
@@ -282,6 +282,7 @@ class VanillaTrainer:
             self._static[k].copy_(batch[k], non_blocking=True)
         self.adam_t += 1; self.global_step += 1; self._step_host += 1
         self._graphs[self.adam_t & 1 if self.peer is not None else 0].replay()
+        self.nerf_c._infer_stale = self.nerf_f._infer_stale = True      # the graph re-packs the training images only
         return self.scalars
 
     def check_peers(self):
