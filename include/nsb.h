@@ -178,10 +178,17 @@ int nsb_grad_clip(float* grads, int64_t n, float max_norm, float pre_scale, floa
  * epoch parity (that is what makes one flag exchange per step sufficient).  n % 4 == 0.
  * mc_grads (optional): multicast (NVLS) address of the same gradient buffers; when given, the sum is one
  * `multimem.ld_reduce` per 16 bytes -- the NVSwitch reduces, every rank receives n_nets * n floats instead of world times that.
+ * mc_reduced / reduced / local_sync (optional, all three or none; need mc_grads): the TWO-PHASE exchange for 4+ ranks.  With
+ * mc_grads alone every rank pulls the whole reduced buffer, i.e. every GPU's buffer is read `world` times by the switch;
+ * here rank r reduces only its 1/world slice and multicast-stores it (`multimem.st`) into every rank's reduced-gradient
+ * buffer -- mc_reduced = multicast address, reduced = this rank's own copy, both n_nets * n floats of symmetric memory --,
+ * a second flag round follows, and Adam runs on the local copy (two launches).  local_sync: 2 device ints of this rank,
+ * zeroed once.  The flag blocks then hold uint32[4 * world].
  * loss_guard [opt]: this rank's loss (device); a non-finite loss on ANY rank makes EVERY rank skip the update
  * (train/trainer.py:713-716, made collective so the replicas stay identical). */
 int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
-                            const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr,
+                            const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync,
+                            void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr,
                             float beta1, float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard, void* stream);
 
 /* Health of the peer-memory exchange above.  A rank waits NSB_PEER_TIMEOUT_S seconds (environment, default 600 -- a peer
@@ -215,7 +222,8 @@ int nsb_train_step(const float* rays_o, const float* rays_d, const float* ray_no
                    int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
                    uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
                    float grad_clip_norm, uint64_t* step_counter,
-                   const void* const* peer_grads, const void* mc_grads, void* const* peer_flags, int rank, int world, void* stream);
+                   const void* const* peer_grads, const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync,
+                   void* const* peer_flags, int rank, int world, void* stream);
 
 /* Trainer._train_step + loss.backward(), train/trainer.py:876-1013 and :717.  Batch tensors as
  * trainer.py:880-884.  grads_c/grads_f[NSB_N_PARAMS] are overwritten with dloss/dparams * grad_scale.

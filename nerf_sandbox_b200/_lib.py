@@ -47,13 +47,13 @@ SIGNATURES = {
     "nsb_field_bwd": (_i32, [_p, _p, _p, _p, _sz, _i64, _i32, _p]),
     "nsb_adam_step": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _p, _p]),
     "nsb_grad_clip": (_i32, [_p, _i64, _f32, _f32, _p, _p]),
-    "nsb_adam_allreduce_step": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _i32, _i32, _u32, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _p, _p]),
+    "nsb_adam_allreduce_step": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _u32, _i64, _f32, _f32, _f32, _f32, _i64, _f32, _p, _p]),
     "nsb_peer_status": (_i32, [C.POINTER(C.c_int)]),
     "nsb_train_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nsb_train_fwd_bwd": (_i32, [_p] * 13 + [_sz, _i64, _i32, _i32, _f32, _f32, _f32, _u32, _i32, _i32, _f32, _u64, _u64,
                                  _p, _p, _p, _p, _p]),
     "nsb_train_step": (_i32, [_p] * 14 + [_sz, _i64, _i32, _i32, _f32, _f32, _f32, _u32, _i32, _i32, _u64, _f32, _f32, _i64, _f32, _f32, _f32,
-                              _f32, _p, _p, _p, _p, _i32, _i32, _p]),
+                              _f32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "nsb_render_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nsb_render_rays": (_i32, [_p] * 10 + [_sz, _i64, _i32, _i32, _f32, _f32, _u32, _i32, _p]),
     "nsb_frame_output": (_i32, [_p, _p, _p, _i64, C.c_double, C.c_double, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),

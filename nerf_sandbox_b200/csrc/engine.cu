@@ -300,7 +300,7 @@ int adam_impl(float* params, const float* grads, float* m, float* v, int64_t n, 
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
                         float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max,
-                        const void* mc_grads, const float* loss_guard, void* stream);
+                        const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync, const float* loss_guard, void* stream);
 __global__ void counter_inc_kernel(uint64_t* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
 }  // namespace nsb
 
@@ -310,8 +310,8 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
                               int Nc, int Nf, float near_, float far_, float noise_std, uint32_t flags, int det_fine, int mode,
                               uint64_t seed, float lr, float lr_eta_min, int64_t lr_T_max, float beta1, float beta2, float eps,
                               float grad_clip_norm, uint64_t* step_counter,
-                              const void* const* peer_grads, const void* mc_grads, void* const* peer_flags, int rank, int world,
-                              void* stream) {
+                              const void* const* peer_grads, const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync,
+                              void* const* peer_flags, int rank, int world, void* stream) {
     if (!params || !m || !v || !packed || !grads || !step_counter) return NSB_E_BADARG;
     for (int k = 0; k < 2; ++k)
         if (!params[k] || !m[k] || !v[k] || !packed[k]) return NSB_E_BADARG;
@@ -328,13 +328,13 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
     // optimiser (+ gradient exchange over peer memory), t = *step_counter + 1
     if (world > 1) {
         NSB_TRY(adam_allreduce_impl(params, m, v, 2, peer_grads, peer_flags, rank, world, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1,
-                                    1.0f / (float)world, step_counter, lr_eta_min, lr_T_max, mc_grads, scalars, stream));
+                                    1.0f / (float)world, step_counter, lr_eta_min, lr_T_max, mc_grads, mc_reduced, reduced, local_sync, scalars, stream));
     } else {        // one rank: the same kernel without the exchange -- both nets in one launch
         if (grad_clip_norm > 0.f)      // trainer.py:719-721; scratch = scalars[4]
             NSB_TRY(nsb_grad_clip(grads, 2 * (int64_t)NSB_N_PARAMS, grad_clip_norm, 1.0f, scalars + 4, stream));
         const void* own[1] = {grads};
         NSB_TRY(adam_allreduce_impl(params, m, v, 2, own, nullptr, 0, 1, 0, NSB_N_PARAMS, lr, beta1, beta2, eps, 1, 1.0f, step_counter,
-                                    lr_eta_min, lr_T_max, nullptr, scalars, stream));
+                                    lr_eta_min, lr_T_max, nullptr, nullptr, nullptr, nullptr, scalars, stream));
     }
     const float* cparams[2] = {params[0], params[1]};
     NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode | NSB_PACK_TRAIN_ONLY, stream));      // inference images: on demand

@@ -619,6 +619,9 @@ struct AdamArParams {
     float* p[kMaxNets]; float* m[kMaxNets]; float* v[kMaxNets];   // n floats each; net k's gradients are grads[r] + k * n
     const float* grads[kMaxPeers];          // every rank's gradient buffer (peer-mapped addresses), n_nets * n floats
     const float* mc_grads;                  // multicast address of the same buffers (NVLS), or null
+    float* mc_red;                          // two-phase NVLS exchange: multicast address of the REDUCED-gradient buffers, or null
+    const float* red;                       // ... this rank's reduced-gradient buffer (n_nets * n floats)
+    int* local_sync;                        // ... device ints of this rank: [0] finished-block counter, [1] epoch whose update is skipped
     uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
@@ -712,6 +715,98 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
     }
 }
 
+// ---- two-phase exchange through the NVSwitch (4+ ranks) ------------------------------------------------------------------
+// In the one-kernel exchange above EVERY rank pulls the WHOLE reduced buffer through `multimem.ld_reduce`: the switch then
+// reads each GPU's 4.77 MB once per requester, i.e. 8 x 4.77 MB leave every GPU at 8 ranks (~55 us at NVLink rate; the same
+// volume as reading seven peers' buffers, which is why NVLS barely beat the peer loads in round 1).  Bandwidth-optimal is
+// reduce-scatter + all-gather: rank r reduces only ITS 1/world slice (its GPU sends and receives 4.77 MB in total) and
+// multicast-STORES the result into every rank's `red` buffer (`multimem.st`); a second flag round, then every rank runs Adam
+// on its local copy.  Two kernels, so no block ever waits on another block of its own grid: kernel 1's blocks wait only for
+// the peers' "gradients complete" flags, kernel 2 (stream-ordered after kernel 1) only for the peers' "slice stored" flags.
+__device__ __forceinline__ void st_mc(float4* p, const float4& x) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+}
+// wait until every rank's word at flags[own][base + r] has reached `epoch`; returns false on timeout (recorded in g_peer_error)
+__device__ __forceinline__ bool wait_peer_flags(const AdamArParams& a, int base, int r, uint32_t epoch) {
+    uint32_t seen;
+    uint64_t t0 = 0;
+    for (uint32_t i = 1;; ++i) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.flags[a.rank] + base + r) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) return true;
+        if (i & 0x3FFu) continue;
+        if (t0 == 0) { t0 = ar_global_ns(); continue; }
+        if (ar_global_ns() - t0 > a.timeout_ns) {
+            if (blockIdx.x == 0) printf("nsb exchange: rank %d gave up waiting for rank %d at epoch %u (flag set %d)\n", a.rank, r, epoch, base);
+            atomicMax(&g_peer_error, 1u + (unsigned)r);
+            return false;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) grad_reduce_scatter_kernel(const __grid_constant__ AdamArParams a) {
+    const int world = a.world;
+    const uint32_t epoch = a.t_dev ? (uint32_t)(*a.t_dev + 1) : a.epoch;
+    __shared__ int s_abort;
+    const uint32_t bad = (a.loss_guard && !isfinite(*a.loss_guard)) ? 1u : 0u;
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        const int bad_ofs = world * (1 + (int)(epoch & 1u));
+        if (blockIdx.x == 0) {
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + bad_ofs + a.rank), "r"(bad) : "memory");
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(epoch) : "memory");
+        }
+        if (!wait_peer_flags(a, 0, r, epoch)) s_abort = 1;
+        uint32_t peer_bad;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(peer_bad) : "l"(a.flags[a.rank] + bad_ofs + r) : "memory");
+        if (peer_bad) s_abort = 1;
+    }
+    __syncthreads();
+    if (!s_abort) {
+        const int64_t total4 = (a.n >> 2) * a.n_nets;
+        const int64_t per = (total4 + world - 1) / world;
+        const int64_t begin = a.rank * per, end = begin + per < total4 ? begin + per : total4;
+        for (int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x)
+            st_mc(reinterpret_cast<float4*>(a.mc_red) + i, ld_reduce_mc(reinterpret_cast<const float4*>(a.mc_grads) + i));
+    }
+    __threadfence_system();                 // this block's multicast stores are performed before it counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_abort) atomicExch(&a.local_sync[1], (int)epoch);        // kernel 2 of this epoch skips the update
+        if (atomicAdd(&a.local_sync[0], 1) == (int)gridDim.x - 1) {   // last block of this rank: publish "my slice is stored"
+            a.local_sync[0] = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + 3 * world + a.rank), "r"(epoch) : "memory");
+        }
+    }
+}
+__global__ void __launch_bounds__(256) adam_reduced_kernel(const __grid_constant__ AdamArParams a) {
+    const int world = a.world;
+    float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2;
+    uint32_t epoch = a.epoch;
+    if (a.t_dev) { adam_bias_corrections(a.t_dev, a.lr, a.eta_min, a.T_max, a.b1, a.b2, lr_over_bc1, inv_sqrt_bc2); epoch = (uint32_t)(*a.t_dev + 1); }
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = (*reinterpret_cast<volatile int*>(a.local_sync + 1) == (int)epoch) ? 1 : 0;
+    __syncthreads();
+    if (s_abort) return;
+    if (threadIdx.x < world && !wait_peer_flags(a, 3 * world, threadIdx.x, epoch)) s_abort = 1;
+    __syncthreads();
+    if (s_abort) return;
+    const int64_t n4 = a.n >> 2, total4 = n4 * a.n_nets;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / n4);
+        const int64_t j = i - k * n4;
+        float4 g = ld_peer(reinterpret_cast<const float4*>(a.red) + i);      // written by the peers' multicast stores: not through a stale L1 line
+        float4 pm = reinterpret_cast<float4*>(a.m[k])[j], pv = reinterpret_cast<float4*>(a.v[k])[j], pp = reinterpret_cast<float4*>(a.p[k])[j];
+        float* gg = &g.x; float* mm = &pm.x; float* vv = &pv.x; float* pq = &pp.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) adam_update(pq[c], mm[c], vv[c], gg[c], a.grad_scale, a.b1, a.b2, a.eps, lr_over_bc1, inv_sqrt_bc2);
+        reinterpret_cast<float4*>(a.m[k])[j] = pm; reinterpret_cast<float4*>(a.v[k])[j] = pv; reinterpret_cast<float4*>(a.p[k])[j] = pp;
+    }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
@@ -720,7 +815,7 @@ namespace nsb {
 int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
                         void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n, float lr, float beta1,
                         float beta2, float eps, int64_t t, float grad_scale, const uint64_t* t_dev, float eta_min, int64_t T_max,
-                        const void* mc_grads, const float* loss_guard, void* stream) {
+                        const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync, const float* loss_guard, void* stream) {
     if (!params || !m || !v || !peer_grads || (!peer_flags && world > 1) || n_nets < 1 || n_nets > kMaxNets || n < 4 || (n & 3) || t < 1 ||
         world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return NSB_E_BADARG;
@@ -738,6 +833,7 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
     a.lr_over_bc1 = (float)(lr / bc1); a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     a.grad_scale = grad_scale; a.t_dev = t_dev; a.lr = lr; a.eta_min = eta_min; a.T_max = T_max;
     a.mc_grads = static_cast<const float*>(mc_grads);
+    a.mc_red = static_cast<float*>(mc_reduced); a.red = reduced; a.local_sync = local_sync;
     a.loss_guard = loss_guard;
     static const uint64_t timeout_ns = [] {
         const char* e = getenv("NSB_PEER_TIMEOUT_S");
@@ -745,6 +841,19 @@ int adam_allreduce_impl(float* const* params, float* const* m, float* const* v, 
         return (uint64_t)(sec * 1e9);
     }();
     a.timeout_ns = timeout_ns;
+    if (world > 1 && mc_grads && mc_reduced && reduced && local_sync) {
+        // two-phase exchange through the switch: reduce-scatter + multicast store, then Adam on the local reduced copy
+        const int64_t total4 = (n >> 2) * n_nets, per = cdiv(total4, world);
+        int g1 = (int)cdiv(per, 256);
+        if (g1 > num_sms()) g1 = num_sms();
+        grad_reduce_scatter_kernel<<<g1, 256, 0, as_stream(stream)>>>(a);
+        NSB_LAUNCH_CHECK("grad_reduce_scatter_kernel");
+        int g2 = (int)cdiv(total4, 256);
+        if (g2 > 4 * num_sms()) g2 = 4 * num_sms();
+        adam_reduced_kernel<<<g2, 256, 0, as_stream(stream)>>>(a);
+        NSB_LAUNCH_CHECK("adam_reduced_kernel");
+        return NSB_OK;
+    }
     // every block spins on the flag exchange first, so the whole grid must be co-resident: cap it at what the occupancy
     // calculator says fits (registers of the chosen instantiation included), at most four blocks per SM
     void (*kern)(const AdamArParams) = world == 1 ? adam_allreduce_kernel<1> : world == 2 ? adam_allreduce_kernel<2>
@@ -767,11 +876,12 @@ int peer_status(int* code) {
 }  // namespace nsb
 
 extern "C" int nsb_adam_allreduce_step(float* const* params, float* const* m, float* const* v, int n_nets, const void* const* peer_grads,
-                                       const void* mc_grads, void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n,
+                                       const void* mc_grads, void* mc_reduced, const float* reduced, int* local_sync,
+                                       void* const* peer_flags, int rank, int world, uint32_t epoch, int64_t n,
                                        float lr, float beta1, float beta2, float eps, int64_t t, float grad_scale, const float* loss_guard,
                                        void* stream) {
     return adam_allreduce_impl(params, m, v, n_nets, peer_grads, peer_flags, rank, world, epoch, n, lr, beta1, beta2, eps, t, grad_scale,
-                               nullptr, 0.f, 0, mc_grads, loss_guard, stream);
+                               nullptr, 0.f, 0, mc_grads, mc_reduced, reduced, local_sync, loss_guard, stream);
 }
 
 extern "C" int nsb_peer_status(int* code) {

@@ -59,6 +59,20 @@ class PeerGrads:
         if want == "1" and not mc:
             raise RuntimeError("NSB_NVLS=1 but the symmetric-memory handle reports no multicast support")
         self.mc_ptr = mc if (want == "1" or self.world >= 4) else 0
+        # two-phase exchange (reduce-scatter + multicast store, nsb_adam_allreduce_step): one more symmetric buffer that receives
+        # the REDUCED gradient on every rank, + two device ints of local bookkeeping.  Used whenever the NVLS sum is
+        # (NSB_TWO_PHASE=0 falls back to every rank pulling the whole buffer through multimem.ld_reduce).
+        self.red = self.red_mc = self.local_sync = None
+        if self.mc_ptr and os.environ.get("NSB_TWO_PHASE", "1") != "0":
+            self.red = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+            self.red.zero_()
+            self._h_red = symm_mem.rendezvous(self.red, group.group_name)
+            rmc = int(getattr(self._h_red, "multicast_ptr", 0) or 0)
+            if rmc:
+                self.red_mc = rmc
+                self.local_sync = torch.zeros(4, dtype=torch.int32, device=device)
+            else:
+                self.red = None
         self.flag_ptrs = [int(p) for p in self._h_flags.buffer_ptrs]
         self._C = C
         self.flag_array = (C.c_void_p * self.world)(*self.flag_ptrs)
@@ -72,6 +86,12 @@ class PeerGrads:
     def multicast(self, epoch: int):
         """Multicast address of the gradient buffer of `epoch` (None without NVLS)."""
         return (self.mc_ptr + (epoch & 1) * self.n * 4) if self.mc_ptr else None
+
+    def two_phase(self):
+        """(multicast address of the reduced-gradient buffers, this rank's copy, local sync ints) or (None, None, None)."""
+        if self.red is None:
+            return None, None, None
+        return self.red_mc, self.red, self.local_sync
 
     def pointers(self, epoch: int, float_offset: int = 0):
         byte_ofs = ((epoch & 1) * self.n + float_offset) * 4

@@ -193,8 +193,10 @@ class VanillaTrainer:
             # all-reduce + Adam in one kernel per net: peer loads over NVLink, no NCCL call on the step path
             pr = self.peer
             arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+            red_mc, red, lsync = pr.two_phase()
             _lib.check(L.nsb_adam_allreduce_step(arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]), arr([self.m_c, self.m_f]),
-                                                 arr([self.v_c, self.v_f]), 2, pr.pointers(epoch), pr.multicast(epoch), pr.flag_array, pr.rank, pr.world,
+                                                 arr([self.v_c, self.v_f]), 2, pr.pointers(epoch), pr.multicast(epoch), red_mc, _lib.ptr(red),
+                                                 _lib.ptr(lsync), pr.flag_array, pr.rank, pr.world,
                                                  epoch, n, lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
                                                  1.0 / pr.world, _lib.ptr(self.scalars), _lib.stream()), "nsb_adam_allreduce_step")
             NeRF.repack((self.nerf_c, self.nerf_f))
@@ -227,8 +229,10 @@ class VanillaTrainer:
         if self.peer is not None:
             grads, pg, pf, rank, world = self.peer.buffer(parity), self.peer.pointers(parity), self.peer.flag_array, self.peer.rank, self.peer.world
             mc = self.peer.multicast(parity)
+            red_mc, red, lsync = self.peer.two_phase()
         else:
             grads, pg, pf, rank, world, mc = self.grads_all, None, None, 0, 1, None
+            red_mc = red = lsync = None
         _lib.check(L.nsb_train_step(
             _lib.ptr(st["rays_o_marching"]), _lib.ptr(st["rays_d_marching_unit"]), _lib.ptr(st["rays_d_marching_norm"].reshape(B)),
             _lib.ptr(st["rays_d_world_unit"]), _lib.ptr(st["rgb"]), arr([self.nerf_c.flat_params(), self.nerf_f.flat_params()]),
@@ -236,7 +240,7 @@ class VanillaTrainer:
             _lib.ptr(self._scal8), _lib.ptr(self._static_comp[0]), _lib.ptr(self._static_comp[1]), _lib.ptr(ws), wsb, B, self.nc,
             self.nf, self.samp_near, self.samp_far, self.raw_noise_std, self._flags(), int(self.det_fine), self.mode, self.seed,
             self.lr, self.lr_eta_min, self.lr_T_max, self.betas[0], self.betas[1], self.eps, self.grad_clip_norm,
-            _lib.ptr(self._step_dev), pg, mc, pf, rank,
+            _lib.ptr(self._step_dev), pg, mc, red_mc, _lib.ptr(red), _lib.ptr(lsync), pf, rank,
             world, _lib.stream()),
             "nsb_train_step")
 

@@ -52,10 +52,11 @@ for epoch in range(1, 4):
     gr = torch.Generator(device=dev); gr.manual_seed(1000 * epoch + rank)
     grads = torch.randn(2 * n, device=dev, generator=gr)
     pg.buffer(epoch).copy_(grads)
-    mc = pg.multicast(epoch) if os.environ.get("NSB_NVLS") == "1" else None      # NVLS variant: multimem.ld_reduce
+    mc = pg.multicast(epoch) if (os.environ.get("NSB_NVLS") == "1" or world >= 4) else None      # NVLS variant: multimem.ld_reduce
+    red_mc, red, lsync = pg.two_phase() if mc else (None, None, None)                            # ... two-phase from 4 ranks
     _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
-                                         pg.pointers(epoch), mc, pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
-                                         1.0 / world, None, _lib.stream()), "fused")
+                                         pg.pointers(epoch), mc, red_mc, _lib.ptr(red), _lib.ptr(lsync), pg.flag_array, rank, world, epoch, n,
+                                         5e-4, 0.9, 0.999, 1e-8, epoch, 1.0 / world, None, _lib.stream()), "fused")
     red = grads.clone(); dist.all_reduce(red)
     for k in range(2):
         _lib.check(L.nsb_adam_step(_lib.ptr(st[2 + k][0]), _lib.ptr(red[k * n:(k + 1) * n]), _lib.ptr(st[2 + k][1]), _lib.ptr(st[2 + k][2]),
@@ -71,9 +72,11 @@ before = [t.clone() for t in st[0]]
 for epoch, bad_rank in ((4, 1), (5, None)):
     loss = torch.tensor([float("nan") if rank == bad_rank else 0.5], device=dev)
     pg.buffer(epoch).copy_(torch.ones(2 * n, device=dev))
+    mc = pg.multicast(epoch) if world >= 4 else None
+    red_mc, red, lsync = pg.two_phase() if mc else (None, None, None)
     _lib.check(L.nsb_adam_allreduce_step(arr([st[0][0], st[1][0]]), arr([st[0][1], st[1][1]]), arr([st[0][2], st[1][2]]), 2,
-                                         pg.pointers(epoch), None, pg.flag_array, rank, world, epoch, n, 5e-4, 0.9, 0.999, 1e-8, epoch,
-                                         1.0 / world, _lib.ptr(loss), _lib.stream()), "fused+guard")
+                                         pg.pointers(epoch), mc, red_mc, _lib.ptr(red), _lib.ptr(lsync), pg.flag_array, rank, world, epoch, n,
+                                         5e-4, 0.9, 0.999, 1e-8, epoch, 1.0 / world, _lib.ptr(loss), _lib.stream()), "fused+guard")
     torch.cuda.synchronize()
     same = all(torch.equal(a, b) for a, b in zip(st[0], before))
     assert same == (bad_rank is not None), (epoch, rank, same)

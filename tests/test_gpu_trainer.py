@@ -81,8 +81,8 @@ def test_non_finite_loss_skips_the_update():
             loss = torch.tensor([0.25 if bad is None else bad], device=DEV)
             if fused:
                 arr = lambda ts: (C.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
-                _lib.check(L.nsb_adam_allreduce_step(arr([p[:n], p[n:]]), arr([m[:n], m[n:]]), arr([v[:n], v[n:]]), 2, arr([g]), None, None, 0, 1, 1, n,
-                                                     5e-4, 0.9, 0.999, 1e-8, 1, 1.0, _lib.ptr(loss), _lib.stream()))
+                _lib.check(L.nsb_adam_allreduce_step(arr([p[:n], p[n:]]), arr([m[:n], m[n:]]), arr([v[:n], v[n:]]), 2, arr([g]), None, None, None,
+                                                     None, None, 0, 1, 1, n, 5e-4, 0.9, 0.999, 1e-8, 1, 1.0, _lib.ptr(loss), _lib.stream()))
             else:
                 _lib.check(L.nsb_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), 2 * n, 5e-4, 0.9, 0.999, 1e-8, 1, 1.0, _lib.ptr(loss),
                                            _lib.stream()))
