@@ -393,7 +393,7 @@ def main():
     traffic = None
     try:      # DRAM bytes of this launch set from the committed ncu --set full captures (bf16 mode only)
         if args.mode == "bf16":
-            traffic = int(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["field_fwd_bwd_fine_bytes"])
+            traffic = int(json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["field_fwd_bwd_fine_bytes"])
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
