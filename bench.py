@@ -81,7 +81,7 @@ def llff_ndc_rays(rng, n):
                 rgb=f32(rng.uniform(0, 1, (n, 3))))
 
 
-def dropin_rays_per_s(mode, dev, batches, steps=20):
+def dropin_rays_per_s(mode, dev, batches, steps=20, fuse=True):
     """rays/s of the loop body train/trainer.py:702-725 executed by the REFERENCE'S code (baseline/_ref) on this package's
     kernels: install(mode) rebinds its by-name imports, then its unbound Trainer._train_step, autograd backward and
     torch.optim.Adam run unmodified (amp off: the arithmetic mode is the kernels')."""
@@ -89,7 +89,7 @@ def dropin_rays_per_s(mode, dev, batches, steps=20):
     from baseline import ref_runner
     from nerf_sandbox_b200.install import install, uninstall
     TR, _ = ref_runner.import_reference()
-    install(mode=mode)
+    install(mode=mode, fuse_train_step=fuse)
     try:
         return _dropin_timed(TR, ref_runner, mode, dev, batches, steps)
     finally:
@@ -122,7 +122,10 @@ def _dropin_timed(TR, ref_runner, mode, dev, batches, steps):
         loss = step(batches[i % len(batches)])
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"path": "reference Trainer._train_step + loss.backward() + torch.optim.Adam after nerf_sandbox_b200.install(mode)", "mode": mode,
+    fused = hasattr(TR.Trainer._train_step, "_nsb_original")
+    return {"path": "reference loop body (Trainer._train_step + loss.backward() + torch.optim.Adam) after nerf_sandbox_b200.install(mode); "
+                    + ("_train_step = the fused step (install default)" if fused else "the reference's own _train_step body on the rebound callables"),
+            "mode": mode,
             "ms_per_step": ms, "train_rays_per_s": RAYS / (ms * 1e-3), "steps": steps, "loss_after": float(loss.detach())}
 
 
@@ -459,8 +462,9 @@ def main():
 
     # ---- the drop-in seam: the REFERENCE'S OWN Trainer._train_step + backward + torch Adam after install(mode) (N=1) -------
     if rank == 0 and world == 1 and not args.no_dropin:
-        try:
+        try:      # install()'s default (Trainer._train_step = the fused step) and the reference's own _train_step body
             extra["dropin"] = dropin_rays_per_s(args.mode, dev, devb)
+            extra["dropin_reference_body"] = dropin_rays_per_s(args.mode, dev, devb, fuse=False)
         except Exception as exc:                      # baseline/_ref absent, ...: report, do not fail the bench
             extra["dropin"] = {"unavailable": repr(exc)[:200]}
 

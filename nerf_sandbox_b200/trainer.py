@@ -123,6 +123,27 @@ class VanillaTrainer:
         self._graph_key = None
         self.nerf_c.packed(); self.nerf_f.packed()
 
+    @classmethod
+    def step_engine(cls, nerf_c, nerf_f, *, nc, nf, near, far, white_bkgd=True, raw_noise_std=1.0, infinite_last_bin=True,
+                    det_fine=False, sigma_activation="relu", seed=0):
+        """A trainer shell around EXISTING modules (no optimiser state): what `install(fuse_train_step=True)` puts behind the
+        reference's `Trainer._train_step` -- only `_train_step` / `_fwd_bwd` may be used on it."""
+        if nerf_c.mode != nerf_f.mode:
+            raise ValueError("coarse and fine NeRF must use the same arithmetic mode")
+        self = cls.__new__(cls)
+        self.device = nerf_c.flat_params().device
+        self.nc, self.nf, self.samp_near, self.samp_far = int(nc), int(nf), float(near), float(far)
+        self.white_bkgd, self.raw_noise_std = bool(white_bkgd), float(raw_noise_std)
+        self.infinite_last_bin, self.det_fine = bool(infinite_last_bin), bool(det_fine)
+        self.sigma_activation = (sigma_activation or "relu").lower()
+        self.mode, self.seed, self.global_step, self.adam_t = nerf_c.mode, int(seed), 0, 0
+        self.nerf_c, self.nerf_f, self.peer, self.pg = nerf_c, nerf_f, None, None
+        self._scal8 = torch.zeros(8, device=self.device, dtype=torch.float32)
+        self.scalars = self._scal8[:4]
+        self.grads_all = self.grads_c = self.grads_f = None            # _FusedStepFn brings its own gradient buffer
+        self._ws = self._graphs = self._graph_key = None
+        return self
+
     def current_lr(self, sched_steps=None) -> float:
         """Learning rate after `sched_steps` scheduler steps (default: now) -- closed form of CosineAnnealingLR."""
         t = self.adam_t if sched_steps is None else int(sched_steps)

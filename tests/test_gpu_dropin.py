@@ -42,13 +42,17 @@ def ref():
     uninstall()
 
 
-def test_reference_train_step_through_install_matches_golden_fp32(ref):
+@pytest.mark.parametrize("fuse", [False, True])
+def test_reference_train_step_through_install_matches_golden_fp32(ref, fuse):
+    """fuse=False: the reference's own _train_step body on the rebound callables.  fuse=True (install's default): the same
+    method replaced by the fused step (one library call), behind the same contract."""
     ref_runner, TR, RU = ref
     from nerf_sandbox_b200 import _hooks, _lib
     from nerf_sandbox_b200.install import install
     from oracle import nerf_oracle as O
     import nerf_sandbox_b200 as nsb
-    install(mode="fp32")
+    install(mode="fp32", fuse_train_step=fuse)
+    assert hasattr(TR.Trainer._train_step, "_nsb_original") == fuse
     assert TR.NeRF is nsb.NeRF and TR.nerf_forward_pass is nsb.nerf_forward_pass and TR.sample_pdf is nsb.sample_pdf
     g = golden("train_step")
     B, nc, nf = int(g["B"]), int(g["nc"]), int(g["nf"])
@@ -68,14 +72,17 @@ def test_reference_train_step_through_install_matches_golden_fp32(ref):
     normals = [g["noise_c"], g["noise_f"]]
     _hooks.normal = lambda n, device: T(normals.pop(0)).reshape(-1)[:n]
     _hooks.uniform = lambda b, n, device: T(g["u_fine"]).reshape(b, n)
+    _hooks.jitter = lambda b, n, device: T(g["U"]).reshape(b, n)              # (the fused step's stratified draws)
+    launches = _lib.launch_count()
     orig = torch.rand_like
     torch.rand_like = lambda x, *a, **k: T(g["U"]).reshape(x.shape).to(x.dtype)
     try:
         out = TR.Trainer._train_step(ns, batch)
     finally:
         torch.rand_like = orig
-        _hooks.normal = _hooks.uniform = None
+        _hooks.normal = _hooks.uniform = _hooks.jitter = None
     assert not normals, "both passes must have consumed their noise"
+    assert _lib.launch_count() > launches
     assert abs(float(out["loss"].detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
     assert abs(float(out["psnr"]) - float(g["psnr"])) <= 1e-3
     np.testing.assert_allclose(N(out["comp_c"]), g["comp_c"], rtol=1e-4, atol=1e-6)
@@ -125,7 +132,8 @@ def test_reference_cli_vanilla_trains_on_tensor_cores(ref, tmp_path, capsys):
     from nerf_sandbox_b200 import _lib
     from nerf_sandbox_b200.install import install
     import nerf_sandbox_b200 as nsb
-    install(mode="bf16")
+    install(mode="bf16")                                          # default: fused Trainer._train_step
+    assert hasattr(TR.Trainer._train_step, "_nsb_original")
     from nerf_sandbox.source.scripts import train_nerf as CLI
     scene, out_dir = str(tmp_path / "scene"), str(tmp_path / "out")
     _tiny_blender_scene(scene)
@@ -146,6 +154,7 @@ def test_reference_cli_vanilla_trains_on_tensor_cores(ref, tmp_path, capsys):
     p1 = torch.cat([p.detach().reshape(-1) for p in trainer.nerf_f.parameters()])
     assert torch.isfinite(p1).all() and float((p1 - p0).abs().max()) > 0        # the optimiser moved the fine net
     assert _lib.launch_count() - before > 12 * 10                               # ... through libnsb kernels
+    assert trainer.__dict__.get("_nsb_engine") not in (None, False)             # ... and the fused step engine was used
     dbg = json.load(open(os.path.join(out_dir, "run_debug.json")))
     assert "error" not in dbg["forward_probe"] and "error" not in dbg["hier_sampling"], dbg
     assert abs(dbg["forward_probe"]["weights_sum_minus_acc_maxabs"]) < 1e-4
