@@ -323,6 +323,158 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// resample + merge, register-resident fast path: Nc = 32 NCL and Nf = 32 NFL known at compile time (every vanilla shape:
+// 64 / 128, and the whole BASELINE configs[4] sweep grid), deterministic or in-kernel draws.  Lane l owns the CONTIGUOUS coarse
+// samples [l NCL, l NCL + NCL) (z, w, midpoints, edges, pdf and its prefix all in registers: neighbours by shuffle, one warp
+// scan for the CDF) and the contiguous block [l NFL, l NFL + NFL) of the SORTED uniforms; only the random-access tables (cdf,
+// edges, zc, fine, merged row) live in shared memory; every loop is unrolled and every search has a fixed trip count.
+// Same arithmetic, operation by operation, as resample_merge_kernel (this file is compiled with -fmad=false).
+// ---------------------------------------------------------------------------------------------------
+template <int NCL, int NFL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict__ w_c, float* __restrict__ z_all, float* __restrict__ z_fine,
+                           int64_t B, int deterministic, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+    constexpr int NC = 32 * NCL, NF = 32 * NFL, M = NC - 1, NT = NC + NF;
+    if (step_dev) offset += 8 * *step_dev;
+    __shared__ float sm[kWarpsPerBlock][3 * NC + NF + NT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* zrow = sm[warp];
+    float* edges = zrow + NC;
+    float* cdf = edges + NC;
+    float* fine = cdf + NC;
+    float* merged = fine + NF;
+    const unsigned full = 0xffffffffu;
+    for (int64_t b = blockIdx.x * (int64_t)kWarpsPerBlock + warp; b < B; b += (int64_t)gridDim.x * kWarpsPerBlock) {
+        // ---- this lane's coarse samples and weights (NCL consecutive floats: one vector load each when NCL is 2 or 4)
+        float z[NCL + 1], w[NCL + 1];
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) { z[k] = __ldg(zc + b * NC + lane * NCL + k); w[k] = __ldg(w_c + b * NC + lane * NCL + k); }
+        z[NCL] = __shfl_down_sync(full, z[0], 1);                 // first sample of the next lane (unused on lane 31)
+        w[NCL] = __shfl_down_sync(full, w[0], 1);
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) zrow[lane * NCL + k] = z[k];
+        // ---- midpoints m_j = 0.5 (z_{j+1} + z_j), j < M  (:926) and the two before this lane's first
+        float m[NCL];
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) m[k] = 0.5f * (z[k + 1] + z[k]);
+        const float m_m1 = __shfl_up_sync(full, m[NCL - 1], 1);                                   // m_{j0-1}
+        const float m_m2 = NCL >= 2 ? __shfl_up_sync(full, m[NCL >= 2 ? NCL - 2 : 0], 1) : __shfl_up_sync(full, m[0], 2);   // m_{j0-2}
+        const float m_p1 = __shfl_down_sync(full, m[0], 1);                                       // m_{j0+NCL}
+        // ---- edges e_j, j = 0..M  (sampling_utils.py:24-33)
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) {
+            const int j = lane * NCL + k;
+            const float mj = m[k];
+            const float mjm1 = k >= 1 ? m[k >= 1 ? k - 1 : 0] : m_m1;
+            const float mjm2 = k >= 2 ? m[k >= 2 ? k - 2 : 0] : (k == 1 ? m_m1 : m_m2);
+            const float mjp1 = k + 1 < NCL ? m[k + 1 < NCL ? k + 1 : 0] : m_p1;
+            float e;
+            if (j == 0) e = mj - 0.5f * (mjp1 - mj);
+            else if (j == M) e = mjm1 + 0.5f * (mjm1 - mjm2);
+            else e = 0.5f * (mj + mjm1);
+            edges[j] = e;
+        }
+        // ---- pdf and cdf: weights_bins = 0.5 (w_{j+1} + w_j) + 1e-5 (:927-928), + 1e-5 and clamp (sampling_utils.py:38)
+        float pw[NCL], local = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) {
+            const int j = lane * NCL + k;
+            pw[k] = j < M ? fmaxf((0.5f * (w[k + 1] + w[k]) + 1e-5f) + 1e-5f, 0.0f) : 0.f;
+            local += pw[k];
+        }
+        const float wsum = warp_sum(local);                       // :39
+        float run_c = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) { pw[k] = run_c + pw[k] / wsum; run_c = pw[k]; }      // in-lane inclusive prefix of the pdf
+        float incl_c = run_c;                                     // :40 cumsum: one scan over the 32 lane totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_up_sync(full, incl_c, d);
+            if (lane >= d) incl_c += t;
+        }
+        const float excl_c = incl_c - run_c;
+        if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) {
+            const int j = lane * NCL + k;
+            if (j < M) cdf[j + 1] = excl_c + pw[k];
+        }
+        __syncwarp();
+        // ---- this lane's block of the sorted uniforms
+        float u[NFL];
+        if (deterministic) {
+#pragma unroll
+            for (int q = 0; q < NFL; ++q) u[q] = linspace01(lane * NFL + q, NF);                  // sampling_utils.py:44-46
+        } else {
+            // sorted iid uniforms = normalised partial sums of NF + 1 iid exponentials (order statistics of U[0,1))
+            const uint32_t key = hash_key(seed, offset, (uint64_t)b);
+            float ex[NFL], loc = 0.f;
+#pragma unroll
+            for (int q = 0; q < NFL; ++q) {
+                const uint32_t h = mix32(((uint32_t)b * (uint32_t)(NF + 1) + (uint32_t)(lane * NFL + q)) * 0x9E3779B1u + key);
+                ex[q] = -0.6931471805599453f * lg2_approx((float)((h >> 8) + 1u) * (1.0f / 16777216.0f));
+                loc += ex[q];
+            }
+            float tail = 0.f;
+            if (lane == 31) tail = -0.6931471805599453f *
+                                   lg2_approx((float)((mix32(((uint32_t)b * (uint32_t)(NF + 1) + (uint32_t)NF) * 0x9E3779B1u + key) >> 8) + 1u) * (1.0f / 16777216.0f));
+            float incl = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float t = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const float inv_total = 1.0f / __shfl_sync(full, incl + tail, 31);      // (one division per lane; any monotone scaling will do)
+            float run = __shfl_up_sync(full, incl, 1);
+            if (lane == 0) run = 0.f;
+#pragma unroll
+            for (int q = 0; q < NFL; ++q) { run = fminf(run + ex[q], incl); u[q] = fminf(run * inv_total, 1.0f); }
+        }
+        // ---- inverse CDF, rank among the coarse samples, scatter into the merged row
+#pragma unroll
+        for (int q = 0; q < NFL; ++q) {
+            const int s = lane * NFL + q;
+            int ind = 0;                                          // searchsorted(cdf, u, right=True) = #{cdf <= u}  (:51)
+#pragma unroll
+            for (int step = NC; step > 0; step >>= 1) {
+                const int mid = ind + step;
+                if (mid <= NC && cdf[mid - 1] <= u[q]) ind = mid;
+            }
+            const int below = min(max(ind - 1, 0), M), above = min(max(ind, 1), M);             // :52-53
+            const float c_lo = cdf[below], c_hi = cdf[above];
+            float denom = c_hi - c_lo;
+            if (denom < 1e-5f) denom = 1.0f;                      // :62
+            const float t = (u[q] - c_lo) / denom;
+            const float e_lo = edges[below], e_hi = edges[above];
+            const float zf = e_lo + t * (e_hi - e_lo);            // :64
+            fine[s] = zf;
+            if (z_fine) z_fine[b * NF + s] = zf;
+            int r = below;                                        // #{zc <= zf}: at most zc[below .. below+2] (see resample_merge_kernel)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r += (below + k < NC && zrow[min(below + k, NC - 1)] <= zf) ? 1 : 0;
+            if (r == below + 3) { while (r < NC && zrow[r] <= zf) ++r; }
+            merged[s + r] = zf;
+        }
+        __syncwarp();
+        // ---- coarse samples: position i + #{fine < zc[i]} (coarse first on ties)
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) {
+            int lo = 0;
+#pragma unroll
+            for (int step = NF; step > 0; step >>= 1) {
+                const int mid = lo + step;
+                if (mid <= NF && fine[mid - 1] < z[k]) lo = mid;
+            }
+            merged[lane * NCL + k + lo] = z[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NCL + NFL; ++t) z_all[b * NT + t * 32 + lane] = merged[t * 32 + lane];
+        __syncwarp();
+    }
+}
+
 static int grid_for_rays(int64_t B) {
     const int64_t want = cdiv(B, kWarpsPerBlock);
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -365,6 +517,26 @@ extern "C" int nsb_resample_merge(const float* zc, const float* w_c, const float
                                   void* stream) {
     if (B == 0) return NSB_OK;
     if (!zc || !w_c || !z_all || Nc < 2 || Nf < 1 || B < 0) return NSB_E_BADARG;
+    if ((deterministic || !u) && Nc % 32 == 0 && Nf % 32 == 0) {        // register-resident fast path for the shapes it is built for
+        const int ncl = Nc / 32, nfl = Nf / 32;
+        const int grid = grid_for_rays(B);
+        cudaStream_t st = as_stream(stream);
+        bool launched = true;
+#define NSB_RM_FAST(A, F)                                                                                                            \
+    else if (ncl == A && nfl == F)                                                                                                  \
+        resample_merge_fast_kernel<A, F><<<grid, kWarpsPerBlock * 32, 0, st>>>(zc, w_c, z_all, z_fine, B, deterministic, seed, offset, g_step_dev);
+        if (false) {}
+        NSB_RM_FAST(1, 2) NSB_RM_FAST(1, 4) NSB_RM_FAST(1, 8) NSB_RM_FAST(1, 16)
+        NSB_RM_FAST(2, 2) NSB_RM_FAST(2, 4) NSB_RM_FAST(2, 8) NSB_RM_FAST(2, 16)
+        NSB_RM_FAST(4, 2) NSB_RM_FAST(4, 4) NSB_RM_FAST(4, 8) NSB_RM_FAST(4, 16)
+        NSB_RM_FAST(8, 2) NSB_RM_FAST(8, 4) NSB_RM_FAST(8, 8) NSB_RM_FAST(8, 16)
+        else launched = false;
+#undef NSB_RM_FAST
+        if (launched) {
+            NSB_LAUNCH_CHECK("resample_merge_fast_kernel");
+            return NSB_OK;
+        }
+    }
     int sort_len = 32;
     while (sort_len < Nf) sort_len <<= 1;
     const size_t smem = (size_t)kWarpsPerBlock * (3 * Nc + sort_len + Nc + Nf) * sizeof(float);
