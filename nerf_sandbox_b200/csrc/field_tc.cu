@@ -1463,7 +1463,7 @@ struct WgradJob {
 constexpr int kMaxJobs = 16;
 struct WgradParams {
     const uint8_t* stash; const uint8_t* dstash; const float* d_raw; float* grads;
-    int64_t num_tiles, Q; int num_jobs; int dbg;
+    int64_t num_tiles, Q; int num_jobs; int dbg; int rev;
     WgradJob jobs[kMaxJobs];
 };
 constexpr int kWgPiece = 32768;                       // ring slot: one column half of a tile image
@@ -1541,7 +1541,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
         for (int64_t tile = part; tile < p.num_tiles; tile += job.cta_count) {
             for (int i = 0; i < job.n_pieces; ++i) {
                 const WgPiece& pc = job.pieces[i];
-                const uint8_t* src = pc.from_stash ? p.stash + (size_t)tile * kStashTile + pc.ofs : p.dstash + (size_t)tile * kDstashTile + pc.ofs;
+                // tiles are walked from the LAST one down: dgrad has just written the gradient stash front to back, so its tail (as much
+                // as the 126 MB L2 still holds) is read back without going to HBM
+                const int64_t pt = p.rev ? p.num_tiles - 1 - tile : tile;
+                const uint8_t* src = pc.from_stash ? p.stash + (size_t)pt * kStashTile + pc.ofs : p.dstash + (size_t)pt * kDstashTile + pc.ofs;
                 mbar_wait(bar_empty + 8 * slot, (round & 1) ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(bar_full + 8 * slot, pc.bytes);
@@ -1603,7 +1606,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) field_wgrad_kernel(const __grid
         auto load_dr = [&](int64_t tile, float4 (&dr)[4]) {
 #pragma unroll
             for (int rg = 0; rg < 4; ++rg) {
-                const int64_t q = tile * TILE_M + rg * 32 + lane;
+                const int64_t q = (p.rev ? p.num_tiles - 1 - tile : tile) * TILE_M + rg * 32 + lane;
                 dr[rg] = (tile < p.num_tiles && q < p.Q) ? __ldg(reinterpret_cast<const float4*>(p.d_raw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -1964,6 +1967,7 @@ int tc_field_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     }
     wp.num_jobs = nj;
     wp.dbg = getenv("NSB_WG_DBG") != nullptr;
+    { static const int rev = [] { const char* e = getenv("NSB_WG_REVERSE"); return (e && e[0] == '0') ? 0 : 1; }(); wp.rev = rev; }
     // CTAs per job: greedy min-max of (tiles per CTA) x (cycles per tile).  The per-tile cost is what the MMA thread of
     // each job kind was measured to take on B200 (scripts/perf_bwd.py with NSB_WG_DBG=1): an MN-major MMA costs
     // ~200-250 cycles whatever its N, so cost follows the instruction count more than the bytes.
