@@ -104,6 +104,14 @@ int nsb_composite_raw_bwd(const float* raw, const float* noise, float noise_std,
                           const float* ray_norm, const float* g_comp, float* d_raw, int64_t B, int N,
                           uint32_t flags, uint64_t seed, uint64_t offset, void* stream);
 
+/* nsb_composite_raw_bwd with the step's loss gradient formed in place (train/trainer.py:999-1004 + :717): instead of g_comp it
+ * takes target[B,3] and loss_scale = 2 * grad_scale / (3 * B_total), and uses dL/dcomp = (guard(comp) - guard(target)) *
+ * loss_scale on the composite it recomputes anyway (guard = nan_to_num(nan=0, posinf=1, neginf=0).clamp(0,1)) -- the MSE
+ * kernel then only produces the scalars and is off the step's critical path. */
+int nsb_composite_raw_bwd_mse(const float* raw, const float* noise, float noise_std, const float* z, const float* ray_norm,
+                              const float* target, float loss_scale, float* d_raw, int64_t B, int N, uint32_t flags,
+                              uint64_t seed, uint64_t offset, void* stream);
+
 /* Loss of Trainer._train_step, train/trainer.py:999-1006: guards + mse(comp_c)+mse(comp_f) and its
  * gradient.  scalars[4] = {loss, psnr, mse_c, mse_f} (device).  g_c/g_f[B,3] = dloss/dcomp * grad_scale.
  * comp_c may be NULL (coarse-only). */

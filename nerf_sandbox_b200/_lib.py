@@ -36,6 +36,7 @@ SIGNATURES = {
     "nsb_composite_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _u32, _f32, _p]),
     "nsb_composite_raw_fwd": (_i32, [_p, _p, _f32, _p, _p, _p, _p, _p, _p, _i64, _i32, _u32, _u64, _u64, _p]),
     "nsb_composite_raw_bwd": (_i32, [_p, _p, _f32, _p, _p, _p, _p, _i64, _i32, _u32, _u64, _u64, _p]),
+    "nsb_composite_raw_bwd_mse": (_i32, [_p, _p, _f32, _p, _p, _p, _f32, _p, _i64, _i32, _u32, _u64, _u64, _p]),
     "nsb_mse_loss": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _f32, _p]),
     "nsb_encode": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p]),
     "nsb_packed_weights_bytes": (_sz, []),

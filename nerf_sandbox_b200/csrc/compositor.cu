@@ -18,7 +18,7 @@ template <bool RAW>
 __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                                               const float* __restrict__ noise, float noise_std, bool add_noise,
                                               uint64_t seed, uint64_t offset, int64_t q, float* pre_out,
-                                              const float* pre_in = nullptr, bool softplus = false) {
+                                              const float* pre_in = nullptr, bool softplus = false, int64_t idx0 = 0) {
     Sample s;
     if (RAW) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(rgb_or_raw) + q);
@@ -27,7 +27,7 @@ __device__ __forceinline__ Sample load_sample(const float* __restrict__ rgb_or_r
         s.b = 1.0f / (1.0f + expf(-v.z));
         float pre = v.w;
         if (pre_in) pre = *pre_in;                            // reverse pass: noisy pre-activation kept from pass 1
-        else if (add_noise) pre += (noise ? noise[q] : hash_normal(seed, offset, (uint64_t)q)) * noise_std;   // :239-241
+        else if (add_noise) pre += (noise ? noise[q] : hash_normal(seed, offset, (uint64_t)(q + idx0))) * noise_std;   // :239-241
         if (pre_out) *pre_out = pre;
         // :243-246 relu, or F.softplus (beta = 1, threshold = 20: identity above it)
         s.sigma = softplus ? (pre > 20.0f ? pre : log1pf(expf(pre))) : fmaxf(pre, 0.0f);
@@ -60,13 +60,25 @@ __device__ __forceinline__ float finalize_color(float c) {   // :165 nan_to_num(
     return fminf(fmaxf(c, 0.0f), 1.0f);
 }
 
+// dL/dcomp of one channel: either handed in (g_comp), or the MSE term of the step's loss formed right here from the
+// recomputed composite and the target -- train/trainer.py:999-1004: mse(guard(comp), guard(target)), guard = nan_to_num(nan=0,
+// posinf=1, neginf=0).clamp(0,1); loss_scale = 2 * grad_scale / (3 B).  (The composite's own clamp mask is applied by the caller.)
+__device__ __forceinline__ float comp_grad(const float* __restrict__ g_comp, const float* __restrict__ target, float loss_scale, float craw,
+                                           int64_t i) {
+    if (!target) return __ldg(g_comp + i);
+    float t = __ldg(target + i);
+    if (isnan(t)) t = 0.0f;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    return (finalize_color(craw) - t) * loss_scale;
+}
+
 template <bool RAW>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                      const float* __restrict__ noise, float noise_std, const float* __restrict__ z,
                      const float* __restrict__ ray_norm, float* __restrict__ comp, float* __restrict__ weights,
                      float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N, uint32_t flags,
-                     float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+                     float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0) {
     if (step_dev) offset += 8 * *step_dev;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
@@ -84,7 +96,7 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             Sample s = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 zi = zrow[i];
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, nullptr, nullptr, softplus);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, nullptr, nullptr, softplus, idx0);
                 const float sdt = fminf(fmaxf(s.sigma * delta_at(zrow, i, N, inf_last, rn, has_rn), 0.0f), 60.0f);  // :144
                 alpha = 1.0f - expf(-sdt);                     // :145
                 f = (1.0f - alpha) + eps;                      // :149
@@ -122,7 +134,8 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
                      const float* __restrict__ g_weights, const float* __restrict__ g_acc,
                      const float* __restrict__ g_depth, float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma,
-                     int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+                     int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev,
+                     int64_t idx0, const float* __restrict__ target, float loss_scale) {
     if (step_dev) offset += 8 * *step_dev;
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,7 +159,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             if (valid) {
                 zi = zrow[i];
                 float pre1 = 0.f;
-                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre1, nullptr, softplus);
+                s = load_sample<RAW>(rgb_or_raw, sigma, noise, noise_std, add_noise, seed, offset, b * N + i, &pre1, nullptr, softplus, idx0);
                 if (RAW) s_pre[i] = pre1;
                 const float sdt = fminf(fmaxf(s.sigma * delta_at(zrow, i, N, inf_last, rn, has_rn), 0.0f), 60.0f);
                 alpha = 1.0f - expf(-sdt);
@@ -174,7 +187,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
             const float craw[3] = {sr + bg, sg + bg, sb + bg};
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? g_comp[b * 3 + c] : 0.0f;
+                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? comp_grad(g_comp, target, loss_scale, craw[c], b * 3 + c) : 0.0f;
         }
         const float inv = 1.0f / (acc + eps);
         const float gd = g_depth ? g_depth[b] : 0.0f;
@@ -268,7 +281,7 @@ template <bool RAW, int R, bool FULL>
 __device__ __forceinline__ float run_forward(RunSamples<RAW, R>& s, const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                                              const float* __restrict__ noise, float noise_std, bool add_noise, bool softplus,
                                              uint64_t seed, uint64_t offset, const float* __restrict__ zrow, int64_t q0, int start, int cnt,
-                                             int N, bool inf_last, float rn, bool has_rn, float eps) {
+                                             int N, bool inf_last, float rn, bool has_rn, float eps, int64_t idx0) {
     float4 v[R];
     float nz[R];
 #pragma unroll
@@ -287,11 +300,11 @@ __device__ __forceinline__ float run_forward(RunSamples<RAW, R>& s, const float*
     }
     const float z_next_lane = __shfl_down_sync(0xffffffffu, s.z[0], 1);      // first z of the next lane's run
     if (RAW && add_noise && !noise) {
-        const uint32_t key = hash_key(seed, offset, (uint64_t)q0);
+        const uint32_t key = hash_key(seed, offset, (uint64_t)(q0 + idx0));
 #pragma unroll
         for (int k = 0; k < R; k += 2) {
             float n0, n1;
-            hash_normal_pair(key, (uint32_t)(q0 + k), n0, n1);
+            hash_normal_pair(key, (uint32_t)(q0 + idx0 + k), n0, n1);
             nz[k] = n0;
             if (k + 1 < R) nz[k + 1] = n1;
         }
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(kRunWarps * 32)
 composite_fwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
                          float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, float* __restrict__ comp,
                          float* __restrict__ weights, float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N,
-                         uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+                         uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0) {
     if (step_dev) offset += 8 * *step_dev;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
@@ -345,7 +358,7 @@ composite_fwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
         const int64_t q0 = b * N + start;
         RunSamples<RAW, R> s;
         const float prod = run_forward<RAW, R, FULL>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
-                                               cnt, N, inf_last, rn, has_rn, eps);
+                                               cnt, N, inf_last, rn, has_rn, eps, idx0);
         const float incl = warp_scan_mul(prod, lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);                   // product over all earlier lanes' runs
         if (lane == 0) excl = 1.0f;
@@ -378,7 +391,8 @@ composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
                          float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
                          const float* __restrict__ g_weights, const float* __restrict__ g_acc, const float* __restrict__ g_depth,
                          float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma, int64_t B, int N, uint32_t flags, float eps,
-                         uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+                         uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0, const float* __restrict__ target,
+                         float loss_scale) {
     if (step_dev) offset += 8 * *step_dev;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
@@ -393,7 +407,7 @@ composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
         // ---- pass 1: forward recompute, everything about this lane's run stays in registers
         RunSamples<RAW, R> s;
         const float prod = run_forward<RAW, R, FULL>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
-                                               cnt, N, inf_last, rn, has_rn, eps);
+                                               cnt, N, inf_last, rn, has_rn, eps, idx0);
         float gwv[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) gwv[k] = (g_weights && (FULL || k < cnt)) ? __ldg(g_weights + q0 + k) : 0.0f;
@@ -419,7 +433,7 @@ composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
             const float craw[3] = {sr + bg, sg + bg, sb + bg};
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? __ldg(g_comp + b * 3 + c) : 0.0f;
+                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? comp_grad(g_comp, target, loss_scale, craw[c], b * 3 + c) : 0.0f;
         }
         const float inv = 1.0f / (acc + eps);
         const float gd = g_depth ? __ldg(g_depth + b) : 0.0f;
@@ -479,16 +493,16 @@ static int run_grid(int64_t B) {
 template <bool RAW>
 static int launch_fwd_run(const float* a, const float* sigma, const float* noise, float noise_std, const float* z, const float* rn,
                           float* comp, float* weights, float* acc, float* depth, int64_t B, int N, uint32_t flags, float eps, uint64_t seed,
-                          uint64_t off, void* stream) {
+                          uint64_t off, void* stream, int64_t idx0 = 0) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
     const int grid = run_grid(B);
 #define NSB_RUN_FWD(RR)                                                                                                              \
     case RR:                                                                                                                         \
         if (N == 32 * RR) composite_fwd_run_kernel<RAW, RR, true><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, \
-                                                                                                    acc, depth, B, N, flags, eps, seed, off, g_step_dev); \
+                                                                                                    acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0); \
         else composite_fwd_run_kernel<RAW, RR, false><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, \
-                                                                                        B, N, flags, eps, seed, off, g_step_dev);                 \
+                                                                                        B, N, flags, eps, seed, off, g_step_dev, idx0);           \
         break;
     switch (R) { NSB_RUN_FWD(1) NSB_RUN_FWD(2) NSB_RUN_FWD(3) NSB_RUN_FWD(4) NSB_RUN_FWD(5) NSB_RUN_FWD(6) NSB_RUN_FWD(7) NSB_RUN_FWD(8)
         default: return NSB_E_BADARG; }
@@ -500,16 +514,17 @@ static int launch_fwd_run(const float* a, const float* sigma, const float* noise
 template <bool RAW>
 static int launch_bwd_run(const float* a, const float* sigma, const float* noise, float noise_std, const float* z, const float* rn,
                           const float* g_comp, const float* g_w, const float* g_a, const float* g_d, float* d0, float* d1, int64_t B, int N,
-                          uint32_t flags, float eps, uint64_t seed, uint64_t off, void* stream) {
+                          uint32_t flags, float eps, uint64_t seed, uint64_t off, void* stream, int64_t idx0 = 0, const float* target = nullptr,
+                          float loss_scale = 0.f) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
     const int grid = run_grid(B);
 #define NSB_RUN_BWD(RR)                                                                                                             \
     case RR:                                                                                                                         \
         if (N == 32 * RR) composite_bwd_run_kernel<RAW, RR, true><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, \
-                                                                                                    g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev); \
+                                                                                                    g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale); \
         else composite_bwd_run_kernel<RAW, RR, false><<<grid, kRunWarps * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, \
-                                                                                        B, N, flags, eps, seed, off, g_step_dev);                  \
+                                                                                        B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale); \
         break;
     switch (R) { NSB_RUN_BWD(1) NSB_RUN_BWD(2) NSB_RUN_BWD(3) NSB_RUN_BWD(4) NSB_RUN_BWD(5) NSB_RUN_BWD(6) NSB_RUN_BWD(7) NSB_RUN_BWD(8)
         default: return NSB_E_BADARG; }
@@ -528,13 +543,13 @@ template <bool RAW>
 static int launch_bwd(const float* a, const float* sigma, const float* noise, float noise_std, const float* z,
                       const float* rn, const float* g_comp, const float* g_w, const float* g_a, const float* g_d,
                       float* d0, float* d1, int64_t B, int N, uint32_t flags, float eps, uint64_t seed, uint64_t off,
-                      void* stream) {
+                      void* stream, int64_t idx0 = 0, const float* target = nullptr, float loss_scale = 0.f) {
     const size_t smem = (size_t)kCompWarps * 3 * N * sizeof(float);
     if (smem > 200 * 1024) return NSB_E_BADARG;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(composite_bwd_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     composite_bwd_kernel<RAW><<<comp_grid(B), kCompWarps * 32, smem, as_stream(stream)>>>(
-        a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev);
+        a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
     NSB_LAUNCH_CHECK("composite_bwd_kernel");
     return NSB_OK;
 }
@@ -620,7 +635,7 @@ extern "C" int nsb_composite_fwd(const float* rgb, const float* sigma, const flo
     if (!rgb || !sigma || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     if (N <= kRunMaxN) return launch_fwd_run<false>(rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, stream);
     composite_fwd_kernel<false><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
-        rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, nullptr);
+        rgb, sigma, nullptr, 0.f, z, ray_norm, comp, weights, acc, depth, B, N, flags, eps, 0, 0, nullptr, 0);
     NSB_LAUNCH_CHECK("composite_fwd_kernel");
     return NSB_OK;
 }
@@ -638,17 +653,40 @@ extern "C" int nsb_composite_bwd(const float* rgb, const float* sigma, const flo
                              B, N, flags, eps, 0, 0, stream);
 }
 
-extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float noise_std, const float* z,
-                                     const float* ray_norm, float* comp, float* weights, float* acc, float* depth,
-                                     int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
+namespace nsb {
+// nsb_composite_raw_fwd on rays [b0, b0 + B) of a larger batch: idx0 = b0 * N shifts the index of the in-kernel noise draws, so
+// a batch processed in pieces draws the same numbers as the batch processed whole (engine.cu: half batches on two streams)
+int composite_raw_fwd_at(const float* raw, const float* noise, float noise_std, const float* z, const float* ray_norm, float* comp,
+                         float* weights, float* acc, float* depth, int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset,
+                         int64_t idx0, void* stream) {
     if (B == 0) return NSB_OK;
     if (!raw || !z || !comp || N < 1 || B < 0) return NSB_E_BADARG;
     if (N <= kRunMaxN)
-        return launch_fwd_run<true>(raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, stream);
+        return launch_fwd_run<true>(raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, stream,
+                                    idx0);
     composite_fwd_kernel<true><<<comp_grid(B), kCompWarps * 32, 0, as_stream(stream)>>>(
-        raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, g_step_dev);
+        raw, nullptr, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, 1e-10f, seed, offset, g_step_dev, idx0);
     NSB_LAUNCH_CHECK("composite_raw_fwd_kernel");
     return NSB_OK;
+}
+}  // namespace nsb
+
+extern "C" int nsb_composite_raw_fwd(const float* raw, const float* noise, float noise_std, const float* z,
+                                     const float* ray_norm, float* comp, float* weights, float* acc, float* depth,
+                                     int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset, void* stream) {
+    return composite_raw_fwd_at(raw, noise, noise_std, z, ray_norm, comp, weights, acc, depth, B, N, flags, seed, offset, 0, stream);
+}
+
+extern "C" int nsb_composite_raw_bwd_mse(const float* raw, const float* noise, float noise_std, const float* z, const float* ray_norm,
+                                         const float* target, float loss_scale, float* d_raw, int64_t B, int N, uint32_t flags,
+                                         uint64_t seed, uint64_t offset, void* stream) {
+    if (B == 0) return NSB_OK;
+    if (!raw || !z || !target || !d_raw || N < 1 || B < 0) return NSB_E_BADARG;
+    if (N <= kRunMaxN)
+        return launch_bwd_run<true>(raw, nullptr, noise, noise_std, z, ray_norm, nullptr, nullptr, nullptr, nullptr, d_raw, nullptr, B, N, flags,
+                                    1e-10f, seed, offset, stream, 0, target, loss_scale);
+    return launch_bwd<true>(raw, nullptr, noise, noise_std, z, ray_norm, nullptr, nullptr, nullptr, nullptr, d_raw, nullptr, B, N, flags, 1e-10f,
+                            seed, offset, stream, 0, target, loss_scale);
 }
 
 extern "C" int nsb_composite_raw_bwd(const float* raw, const float* noise, float noise_std, const float* z,

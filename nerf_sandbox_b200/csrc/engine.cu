@@ -42,6 +42,7 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
 size_t tc_workspace_bytes(int64_t Q, int stash);
 size_t tc_stash_tile_bytes();
 thread_local const uint64_t* g_step_dev = nullptr;
+thread_local uint64_t* g_pack_counter = nullptr;      // nsb_train_step: step counter the next tc_pack launch increments when it is done
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, bool train_only, cudaStream_t st);
 int tc_field_fwd_rays(const float*, const float*, const float*, const float*, const float*, const void* packed,
                       float* raw, void* ws, int64_t B, int N, int stash, cudaStream_t st);
@@ -59,6 +60,9 @@ static bool fp32_eval_on_tc() {
     return on;
 }
 
+int composite_raw_fwd_at(const float* raw, const float* noise, float noise_std, const float* z, const float* ray_norm, float* comp,
+                         float* weights, float* acc, float* depth, int64_t B, int N, uint32_t flags, uint64_t seed, uint64_t offset,
+                         int64_t idx0, void* stream);
 int tc_debug_layer(const float*, const float*, const float*, const float*, const float*, const void*, float*, float*, int,
                    int64_t, int, cudaStream_t);
 
@@ -239,22 +243,22 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
         NSB_TRY(nsb_stratified_z(zc, opt(U, b0 * Nc), nb, Nc, near_, far_, 1, seed, s_jit + sid, strm));                     // trainer.py:901-908
         NSB_TRY(nsb_field_fwd_rays(rays_o + 3 * b0, rays_d + 3 * b0, zc, rn, vd, packed_c, raw_c, static_cast<char*>(t.field_c) + off_c,
                                    t.field_c_bytes - off_c, nb, Nc, mode, 1, strm));
-        NSB_TRY(nsb_composite_raw_fwd(raw_c, opt(noise_c, b0 * Nc), noise_std, zc, rn, t.comp_c + 3 * b0, w_c, nullptr, nullptr, nb, Nc, f,
-                                      seed, s_nc + sid, strm));                                                              // :911-923
+        // (sigma-noise draws are indexed by the sample's position in the WHOLE batch: the backward regenerates them in one launch)
+        NSB_TRY(composite_raw_fwd_at(raw_c, opt(noise_c, b0 * Nc), noise_std, zc, rn, t.comp_c + 3 * b0, w_c, nullptr, nullptr, nb, Nc, f,
+                                     seed, s_nc, b0 * Nc, strm));                                                            // :911-923
         NSB_TRY(nsb_resample_merge(zc, w_c, opt(u_fine, b0 * Nf), z_all, nullptr, nb, Nc, Nf, det_fine, seed, s_u + sid, strm));   // :926-934, :981
         NSB_TRY(nsb_field_fwd_rays(rays_o + 3 * b0, rays_d + 3 * b0, z_all, rn, vd, packed_f, raw_f, static_cast<char*>(t.field_f) + off_f,
                                    t.field_f_bytes - off_f, nb, Nt, mode, 1, strm));
-        return nsb_composite_raw_fwd(raw_f, opt(noise_f, b0 * Nt), noise_std, z_all, rn, t.comp_f + 3 * b0, nullptr, nullptr, nullptr, nb, Nt,
-                                     f, seed, s_nf + sid, strm);                                                             // :984-996
+        return composite_raw_fwd_at(raw_f, opt(noise_f, b0 * Nt), noise_std, z_all, rn, t.comp_f + 3 * b0, nullptr, nullptr, nullptr, nb, Nt,
+                                    f, seed, s_nf, b0 * Nt, strm);                                                           // :984-996
     };
-    // d raw of rays [b0, b0 + nb) from the composite gradients (regenerates the same noise as `forward`)
-    auto composite_bwd = [&](int64_t b0, int64_t nb, uint64_t sid, bool fine, void* strm) -> int {
-        const float* rn = ray_norm ? ray_norm + b0 : nullptr;
+    // d raw of the whole batch straight from the target: the MSE gradient (:999-1004) is formed inside the compositor's backward
+    // from the composite it recomputes anyway, so the loss kernel (scalars only) is off the critical path
+    const float loss_scale = 2.0f * grad_scale / (3.0f * (float)B);
+    auto composite_bwd = [&](bool fine, void* strm) -> int {
         if (fine)
-            return nsb_composite_raw_bwd(t.raw_f + 4 * b0 * Nt, noise_f ? noise_f + b0 * Nt : nullptr, noise_std, t.z_all + b0 * Nt, rn,
-                                         t.g_f + 3 * b0, t.d_raw + 4 * b0 * Nt, nb, Nt, f, seed, s_nf + sid, strm);
-        return nsb_composite_raw_bwd(t.raw_c + 4 * b0 * Nc, noise_c ? noise_c + b0 * Nc : nullptr, noise_std, t.zc + b0 * Nc, rn,
-                                     t.g_c + 3 * b0, t.d_raw_c + 4 * b0 * Nc, nb, Nc, f, seed, s_nc + sid, strm);
+            return nsb_composite_raw_bwd_mse(t.raw_f, noise_f, noise_std, t.z_all, ray_norm, target, loss_scale, t.d_raw, B, Nt, f, seed, s_nf, strm);
+        return nsb_composite_raw_bwd_mse(t.raw_c, noise_c, noise_std, t.zc, ray_norm, target, loss_scale, t.d_raw_c, B, Nc, f, seed, s_nc, strm);
     };
     // Two half batches on two streams (tensor-core mode): each persistent field kernel ends with a partly filled round of
     // tiles (e.g. 768 tile pairs on 148 SMs = 5.19 rounds); with the other half's kernels in flight those SMs are not idle.
@@ -273,17 +277,15 @@ extern "C" int nsb_train_fwd_bwd(const float* rays_o, const float* rays_d, const
     } else {
         NSB_TRY(forward(0, B, 0, stream));
     }
-    // loss (:999-1006) and backward (:717)
-    NSB_TRY(nsb_mse_loss(t.comp_c, t.comp_f, target, t.g_c, t.g_f, scalars, B, grad_scale, stream));
-    // The two backward chains are independent (coarse weights only feed the detached resampling), so the coarse one runs on
-    // the side stream forked here and joined below: its CTAs fill the SMs the fine kernels leave idle in their last round.
-    // Fork/join through events, so the sequence stays graph-capturable.
+    // loss (:999-1006) and backward (:717).  The two backward chains are independent (coarse weights only feed the detached
+    // resampling), so the coarse one runs on the side stream forked here and joined below: its CTAs fill the SMs the fine kernels
+    // leave idle in their last round.  The loss scalars are computed at the head of the side stream.  Fork/join through events,
+    // so the sequence stays graph-capturable.
     if (side && !fork()) return NSB_E_CUDA;
-    if (split) { NSB_TRY(composite_bwd(0, hb, 0, true, stream)); NSB_TRY(composite_bwd(hb, hb, sid1, true, stream)); }
-    else NSB_TRY(composite_bwd(0, B, 0, true, stream));
+    NSB_TRY(composite_bwd(true, stream));
     NSB_TRY(nsb_field_bwd(t.d_raw, packed_f, grads_f, t.field_f, t.field_f_bytes, Qf, mode, stream));
-    if (split) { NSB_TRY(composite_bwd(0, hb, 0, false, sstream)); NSB_TRY(composite_bwd(hb, hb, sid1, false, sstream)); }
-    else NSB_TRY(composite_bwd(0, B, 0, false, sstream));
+    NSB_TRY(nsb_mse_loss(t.comp_c, t.comp_f, target, nullptr, nullptr, scalars, B, grad_scale, sstream));
+    NSB_TRY(composite_bwd(false, sstream));
     NSB_TRY(nsb_field_bwd(t.d_raw_c, packed_c, grads_c, t.field_c, t.field_c_bytes, Qc, mode, sstream));
     if (side && !join()) return NSB_E_CUDA;
     if (comp_c && cudaMemcpyAsync(comp_c, t.comp_c, B * 12, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return NSB_E_CUDA;
@@ -337,9 +339,14 @@ extern "C" int nsb_train_step(const float* rays_o, const float* rays_d, const fl
                                     lr_eta_min, lr_T_max, nullptr, nullptr, nullptr, nullptr, scalars, stream));
     }
     const float* cparams[2] = {params[0], params[1]};
-    NSB_TRY(nsb_pack_weights_batch(cparams, packed, 2, mode | NSB_PACK_TRAIN_ONLY, stream));      // inference images: on demand
-    counter_inc_kernel<<<1, 32, 0, as_stream(stream)>>>(step_counter);
-    NSB_LAUNCH_CHECK("counter_inc_kernel");
+    g_pack_counter = mode == NSB_MODE_BF16 ? step_counter : nullptr;      // the tensor-core pack kernel increments it as its last act
+    rc = nsb_pack_weights_batch(cparams, packed, 2, mode | NSB_PACK_TRAIN_ONLY, stream);           // inference images: on demand
+    g_pack_counter = nullptr;
+    if (rc) return rc;
+    if (mode != NSB_MODE_BF16) {
+        counter_inc_kernel<<<1, 32, 0, as_stream(stream)>>>(step_counter);
+        NSB_LAUNCH_CHECK("counter_inc_kernel");
+    }
     return NSB_OK;
 }
 

@@ -1732,8 +1732,11 @@ __device__ __forceinline__ void pack_tc_transposed(const float* __restrict__ par
 }
 // one launch packs every image of up to four nets: blockIdx.y = forward layer 0..9 (bf16) | 10 + dgrad step 0..8 |
 // 19 + forward layer 0..9 (fp16 = split high halves) | 29 + forward layer 0..9 (split low halves), blockIdx.z = net
-struct PackBatch { const float* params[4]; uint8_t* out[4]; };
+struct PackBatch { const float* params[4]; uint8_t* out[4]; uint64_t* counter; };
 __global__ void pack_tc_kernel(const PackBatch b) {
+    // last kernel of a replayed training step: bump the device-side step counter (nothing else in this launch reads it, every
+    // reader of the next replay starts after this kernel)
+    if (b.counter && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *b.counter += 1;
     const float* params = b.params[blockIdx.z];
     uint8_t* out = b.out[blockIdx.z];
     if (blockIdx.y < kNumMmaLayers) pack_tc_forward<0>(params, out, blockIdx.y);
@@ -1757,6 +1760,7 @@ static inline uint8_t* ws_dstash(void* ws, int64_t Q) { return ws_stash(ws) + (s
 int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, bool train_only, cudaStream_t st) {
     tc::PackBatch b{};
     for (int i = 0; i < n_nets; ++i) { b.params[i] = params[i]; b.out[i] = reinterpret_cast<uint8_t*>(packed_bf16[i]); }
+    b.counter = g_pack_counter;
     // blockIdx.y: [0,19) = the training images (bf16 forward + transposed), [19,39) = the inference-only fp16 hi / lo images
     const int ny = train_only ? tc::kNumMmaLayers + tc::kNumDgradLayers : 3 * tc::kNumMmaLayers + tc::kNumDgradLayers;
     tc::pack_tc_kernel<<<dim3(32, ny, n_nets), 256, 0, st>>>(b);

@@ -13,6 +13,7 @@ int check_launch(const char* what);  // cudaGetLastError -> NSB_E_CUDA
 // Device-resident step counter of the call in progress (nsb_train_step only, else null): kernels that draw random numbers
 // shift their Philox stream by 8 * (*g_step_dev), so a captured CUDA graph draws fresh numbers on every replay.
 extern thread_local const uint64_t* g_step_dev;
+extern thread_local uint64_t* g_pack_counter;
 int num_sms();
 
 #define NSB_LAUNCH_CHECK(name)                        \
