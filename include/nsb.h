@@ -190,7 +190,7 @@ int nsb_grad_clip(float* grads, int64_t n, float max_norm, float pre_scale, floa
  * mc_grads alone every rank pulls the whole reduced buffer, i.e. every GPU's buffer is read `world` times by the switch;
  * here rank r reduces only its 1/world slice and multicast-stores it (`multimem.st`) into every rank's reduced-gradient
  * buffer -- mc_reduced = multicast address, reduced = this rank's own copy, both n_nets * n floats of symmetric memory --,
- * a second flag round follows, and Adam runs on the local copy (two launches).  local_sync: 2 device ints of this rank,
+ * a second flag round follows, and Adam runs on the local copy (two launches).  local_sync: 4 device ints of this rank,
  * zeroed once.  The flag blocks then hold uint32[4 * world].
  * loss_guard [opt]: this rank's loss (device); a non-finite loss on ANY rank makes EVERY rank skip the update
  * (train/trainer.py:713-716, made collective so the replicas stay identical). */

@@ -621,7 +621,8 @@ struct AdamArParams {
     const float* mc_grads;                  // multicast address of the same buffers (NVLS), or null
     float* mc_red;                          // two-phase NVLS exchange: multicast address of the REDUCED-gradient buffers, or null
     const float* red;                       // ... this rank's reduced-gradient buffer (n_nets * n floats)
-    int* local_sync;                        // ... device ints of this rank: [0] finished-block counter, [1] epoch whose update is skipped
+    int* local_sync;                        // ... device ints of this rank: [0] finished-block counter, [1] epoch whose update is
+                                            //     skipped, [2] epoch in which a peer timed out (4 ints, zeroed once)
     uint32_t* flags[kMaxPeers];             // every rank's flag block, uint32[world]
     int rank, world, n_nets; uint32_t epoch;
     int64_t n; float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, grad_scale;
@@ -745,9 +746,9 @@ __device__ __forceinline__ bool wait_peer_flags(const AdamArParams& a, int base,
 __global__ void __launch_bounds__(256) grad_reduce_scatter_kernel(const __grid_constant__ AdamArParams a) {
     const int world = a.world;
     const uint32_t epoch = a.t_dev ? (uint32_t)(*a.t_dev + 1) : a.epoch;
-    __shared__ int s_abort;
+    __shared__ int s_abort, s_timeout;       // s_abort: skip this epoch's update; s_timeout: ... because a peer never arrived
     const uint32_t bad = (a.loss_guard && !isfinite(*a.loss_guard)) ? 1u : 0u;
-    if (threadIdx.x == 0) s_abort = 0;
+    if (threadIdx.x == 0) { s_abort = 0; s_timeout = 0; }
     __syncthreads();
     if (threadIdx.x < world) {
         const int r = threadIdx.x;
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(256) grad_reduce_scatter_kernel(const __grid_c
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(epoch) : "memory");
         }
-        if (!wait_peer_flags(a, 0, r, epoch)) s_abort = 1;
+        if (!wait_peer_flags(a, 0, r, epoch)) { s_abort = 1; s_timeout = 1; }
         uint32_t peer_bad;
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(peer_bad) : "l"(a.flags[a.rank] + bad_ofs + r) : "memory");
         if (peer_bad) s_abort = 1;
@@ -774,11 +775,13 @@ __global__ void __launch_bounds__(256) grad_reduce_scatter_kernel(const __grid_c
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_abort) atomicExch(&a.local_sync[1], (int)epoch);        // kernel 2 of this epoch skips the update
+        if (s_timeout) atomicExch(&a.local_sync[2], (int)epoch);      // a slice that was never reduced must not be announced
         if (atomicAdd(&a.local_sync[0], 1) == (int)gridDim.x - 1) {   // last block of this rank: publish "my slice is stored"
             a.local_sync[0] = 0;
             __threadfence_system();
-            for (int r = 0; r < world; ++r)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + 3 * world + a.rank), "r"(epoch) : "memory");
+            if (*reinterpret_cast<volatile int*>(a.local_sync + 2) != (int)epoch)      // (after a timeout the peers time out too: all raise)
+                for (int r = 0; r < world; ++r)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + 3 * world + a.rank), "r"(epoch) : "memory");
         }
     }
 }

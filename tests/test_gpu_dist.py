@@ -99,7 +99,28 @@ out = D.render_image_sharded(*args, H, W, 2.0, 6.0, tr.nerf_c, tr.nerf_f, 64, 12
                              viewdirs_world_unit=T(rays["rays_d_world_unit"]))
 rgb, acc, depth = nsb.render_rays(*args, T(rays["rays_d_world_unit"]), tr.nerf_c, tr.nerf_f, near=2.0, far=6.0, nc=64, nf=128, white_bkgd=True)
 assert torch.equal(out["rgb"].reshape(-1, 3), rgb) and torch.equal(out["depth"].reshape(-1), depth)
-dist.barrier(); dist.destroy_process_group()
+dist.barrier()
+if os.environ.get("NSB_TEST_TIMEOUT") == "1":
+    # a peer that never arrives: the waiting ranks skip the update after NSB_PEER_TIMEOUT_S, stay alive (no trap) and raise on
+    # the host from check_peers(); the late rank finds everyone's flags and completes normally
+    import time
+    before = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()]).clone()
+    rays = {k: T(v) for k, v in O.synthetic_rays(np.random.default_rng(999), 256).items()}
+    if rank == world - 1:
+        time.sleep(float(os.environ["NSB_PEER_TIMEOUT_S"]) + 4.0)
+    tr.step(rays)
+    torch.cuda.synchronize()
+    after = torch.cat([tr.nerf_c.flat_params(), tr.nerf_f.flat_params()])
+    if rank != world - 1:
+        assert torch.equal(before, after), "a timed-out exchange must skip the update"
+        try:
+            tr.check_peers(); raise SystemExit("check_peers() did not raise")
+        except RuntimeError as e:
+            assert "timed out" in str(e), e
+        x = torch.ones(4, device=dev) * 2; assert float(x.sum()) == 8.0          # the context is still usable
+    print("rank", rank, "timeout path ok", flush=True)
+    os._exit(0)                                  # the ranks are out of step now: no collective teardown
+dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
 
@@ -109,6 +130,8 @@ def test_two_gpu_training_and_tiled_eval(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, NSB_ROOT=ROOT)
+    if env.get("NSB_TEST_TIMEOUT") == "1":
+        env.setdefault("NSB_PEER_TIMEOUT_S", "15")
     nproc = os.environ.get("NSB_TEST_NPROC", "2")            # e.g. 8 on a full node (NVLS path: NSB_NVLS=1 or >= 4 ranks)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", nproc, "--master-addr",
                         "127.0.0.1", "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
