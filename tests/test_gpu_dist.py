@@ -118,6 +118,7 @@ if os.environ.get("NSB_TEST_TIMEOUT") == "1":
         except RuntimeError as e:
             assert "timed out" in str(e), e
         x = torch.ones(4, device=dev) * 2; assert float(x.sum()) == 8.0          # the context is still usable
+        time.sleep(12.0)             # keep this rank's symmetric buffers alive until the late rank has finished reading them
     print("rank", rank, "timeout path ok", flush=True)
     os._exit(0)                                  # the ranks are out of step now: no collective teardown
 dist.destroy_process_group()
