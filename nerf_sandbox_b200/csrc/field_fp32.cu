@@ -157,20 +157,6 @@ __global__ void prepare_from_enc_kernel(const float* __restrict__ enc_pos, const
 // SGEMM  C[m,n] = sum_k A(m,k) * B(n,k)
 // ---------------------------------------------------------------------------------------------------
 constexpr int BM = 128, BN = 128, BK = 16, PITCH = 132;
-enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
-
-struct GemmArgs {
-    const float* A; int64_t lda;
-    const float* B; int64_t ldb;
-    float* C; int64_t ldc;
-    int64_t Mdim, Ndim, Kdim;           // Kdim = contraction length
-    const float* bias; int relu;        // FWD
-    const float* mask; int64_t ldm;     // DGRAD: multiply by (mask > 0)
-    const float* addend; int64_t ldadd; // DGRAD: += addend
-    int n_valid;                        // WGRAD: columns < n_valid are written
-    int64_t k_per_split;                // WGRAD: contraction rows per blockIdx.z
-};
-
 template <bool T>
 __device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t rows,
                                           int64_t k0, int64_t kend, int tid, float4 (&reg)[2]) {
@@ -434,11 +420,19 @@ static inline const float* PB(const void* packed, const PackedLayout& L, int l) 
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + L.f32_b[l]);
 }
 
+// The layer GEMMs run on the tensor cores with bf16-split operands (field_split.cu); NSB_FP32_GEMM=ffma keeps the FFMA tiles
+// of this file (the round-1 path, kept as the cross-check the split path is measured against).
+static bool gemm_on_tc() {
+    static const bool tc = [] { const char* e = getenv("NSB_FP32_GEMM"); return !(e && e[0] == 'f'); }();
+    return tc;
+}
+
 static int gemm_fwd(const float* X, int64_t ldx, const float* W, int Kpad, const float* bias, float* Y, int64_t ldy,
                     int64_t Q, int N, int relu, cudaStream_t st) {
     GemmArgs g{};
     g.A = X; g.lda = ldx; g.B = W; g.ldb = Kpad; g.C = Y; g.ldc = ldy; g.Mdim = Q; g.Ndim = N; g.Kdim = Kpad;
     g.bias = bias; g.relu = relu;
+    if (gemm_on_tc()) return split_gemm(g, EPI_FWD, st);
     dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(N, BN), 1);
     sgemm_kernel<false, false, EPI_FWD><<<grid, 256, 0, st>>>(g);
     NSB_LAUNCH_CHECK("sgemm_fwd");
@@ -451,6 +445,7 @@ static int gemm_dgrad(const float* dY, int64_t ldy, const float* W, int ldw, flo
     GemmArgs g{};
     g.A = dY; g.lda = ldy; g.B = W; g.ldb = ldw; g.C = dX; g.ldc = ldx; g.Mdim = Q; g.Ndim = n_in; g.Kdim = n_out;
     g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd;
+    if (gemm_on_tc()) return split_gemm(g, EPI_DGRAD, st);
     dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(n_in, BN), 1);
     sgemm_kernel<false, true, EPI_DGRAD><<<grid, 256, 0, st>>>(g);
     NSB_LAUNCH_CHECK("sgemm_dgrad");
@@ -462,16 +457,20 @@ static int gemm_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx,
     GemmArgs g{};
     g.A = dY; g.lda = ldy; g.B = X; g.ldb = ldx; g.C = gW; g.ldc = K; g.Mdim = n_out; g.Ndim = Kpad; g.Kdim = Q;
     g.n_valid = K;
-    const int tiles = (int)(cdiv(n_out, BM) * cdiv(Kpad, BN));
-    int64_t splits = (int64_t)num_sms() * 2 / tiles;
-    if (splits < 1) splits = 1;
-    int64_t kps = cdiv(cdiv(Q, splits), BK) * BK;
-    if (kps < 256) kps = 256;
-    splits = cdiv(Q, kps);
-    g.k_per_split = kps;
-    dim3 grid((unsigned)cdiv(n_out, BM), (unsigned)cdiv(Kpad, BN), (unsigned)splits);
-    sgemm_kernel<true, true, EPI_WGRAD><<<grid, 256, 0, st>>>(g);
-    NSB_LAUNCH_CHECK("sgemm_wgrad");
+    if (gemm_on_tc()) {
+        NSB_TRY(split_gemm(g, EPI_WGRAD, st));
+    } else {
+        const int tiles = (int)(cdiv(n_out, BM) * cdiv(Kpad, BN));
+        int64_t splits = (int64_t)num_sms() * 2 / tiles;
+        if (splits < 1) splits = 1;
+        int64_t kps = cdiv(cdiv(Q, splits), BK) * BK;
+        if (kps < 256) kps = 256;
+        splits = cdiv(Q, kps);
+        g.k_per_split = kps;
+        dim3 grid((unsigned)cdiv(n_out, BM), (unsigned)cdiv(Kpad, BN), (unsigned)splits);
+        sgemm_kernel<true, true, EPI_WGRAD><<<grid, 256, 0, st>>>(g);
+        NSB_LAUNCH_CHECK("sgemm_wgrad");
+    }
     // enough blocks to fill the GPU (4 per SM): at 2048 rows per block a 196,608-point pass launched 96 blocks -- less than
     // one wave -- and the bias grads cost more than any SGEMM of the step
     int64_t rpb = cdiv(Q, (int64_t)num_sms() * 4);

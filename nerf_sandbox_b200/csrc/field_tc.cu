@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <mutex>
 #include "nsb_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace nsb {
 namespace tc {
@@ -81,183 +82,6 @@ __host__ __device__ inline int layer_nslabs(int l) { return l == 0 ? 2 : (l == 4
 __host__ __device__ inline int layer_N(int l) { return l == 9 ? 128 : 256; }
 __host__ __device__ inline int layer_bias_ofs(int l) { return l * 256; }
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded spin: a protocol bug traps (kills this context) instead of hanging the GPU
-__device__ __forceinline__ uint64_t global_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    // the timer is read only every 4096 polls: %globaltimer is slow to read and would add its latency to every wake-up
-    uint64_t t0 = 0;
-    for (uint32_t i = 1; !mbar_try_wait(bar, parity); ++i) {
-        if (i & 0xFFFu) continue;
-        if (t0 == 0) { t0 = global_ns(); continue; }
-        if (global_ns() - t0 > 2000000000ull) {   // 2 s
-            printf("nsb tc: mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
-}
-// wait and add the waited cycles to `acc` (profiling aid; acc may be ignored by the optimiser when cyc == null)
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
-// one lane of a converged warp (ptxas then knows a single thread issues and drops the per-lane waterfall)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-// descriptor = constant high word (LBO, SBO, version) | 14-bit start address
-__device__ __forceinline__ uint64_t desc_hi(uint32_t lbo, uint32_t sbo) {
-    return ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ uint64_t desc_at(uint64_t hi, uint32_t saddr) { return hi | (uint64_t)((saddr & 0x3FFFFu) >> 4); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ---- CTA pair (cta_group::2): one MMA spans the two SMs of a cluster -- M = 256 = the 128-row tiles of both CTAs, each
-// CTA holds half of the B operand (N/2 weight rows), accumulators land in each CTA's own TMEM.  Only the leader
-// (cluster rank 0) issues; commits are multicast to the barriers at the same offset in both CTAs.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit2(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-// Half-slab load of a CTA pair: a 2-D tiled TMA copy (rows of 256 B of the packed buffer) into THIS CTA's ring stage whose
-// complete_tx is delivered to the barrier at the same offset in the LEADER CTA (.cta_group::2 allows the remote barrier), so
-// the leader's MMA thread sees both halves of a slab on one barrier and nobody has to relay the peer's arrival.
-__device__ __forceinline__ void tma_load_rows_to_leader(uint32_t dst, const CUtensorMap* tm, uint32_t row, uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .b32 lb;\n\tmapa.shared::cluster.u32 lb, %2, 0;\n\t"
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [lb];\n\t}" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(0u), "r"(row)
-        : "memory");
-}
-// arrive on the barrier at the same offset in CTA `cta` of the cluster.  Default semantics on purpose: an explicit
-// .release.cluster made every arrive cost ~1000 cycles (measured: the relay thread spent >90 % of its time in it); what
-// the arrive publishes was written by the TMA engine / fenced for the async proxy before the relay observed it.
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
-                 "r"(cta)
-                 : "memory");
-}
-// wait on a barrier that a peer CTA arrives on (acquire at cluster scope)
-__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __noinline__ void mbar_wait_cl_slow(uint32_t bar, uint32_t parity) {
-    uint64_t t0 = 0;
-    for (uint32_t i = 1; !mbar_try_wait_cl(bar, parity); ++i) {
-        if (i & 0xFFFu) continue;
-        if (t0 == 0) { t0 = global_ns(); continue; }
-        if (global_ns() - t0 > 2000000000ull) {
-            printf("nsb tc: cluster mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
-    if (!mbar_try_wait_cl(bar, parity)) mbar_wait_cl_slow(bar, parity);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-// compiler-level dependency: uses of v[] may not be scheduled above this point (placed right after tcgen05.wait::ld)
-__device__ __forceinline__ void pin16(uint32_t (&v)[16]) {
-    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                      "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :
-                 : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
-// core matrix = 8 rows x 16 bytes; SBO = byte stride between 8-row groups; LBO = byte stride between the
-// two 8-element K chunks of one K=16 MMA.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
 // Number formats (instruction-descriptor bits [7,10) = A, [10,13) = B: 0 = f16, 1 = bf16; accumulation is fp32 throughout).
 //  * INFERENCE forward (no stash: eval frames, no-grad passes): fp16 operands -- weights, gamma(x), gamma(d), activations.
 //    11 significant bits, what the reference computes in under its CUDA autocast (utils/render_utils.py:334-335), 8x finer

@@ -145,6 +145,24 @@ __host__ __device__ inline LayerDesc layer_desc(int l) {
     return d;
 }
 
+// One layer GEMM of the fp32 mode, C[m,n] = sum_k A(m,k) * B(n,k), with the epilogue of its role (field_fp32.cu: FFMA
+// tiles; field_split.cu: the same contract on the tensor cores with bf16-split operands).
+// AT = false: A stored [m][k] (k contiguous), AT = true: A stored [k][m]; same for BT and B.
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
+struct GemmArgs {
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    int64_t Mdim, Ndim, Kdim;           // Kdim = contraction length
+    const float* bias; int relu;        // FWD
+    const float* mask; int64_t ldm;     // DGRAD: multiply by (mask > 0)
+    const float* addend; int64_t ldadd; // DGRAD: += addend
+    int n_valid;                        // WGRAD: columns < n_valid are written
+    int64_t k_per_split;                // WGRAD: contraction rows per split
+};
+// field_split.cu: role = EPI_* (FWD: A, B k-contiguous; DGRAD: B stored [k][n]; WGRAD: both stored [k][.], split-K with atomics)
+int split_gemm(const GemmArgs& g, int role, cudaStream_t st);
+
 // Packed weights of one net (nsb_pack_weights): [fp32 padded section | bf16 tensor-core section]
 struct PackedLayout {
     size_t f32_w[12], f32_b[12];   // byte offsets; rows padded to Kpad floats

@@ -72,6 +72,35 @@ def grad_probe(net, idx):
     return N(flat)[idx], norms
 
 
+def remove_relu_knife_edges(x, p, pos_enc, enc_dir, rel=2e-6):
+    """A pre-activation of a ReLU layer whose magnitude is below the fp32 rounding error of its own dot product (|pre| < rel * sum|terms|)
+    has no defined sign for an fp32 implementation: the reference, an FFMA GEMM and a tensor-core GEMM may each land on either
+    side, and the ReLU mask flips the gradient of everything upstream (the first version of this fixture had one: layer 6,
+    point 158, unit 29, pre = 3.6e-7 against sum|terms| = 8.5).  Such points are moved (scaled by 0.97, no random draw, so
+    the fixtures generated after this one are unchanged) until none is left; checked in float64 with the fixture's weights."""
+    x = x.copy()
+    for _ in range(100):
+        e = N(pos_enc(T(x))).astype(np.float64)
+        h = e
+        bad = np.zeros(len(x), dtype=bool)
+        for l in range(8):
+            W = p[f"mlp.{l}.weight"].astype(np.float64); b = p[f"mlp.{l}.bias"].astype(np.float64)
+            if l == 4:
+                h = np.concatenate([h, e], -1)
+            pre = h @ W.T + b
+            scale = np.abs(h) @ np.abs(W).T + np.abs(b)
+            bad |= (np.abs(pre) < rel * scale).any(-1)
+            h = np.maximum(pre, 0)
+        feat = h @ p["feature.weight"].astype(np.float64).T + p["feature.bias"].astype(np.float64)
+        hc = np.concatenate([feat, np.broadcast_to(enc_dir.astype(np.float64), (len(x), enc_dir.shape[-1]))], -1)
+        Wc = p["color_fc.weight"].astype(np.float64); bc = p["color_fc.bias"].astype(np.float64)
+        bad |= (np.abs(hc @ Wc.T + bc) < rel * (np.abs(hc) @ np.abs(Wc).T + np.abs(bc))).any(-1)
+        if not bad.any():
+            return x
+        x[bad] *= np.float32(0.97)
+    raise RuntimeError("could not remove the ReLU knife edges")
+
+
 def main():
     rng = np.random.default_rng(1234)
     pos_enc, dir_enc = get_vanilla_nerf_encoders()
@@ -84,8 +113,10 @@ def main():
 
     # ---- MLP forward + parameter grads (a2/a3)
     net, p = ref_nerf(7, sigma_bias=0.3)
-    ep = N(pos_enc(T(rng.uniform(-5, 5, (160, 3)).astype(np.float32))))
+    xm = rng.uniform(-5, 5, (160, 3)).astype(np.float32)
     ed = N(dir_enc(T(d[:1].repeat(160, 0))))
+    xm = remove_relu_knife_edges(xm, p, pos_enc, ed[0])
+    ep = N(pos_enc(T(xm)))
     d_out = rng.standard_normal((160, 4)).astype(np.float32)
     out = net(T(ep), T(ed)); out.backward(T(d_out))
     idx = rng.integers(0, O.N_PARAMS, size=4096)
