@@ -397,7 +397,17 @@ PackedLayout packed_layout() {
     }
     L.bf16_off = off;
     L.bf16_bytes = tc_packed_bytes();
-    L.total = off + L.bf16_bytes;
+    off += L.bf16_bytes;
+    L.split_off = off;
+    for (int l = 0; l < 12; ++l) {
+        const LayerDesc d = layer_desc(l);
+        L.split_fwd[l] = L.split_dgrad[l] = 0;
+        if (l == 9 || l == 11) continue;                       // sigma_out / color_out are CUDA-core heads
+        L.split_fwd[l] = off; off += align_up(split_image_bytes(d.N, d.Kpad), 256);
+        if (l > 0) { L.split_dgrad[l] = off; off += align_up(split_image_bytes(kHidden, d.N), 256); }
+    }
+    L.split_bytes = off - L.split_off;
+    L.total = off;
     return L;
 }
 
@@ -407,7 +417,7 @@ int pack_fp32(const float* params, void* packed, cudaStream_t st) {
     for (int l = 0; l < 12; ++l) { a.w[l] = L.f32_w[l]; a.b[l] = L.f32_b[l]; }
     pack_fp32_kernel<<<dim3(32, 12), 256, 0, st>>>(params, reinterpret_cast<char*>(packed), a);
     NSB_LAUNCH_CHECK("pack_fp32_kernel");
-    return NSB_OK;
+    return split_pack(params, packed, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -419,6 +429,7 @@ static inline const float* PW(const void* packed, const PackedLayout& L, int l) 
 static inline const float* PB(const void* packed, const PackedLayout& L, int l) {
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + L.f32_b[l]);
 }
+static inline const uint8_t* IMG(const void* packed, size_t off) { return reinterpret_cast<const uint8_t*>(packed) + off; }
 
 // The layer GEMMs run on the tensor cores with bf16-split operands (field_split.cu); NSB_FP32_GEMM=ffma keeps the FFMA tiles
 // of this file (the round-1 path, kept as the cross-check the split path is measured against).
@@ -427,11 +438,11 @@ static bool gemm_on_tc() {
     return tc;
 }
 
-static int gemm_fwd(const float* X, int64_t ldx, const float* W, int Kpad, const float* bias, float* Y, int64_t ldy,
+static int gemm_fwd(const float* X, int64_t ldx, const float* W, const uint8_t* w_img, int Kpad, const float* bias, float* Y, int64_t ldy,
                     int64_t Q, int N, int relu, cudaStream_t st) {
     GemmArgs g{};
     g.A = X; g.lda = ldx; g.B = W; g.ldb = Kpad; g.C = Y; g.ldc = ldy; g.Mdim = Q; g.Ndim = N; g.Kdim = Kpad;
-    g.bias = bias; g.relu = relu;
+    g.bias = bias; g.relu = relu; g.b_img = w_img;
     if (gemm_on_tc()) return split_gemm(g, EPI_FWD, st);
     dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(N, BN), 1);
     sgemm_kernel<false, false, EPI_FWD><<<grid, 256, 0, st>>>(g);
@@ -439,12 +450,12 @@ static int gemm_fwd(const float* X, int64_t ldx, const float* W, int Kpad, const
     return NSB_OK;
 }
 // dX[Q, n_in] = dY[Q, n_out] . W[n_out, ldw]  (first n_in columns), (+addend) (*mask)
-static int gemm_dgrad(const float* dY, int64_t ldy, const float* W, int ldw, float* dX, int64_t ldx, int64_t Q,
+static int gemm_dgrad(const float* dY, int64_t ldy, const float* W, const uint8_t* w_img, int ldw, float* dX, int64_t ldx, int64_t Q,
                       int n_out, int n_in, const float* mask, int64_t ldm, const float* addend, int64_t ldadd,
                       cudaStream_t st) {
     GemmArgs g{};
     g.A = dY; g.lda = ldy; g.B = W; g.ldb = ldw; g.C = dX; g.ldc = ldx; g.Mdim = Q; g.Ndim = n_in; g.Kdim = n_out;
-    g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd;
+    g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd; g.b_img = w_img;
     if (gemm_on_tc()) return split_gemm(g, EPI_DGRAD, st);
     dim3 grid((unsigned)cdiv(Q, BM), (unsigned)cdiv(n_in, BN), 1);
     sgemm_kernel<false, true, EPI_DGRAD><<<grid, 256, 0, st>>>(g);
@@ -507,12 +518,12 @@ int fp32_mlp_fwd(const void* packed, float* raw, void* ws, int64_t Q, int stash,
     for (int l = 0; l < 8; ++l) {
         const LayerDesc d = layer_desc(l);
         if (l == 4) { in = w.X4; ldin = kSkipPad; }
-        NSB_TRY(gemm_fwd(in, ldin, PW(packed, L, l), d.Kpad, PB(packed, L, l), w.out[l], w.out_ld[l], Q, 256, 1, st));
+        NSB_TRY(gemm_fwd(in, ldin, PW(packed, L, l), IMG(packed, L.split_fwd[l]), d.Kpad, PB(packed, L, l), w.out[l], w.out_ld[l], Q, 256, 1, st));
         in = w.out[l]; ldin = w.out_ld[l];
     }
     const float* H8 = w.out[7];
-    NSB_TRY(gemm_fwd(H8, kHidden, PW(packed, L, 8), 256, PB(packed, L, 8), w.XC, kColorPad, Q, 256, 0, st));       // feature
-    NSB_TRY(gemm_fwd(w.XC, kColorPad, PW(packed, L, 10), kColorPad, PB(packed, L, 10), w.C, kColorHidden, Q, 128, 1, st));  // color_fc
+    NSB_TRY(gemm_fwd(H8, kHidden, PW(packed, L, 8), IMG(packed, L.split_fwd[8]), 256, PB(packed, L, 8), w.XC, kColorPad, Q, 256, 0, st));       // feature
+    NSB_TRY(gemm_fwd(w.XC, kColorPad, PW(packed, L, 10), IMG(packed, L.split_fwd[10]), kColorPad, PB(packed, L, 10), w.C, kColorHidden, Q, 128, 1, st));  // color_fc
     head_fwd_kernel<<<elem_grid(Q * 32), 256, 0, st>>>(w.C, H8, kHidden, PW(packed, L, 11), PB(packed, L, 11),
                                                       PW(packed, L, 9), PB(packed, L, 9), raw, Q);
     NSB_LAUNCH_CHECK("head_fwd_kernel");
@@ -532,10 +543,10 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
     NSB_LAUNCH_CHECK("head_bwd_kernel");
     // color_fc
     NSB_TRY(gemm_wgrad(w.dC, kColorHidden, w.XC, kColorPad, grads + dfc.w_off, grads + dfc.b_off, Q, 128, dfc.K, dfc.Kpad, st));
-    NSB_TRY(gemm_dgrad(w.dC, kColorHidden, PW(packed, L, 10), kColorPad, w.dB, kHidden, Q, 128, 256, nullptr, 0, nullptr, 0, st));  // dFeat
+    NSB_TRY(gemm_dgrad(w.dC, kColorHidden, PW(packed, L, 10), IMG(packed, L.split_dgrad[10]), kColorPad, w.dB, kHidden, Q, 128, 256, nullptr, 0, nullptr, 0, st));  // dFeat
     // feature (no activation); dH8 = (dFeat.Wf + dsigma*w_sigma) * (H8>0)
     NSB_TRY(gemm_wgrad(w.dB, kHidden, H8, kHidden, grads + dft.w_off, grads + dft.b_off, Q, 256, 256, 256, st));
-    NSB_TRY(gemm_dgrad(w.dB, kHidden, PW(packed, L, 8), 256, w.dA, kHidden, Q, 256, 256, H8, kHidden, w.dA, kHidden, st));
+    NSB_TRY(gemm_dgrad(w.dB, kHidden, PW(packed, L, 8), IMG(packed, L.split_dgrad[8]), 256, w.dA, kHidden, Q, 256, 256, H8, kHidden, w.dA, kHidden, st));
     float* dcur = w.dA; float* dnext = w.dB;
     for (int l = 7; l >= 0; --l) {
         const LayerDesc d = layer_desc(l);
@@ -544,7 +555,7 @@ int fp32_mlp_bwd(const float* d_raw, const void* packed, float* grads, void* ws,
         NSB_TRY(gemm_wgrad(dcur, kHidden, Xin, ldx, grads + d.w_off, grads + d.b_off, Q, 256, d.K, d.Kpad, st));
         if (l > 0) {
             // input of layer l is relu(out[l-1]) -> mask by out[l-1] > 0 (first 256 columns only at the skip layer)
-            NSB_TRY(gemm_dgrad(dcur, kHidden, PW(packed, L, l), d.Kpad, dnext, kHidden, Q, 256, 256, w.out[l - 1],
+            NSB_TRY(gemm_dgrad(dcur, kHidden, PW(packed, L, l), IMG(packed, L.split_dgrad[l]), d.Kpad, dnext, kHidden, Q, 256, 256, w.out[l - 1],
                                w.out_ld[l - 1], nullptr, 0, st));
             float* t = dcur; dcur = dnext; dnext = t;
         }

@@ -8,12 +8,13 @@
 // the cross products in a second one (see the MMA loop for why).  NT = 3 carries 24 significand bits per operand -- the same
 // information as the FFMA path.
 //
-// One CTA = one 128 x 128 output tile; 256 threads.  Per K = 32 chunk every thread loads its share of the fp32 A and B
-// tiles from global memory (prefetched one chunk ahead in registers), splits it and writes the bf16 term images into a
-// shared-memory stage in the canonical K-major core-matrix layout -- operands stored with the OTHER index contiguous
+// One CTA = one 128 x 128 output tile; 512 converter threads (one piece each) + an MMA warp.  Per K = 16 chunk every converter thread owns one 8-element piece of the fp32 A or
+// B tile: cp.async brings it into a thread-private shared-memory slot (three chunks in flight per CTA, no
+// registers held, no barrier), the thread splits it and writes the bf16 term images into a shared-memory stage in the
+// canonical K-major core-matrix layout -- operands stored with the OTHER index contiguous
 // (dgrad's weights, both wgrad operands) are transposed by the same pass, so every MMA is K-major (an MN-major MMA costs
-// 3-4x more).  One thread issues the MMAs of the chunk and commits them to the stage's barrier; the
-// stage is rewritten only after that commit has arrived.  Two CTAs share an SM (96 KB of stages, 256 TMEM columns each), so
+// 3-4x more).  A ninth warp issues the MMAs of a chunk once its 512 pieces are written (mbarrier) and
+// commits them to the stage's "empty" barrier; the stage is rewritten only after that commit has arrived.  Two CTAs share an SM (112 KB of shared memory, 256 TMEM columns each), so
 // one CTA's conversion overlaps the other's MMAs.  Epilogues as in field_fp32.cu: bias + ReLU; addend + mask; split-K atomics.
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -23,15 +24,22 @@
 namespace nsb {
 namespace tc {
 
-constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 32;
-constexpr int SG_THREADS = 256;
-constexpr int SG_TERM_BYTES = SG_BM * SG_BK * 2;          // one bf16 term image of a 128 x 32 operand chunk: [k/8][row][8]
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16;                   // one K = 16 MMA step per chunk
+constexpr int SG_CONV = 256;                                          // converter threads = pieces per operand chunk: 128 rows x 2 groups of 8 k
+constexpr int SG_THREADS = SG_CONV + 64;                              // + the MMA warp + the weight-image producer warp
+constexpr int SG_TERM_BYTES = SG_BM * SG_BK * 2;                      // one bf16 term image of a 128 x 16 operand chunk: [k/8][row][8]
+constexpr int SG_RAW_BYTES = SG_BM * SG_BK * 4;                       // the same chunk as fp32
+constexpr int SG_FIFO = 4;                                            // raw chunks in flight per CTA (cp.async groups)
+constexpr int SG_IMG_TERMS = 3;                                       // pre-split weight images always carry three terms
+constexpr int SG_IMG_CHUNK = SG_IMG_TERMS * SG_TERM_BYTES;            // 12 KB per (128-row tile, K = 16 chunk)
 constexpr uint32_t SG_TMEM_COLS = 256;      // two fp32 accumulators of 128 columns: main (x0 * y0) and cross (every other term product)
 
 template <int NT> struct SgCfg {
-    static constexpr int kStageBytes = 2 * NT * SG_TERM_BYTES;            // A terms then B terms
-    static constexpr int kStages = NT == 3 ? 2 : 3;                       // 96 KB either way -> two CTAs per SM
-    static constexpr int kSmemBytes = kStages * kStageBytes + 128;        // + barriers and the TMEM slot
+    static constexpr int kStageBytes = 2 * NT * SG_TERM_BYTES;            // converted stage: A terms then B terms
+    static constexpr int kStages = 2;
+    static constexpr int kFifoOfs = kStages * kStageBytes;
+    static constexpr int kBarOfs = kFifoOfs + SG_FIFO * 2 * SG_RAW_BYTES;
+    static constexpr int kSmemBytes = kBarOfs + 128;                      // + barriers and the TMEM slot; NT = 3: 112.1 KB -> two CTAs per SM
 };
 
 __device__ __forceinline__ uint32_t pack_bf16_pair(float lo, float hi) {
@@ -59,58 +67,76 @@ __device__ __forceinline__ void split8(float (&x)[8], uint4 (&out)[NT]) {
     }
 }
 
-// Operand chunk loader: rows [row0, row0 + 128) x contraction [k0, k0 + 32) of P, 16 floats per thread in two tasks.
-//   TR = false: P[(row0 + r) * ld + k], k contiguous: task = (row r, group of 8 k) -- two float4 loads;
-//   TR = true : P[k * ld + row0 + r], r contiguous:   task = (row r, group of 8 k) -- eight scalar loads, lanes over r.
-// Either way a task yields the 8 consecutive k of one row = one 16-byte core-matrix row per term.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Operand chunk = rows [row0, row0 + 128) x contraction [k0, k0 + 16) of P: 256 pieces of 8 consecutive k of one row, one per
+// converter thread.  The fp32 data travels global -> shared with cp.async into a slot only this thread reads back (a private
+// FIFO: no barrier is involved and SG_FIFO - 1 chunks stay in flight per CTA without holding registers); out-of-range
+// elements are zero-filled by the copy itself (src-size 0).
+//   TR = false: P[(row0 + r) * ld + k], k contiguous: two 16-byte copies, slot = [half][thread] 16-byte words;
+//   TR = true : P[k * ld + row0 + r], r contiguous: eight 4-byte copies (lanes over r: coalesced), slot = [j][thread] words.
 template <bool TR>
 __device__ __forceinline__ void sg_task(int t, int& r, int& kg) {
-    if (!TR) { r = (t & 7) | ((t >> 5) << 3); kg = (t >> 3) & 3; }      // 8 lanes = 8 rows of one k group: conflict-free stores
+    if (!TR) { r = (t & 7) | ((t >> 4) << 3); kg = (t >> 3) & 1; }      // 8 lanes = 8 rows of one k group: conflict-free 16-byte stores
     else { r = t & 127; kg = t >> 7; }
 }
 template <bool TR>
-__device__ __forceinline__ void sg_load(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t rows, int64_t k0,
-                                        int64_t kend, int tid, float (&reg)[2][8]) {
+__device__ __forceinline__ void sg_fetch(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t rows, int64_t k0, int64_t kend,
+                                         int tid, uint32_t slot_base) {
+    int r, kg;
+    sg_task<TR>(tid, r, kg);
+    const int64_t row = row0 + r, k = k0 + kg * 8;
+    if (!TR) {
+        const bool ok = row < rows && k < kend;               // kend is a multiple of 8 on this path
+        const float* src = ok ? P + row * ld + k : P;
+        cp_async16(slot_base + tid * 16, src, ok ? 16u : 0u);
+        cp_async16(slot_base + SG_CONV * 16 + tid * 16, src + 4, ok ? 16u : 0u);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        int r, kg;
-        sg_task<TR>(tid + i * SG_THREADS, r, kg);
-        const int64_t row = row0 + r, k = k0 + kg * 8;
-        if (!TR) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (row < rows && k < kend) {
-                const float4* src = reinterpret_cast<const float4*>(P + row * ld + k);
-                a = __ldg(src); b = __ldg(src + 1);
-            }
-            reg[i][0] = a.x; reg[i][1] = a.y; reg[i][2] = a.z; reg[i][3] = a.w;
-            reg[i][4] = b.x; reg[i][5] = b.y; reg[i][6] = b.z; reg[i][7] = b.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) reg[i][j] = (row < rows && k + j < kend) ? __ldg(P + (k + j) * ld + row) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = row < rows && k + j < kend;
+            cp_async4(slot_base + j * (SG_CONV * 4) + tid * 4, ok ? P + (k + j) * ld + row : P, ok ? 4u : 0u);
         }
     }
 }
+// read this thread's slot back, split, write the term images of the converted stage
 template <bool TR, int NT>
-__device__ __forceinline__ void sg_store(uint8_t* img, int tid, float (&reg)[2][8]) {
+__device__ __forceinline__ void sg_convert(const uint8_t* slot, uint8_t* img, int tid) {
+    float x[8];
+    if (!TR) {
+        const float4 a = *reinterpret_cast<const float4*>(slot + tid * 16), b = *reinterpret_cast<const float4*>(slot + SG_CONV * 16 + tid * 16);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        int r, kg;
-        sg_task<TR>(tid + i * SG_THREADS, r, kg);
-        uint4 terms[NT];
-        split8<NT>(reg[i], terms);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) *reinterpret_cast<uint4*>(img + t * SG_TERM_BYTES + kg * 2048 + r * 16) = terms[t];
+        for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float*>(slot + j * (SG_CONV * 4) + tid * 4);
     }
+    int r, kg;
+    sg_task<TR>(tid, r, kg);
+    uint4 terms[NT];
+    split8<NT>(x, terms);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) *reinterpret_cast<uint4*>(img + t * SG_TERM_BYTES + kg * 2048 + r * 16) = terms[t];
 }
 
-template <bool AT, bool BT, int EPI, int NT>
-__global__ void __launch_bounds__(SG_THREADS) split_gemm_kernel(const GemmArgs g, int tiles_n, int tiles_mn) {
+// BIMG: the B operand is a weight matrix whose term images were written once per optimiser step (split_pack_kernel): a
+// producer thread bulk-copies the 4 KB term images of each chunk straight into the converted stage, and the converter
+// threads only handle A.
+template <bool AT, bool BT, int EPI, int NT, bool BIMG>
+__global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArgs g, int tiles_n, int tiles_mn) {
     using Cfg = SgCfg<NT>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_empty = sbase + Cfg::kStages * Cfg::kStageBytes;            // one per stage
-    const uint32_t bar_done = bar_empty + 8 * Cfg::kStages;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 64);
+    const uint32_t bar_empty = sbase + Cfg::kBarOfs;                               // per converted stage: its MMAs have completed
+    const uint32_t bar_full = bar_empty + 8 * Cfg::kStages;                        // per converted stage: all pieces (and the weight image) written
+    const uint32_t bar_done = bar_full + 8 * Cfg::kStages;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOfs + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     int64_t tile = blockIdx.x;
@@ -121,14 +147,28 @@ __global__ void __launch_bounds__(SG_THREADS) split_gemm_kernel(const GemmArgs g
         kbeg = split * g.k_per_split;
         kend = kbeg + g.k_per_split < g.Kdim ? kbeg + g.k_per_split : g.Kdim;
     }
-    const int64_t m0 = (tile / tiles_n) * SG_BM, n0 = (tile % tiles_n) * SG_BN;
+    const int64_t tn = tile % tiles_n;
+    const int64_t m0 = (tile / tiles_n) * SG_BM, n0 = tn * SG_BN;
+    const int64_t nchunks = kend > kbeg ? (kend - kbeg + SG_BK - 1) / SG_BK : 0;
+
+    // raw chunks 0 .. SG_FIFO-2 on their way before anything else
+    auto fetch = [&](int64_t c) {
+        if (c < nchunks && tid < SG_CONV) {
+            const uint32_t slot = sbase + Cfg::kFifoOfs + (uint32_t)(c % SG_FIFO) * (2 * SG_RAW_BYTES);
+            sg_fetch<AT>(g.A, g.lda, m0, g.Mdim, kbeg + c * SG_BK, kend, tid, slot);
+            if (!BIMG) sg_fetch<BT>(g.B, g.ldb, n0, g.Ndim, kbeg + c * SG_BK, kend, tid, slot + SG_RAW_BYTES);
+        }
+        cp_async_commit();                                   // one group per chunk index, possibly empty: keeps the wait count uniform
+    };
+#pragma unroll
+    for (int c = 0; c < SG_FIFO - 1; ++c) fetch(c);
 
     if (tid == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) mbar_init(bar_empty + 8 * s, 1);
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_full + 8 * s, SG_CONV + (BIMG ? 1 : 0)); }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == SG_CONV / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                      "r"(SG_TMEM_COLS)
                      : "memory");
@@ -139,33 +179,32 @@ __global__ void __launch_bounds__(SG_THREADS) split_gemm_kernel(const GemmArgs g
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t nchunks = kend > kbeg ? (kend - kbeg + SG_BK - 1) / SG_BK : 0;
-    float ra[2][8], rb[2][8];
-    if (nchunks > 0) {
-        sg_load<AT>(g.A, g.lda, m0, g.Mdim, kbeg, kend, tid, ra);
-        sg_load<BT>(g.B, g.ldb, n0, g.Ndim, kbeg, kend, tid, rb);
-    }
     // kind::f16, D = f32, A = B = bf16, both K-major, N = 128, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SG_BN >> 3) << 17) | ((uint32_t)(SG_BM >> 4) << 24);
-    const uint64_t dhi = desc_hi(2048, 128);          // LBO: between the two 8-wide k groups of a K = 16 step; SBO: between 8-row groups
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int s = (int)(c % Cfg::kStages);
-        const int64_t use = c / Cfg::kStages;
-        if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((use - 1) & 1));      // the MMAs that read this stage have completed
-        uint8_t* stage = smem + s * Cfg::kStageBytes;
-        sg_store<AT, NT>(stage, tid, ra);
-        sg_store<BT, NT>(stage + NT * SG_TERM_BYTES, tid, rb);
-        if (c + 1 < nchunks) {
-            sg_load<AT>(g.A, g.lda, m0, g.Mdim, kbeg + (c + 1) * SG_BK, kend, tid, ra);
-            sg_load<BT>(g.B, g.ldb, n0, g.Ndim, kbeg + (c + 1) * SG_BK, kend, tid, rb);
+    const uint64_t dhi = desc_hi(2048, 128);          // LBO: between the two 8-wide k groups of the K = 16 step; SBO: between 8-row groups
+    if (tid < SG_CONV) {
+        // ---- converters: raw FIFO -> bf16 term images of stage c % 2; nothing here waits for the MMA issue
+        for (int64_t c = 0; c < nchunks; ++c) {
+            fetch(c + SG_FIFO - 1);                              // into the slot chunk c-1 was read from (same thread, program order)
+            cp_async_wait<SG_FIFO - 1>();                        // chunk c has landed (this thread's copies are all this thread reads)
+            const int s = (int)(c % Cfg::kStages);
+            const int64_t use = c / Cfg::kStages;
+            if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((use - 1) & 1));      // the MMAs that read this stage have completed
+            const uint8_t* slot = smem + Cfg::kFifoOfs + (c % SG_FIFO) * (2 * SG_RAW_BYTES);
+            uint8_t* stage = smem + s * Cfg::kStageBytes;
+            sg_convert<AT, NT>(slot, stage, tid);
+            if (!BIMG) sg_convert<BT, NT>(slot + SG_RAW_BYTES, stage + NT * SG_TERM_BYTES, tid);
+            fence_async_smem();
+            mbar_arrive(bar_full + 8 * s);
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a0 = sbase + s * Cfg::kStageBytes, b0 = a0 + NT * SG_TERM_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < SG_BK / 16; ++ks) {
+    } else if (warp == SG_CONV / 32) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int s = (int)(c % Cfg::kStages);
+                mbar_wait(bar_full + 8 * s, (uint32_t)((c / Cfg::kStages) & 1));
+                tc_fence_after();
+                const uint32_t a0 = sbase + s * Cfg::kStageBytes, b0 = a0 + NT * SG_TERM_BYTES;
                 // Two accumulators.  tcgen05 adds each MMA into the fp32 accumulator with TRUNCATION (measured: same-sign sums
                 // come out low by ~0.25 ulp per MMA, scripts/dbg_split_gemm.py), so the error grows with the number of MMAs that
                 // touch an accumulator of full magnitude.  Only the x0 * y0 product (K / 16 MMAs) goes to the main accumulator;
@@ -176,18 +215,28 @@ __global__ void __launch_bounds__(SG_THREADS) split_gemm_kernel(const GemmArgs g
 #pragma unroll
                     for (int ta = 0; ta <= sum; ++ta) {
                         const int tb = sum - ta;
-                        const bool first = c == 0 && ks == 0 && sum == NT - 1 && ta == 0;
-                        tc_mma(tmem_base + 128, desc_at(dhi, a0 + ta * SG_TERM_BYTES + ks * 4096), desc_at(dhi, b0 + tb * SG_TERM_BYTES + ks * 4096),
-                               idesc, first ? 0u : 1u);
+                        tc_mma(tmem_base + 128, desc_at(dhi, a0 + ta * SG_TERM_BYTES), desc_at(dhi, b0 + tb * SG_TERM_BYTES), idesc,
+                               (c == 0 && sum == NT - 1 && ta == 0) ? 0u : 1u);
                     }
                 }
-                tc_mma(tmem_base, desc_at(dhi, a0 + ks * 4096), desc_at(dhi, b0 + ks * 4096), idesc, (c == 0 && ks == 0) ? 0u : 1u);
+                tc_mma(tmem_base, desc_at(dhi, a0), desc_at(dhi, b0), idesc, c == 0 ? 0u : 1u);
+                tc_commit(bar_empty + 8 * s);
+                if (c + 1 == nchunks) tc_commit(bar_done);
             }
-            tc_commit(bar_empty + 8 * s);
-            if (c + 1 == nchunks) tc_commit(bar_done);
+        }
+    } else if (BIMG && lane == 0) {
+        // ---- weight-image producer: chunk c of column tile tn = NT contiguous 4 KB term images
+        const uint8_t* img = g.b_img + ((size_t)tn * (size_t)(g.Kdim / SG_BK) + (size_t)(kbeg / SG_BK)) * SG_IMG_CHUNK;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int s = (int)(c % Cfg::kStages);
+            const int64_t use = c / Cfg::kStages;
+            if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((use - 1) & 1));
+            mbar_expect_tx(bar_full + 8 * s, NT * SG_TERM_BYTES);
+            bulk_g2s(sbase + s * Cfg::kStageBytes + NT * SG_TERM_BYTES, img + (size_t)c * SG_IMG_CHUNK, NT * SG_TERM_BYTES, bar_full + 8 * s);
         }
     }
-    if (nchunks > 0) {
+    cp_async_wait<0>();
+    if (nchunks > 0 && tid < SG_CONV) {
         mbar_wait(bar_done, 0);
         tc_fence_after();
         // ---- epilogue: thread = accumulator row (TMEM lane), warps 0-3 columns 0-63, warps 4-7 columns 64-127
@@ -239,17 +288,45 @@ __global__ void __launch_bounds__(SG_THREADS) split_gemm_kernel(const GemmArgs g
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == SG_CONV / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(SG_TMEM_COLS) : "memory");
     }
 }
 
-template <bool AT, bool BT, int EPI, int NT>
+// Term images of one weight matrix as the B operand of a role: B(n, k), n < n_rows (padded to 128-row tiles), k < k_len
+// (a multiple of 16), element = W[n * ldw + k] (transpose = 0) or W[k * ldw + n] (transpose = 1), zero where k >= k_true
+// (n >= n_true).  Layout: [n / 128][k / 16][term][(k / 8) % 2][n % 128][k % 8] bf16.
+struct SplitPackJob { int64_t w_off; int ldw; int transpose; int n_true, k_true, n_tiles, k_chunks; size_t dst; };
+constexpr int kSplitJobs = 19;
+struct SplitPackArgs { SplitPackJob j[kSplitJobs]; };
+__global__ void __launch_bounds__(256) split_pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ base, const __grid_constant__ SplitPackArgs a) {
+    const SplitPackJob& jb = a.j[blockIdx.y];
+    const int64_t pieces = (int64_t)jb.n_tiles * jb.k_chunks * 256;              // (tile, chunk, k group, row)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pieces; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i & 127), kg = (int)((i >> 7) & 1);
+        const int64_t tc_ = i >> 8;                                               // tile * k_chunks + chunk
+        const int chunk = (int)(tc_ % jb.k_chunks), tile_n = (int)(tc_ / jb.k_chunks);
+        const int n = tile_n * 128 + r, k0 = chunk * 16 + kg * 8;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            x[j] = (n < jb.n_true && k < jb.k_true) ? params[jb.w_off + (jb.transpose ? (int64_t)k * jb.ldw + n : (int64_t)n * jb.ldw + k)] : 0.f;
+        }
+        uint4 terms[SG_IMG_TERMS];
+        split8<SG_IMG_TERMS>(x, terms);
+        uint8_t* dst = base + jb.dst + (size_t)tc_ * SG_IMG_CHUNK + kg * 2048 + r * 16;
+#pragma unroll
+        for (int t = 0; t < SG_IMG_TERMS; ++t) *reinterpret_cast<uint4*>(dst + t * SG_TERM_BYTES) = terms[t];
+    }
+}
+
+template <bool AT, bool BT, int EPI, int NT, bool BIMG>
 static int launch_split_gemm(const GemmArgs& g, cudaStream_t st) {
     using Cfg = SgCfg<NT>;
-    auto kern = split_gemm_kernel<AT, BT, EPI, NT>;
-    static bool configured = false;          // per instantiation; the attribute is per function, not per device context state we track
+    auto kern = split_gemm_kernel<AT, BT, EPI, NT, BIMG>;
+    static bool configured = false;          // per instantiation
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
             cudaGetLastError();
@@ -265,7 +342,7 @@ static int launch_split_gemm(const GemmArgs& g, cudaStream_t st) {
         int64_t want = (int64_t)num_sms() * 2 / (tiles_m * tiles_n);
         if (want < 1) want = 1;
         int64_t kps = cdiv(cdiv(g.Kdim, want), SG_BK) * SG_BK;
-        if (kps < 8 * SG_BK) kps = 8 * SG_BK;
+        if (kps < 256) kps = 256;
         splits = cdiv(g.Kdim, kps);
         a.k_per_split = kps;
     }
@@ -285,15 +362,38 @@ static int split_terms() {
     return nt;
 }
 
+size_t split_image_bytes(int n_rows, int k_len) { return (size_t)cdiv(n_rows, 128) * (size_t)(k_len / 16) * tc::SG_IMG_CHUNK; }
+
+// Every weight image of a net: forward B = W (n = out feature, k = in feature, zero beyond K), dgrad B = W^T restricted to
+// the first 256 in features (n = in feature, k = out feature).  One launch, 19 jobs; ~7 MB written per net.
+int split_pack(const float* params, void* packed, cudaStream_t st) {
+    const PackedLayout L = packed_layout();
+    tc::SplitPackArgs a;
+    int nj = 0;
+    for (int l = 0; l < 12; ++l) {
+        if (l == 9 || l == 11) continue;
+        const LayerDesc d = layer_desc(l);
+        a.j[nj++] = tc::SplitPackJob{d.w_off, d.K, 0, d.N, d.K, (int)cdiv(d.N, 128), d.Kpad / 16, L.split_fwd[l]};
+        if (l > 0) a.j[nj++] = tc::SplitPackJob{d.w_off, d.K, 1, kHidden, d.N, kHidden / 128, d.N / 16, L.split_dgrad[l]};
+    }
+    if (nj != tc::kSplitJobs) return NSB_E_BADARG;
+    tc::split_pack_kernel<<<dim3(16, tc::kSplitJobs), 256, 0, st>>>(params, reinterpret_cast<uint8_t*>(packed), a);
+    NSB_LAUNCH_CHECK("split_pack_kernel");
+    return NSB_OK;
+}
+
 int split_gemm(const GemmArgs& g, int role, cudaStream_t st) {
     // alignment contract of the loaders / epilogues (all layer buffers of field_fp32.cu satisfy it)
-    if ((g.lda & 3) || (g.ldb & 3) || (role != EPI_WGRAD && ((g.Kdim & 7) || (g.ldc & 3) || (g.Ndim & 15)))) return NSB_E_BADARG;
+    if ((g.lda & 3) || (g.ldb & 3) || (role != EPI_WGRAD && ((g.Kdim & 15) || (g.ldc & 3) || (g.Ndim & 15)))) return NSB_E_BADARG;
     const bool t3 = split_terms() == 3;
+    const bool img = g.b_img != nullptr && role != EPI_WGRAD;
+#define NSB_SG(AT, BT, EPI, IMGF) (t3 ? tc::launch_split_gemm<AT, BT, EPI, 3, IMGF>(g, st) : tc::launch_split_gemm<AT, BT, EPI, 2, IMGF>(g, st))
     switch (role) {
-        case EPI_FWD: return t3 ? tc::launch_split_gemm<false, false, EPI_FWD, 3>(g, st) : tc::launch_split_gemm<false, false, EPI_FWD, 2>(g, st);
-        case EPI_DGRAD: return t3 ? tc::launch_split_gemm<false, true, EPI_DGRAD, 3>(g, st) : tc::launch_split_gemm<false, true, EPI_DGRAD, 2>(g, st);
-        case EPI_WGRAD: return t3 ? tc::launch_split_gemm<true, true, EPI_WGRAD, 3>(g, st) : tc::launch_split_gemm<true, true, EPI_WGRAD, 2>(g, st);
+        case EPI_FWD: return img ? NSB_SG(false, false, EPI_FWD, true) : NSB_SG(false, false, EPI_FWD, false);
+        case EPI_DGRAD: return img ? NSB_SG(false, true, EPI_DGRAD, true) : NSB_SG(false, true, EPI_DGRAD, false);
+        case EPI_WGRAD: return NSB_SG(true, true, EPI_WGRAD, false);
     }
+#undef NSB_SG
     return NSB_E_BADARG;
 }
 

@@ -159,15 +159,20 @@ struct GemmArgs {
     const float* addend; int64_t ldadd; // DGRAD: += addend
     int n_valid;                        // WGRAD: columns < n_valid are written
     int64_t k_per_split;                // WGRAD: contraction rows per split
+    const uint8_t* b_img;               // FWD / DGRAD on the tensor cores: pre-split term images of B (split_pack), or null
 };
 // field_split.cu: role = EPI_* (FWD: A, B k-contiguous; DGRAD: B stored [k][n]; WGRAD: both stored [k][.], split-K with atomics)
 int split_gemm(const GemmArgs& g, int role, cudaStream_t st);
+size_t split_image_bytes(int n_rows, int k_len);                       // one weight matrix as a B operand: n_rows x k_len, 3 terms
+int split_pack(const float* params, void* packed, cudaStream_t st);  // writes every split_fwd / split_dgrad image of a net
 
 // Packed weights of one net (nsb_pack_weights): [fp32 padded section | bf16 tensor-core section]
 struct PackedLayout {
     size_t f32_w[12], f32_b[12];   // byte offsets; rows padded to Kpad floats
     size_t bf16_off;               // start of the bf16 image (layout owned by field_tc.cu)
     size_t bf16_bytes;
+    size_t split_fwd[12], split_dgrad[12];   // bf16 term images of the weights for the fp32 mode's tensor-core GEMMs (field_split.cu)
+    size_t split_off, split_bytes;
     size_t total;
 };
 PackedLayout packed_layout();
