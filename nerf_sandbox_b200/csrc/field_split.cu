@@ -32,6 +32,7 @@ constexpr int SG_RAW_BYTES = SG_BM * SG_BK * 4;                       // the sam
 constexpr int SG_FIFO = 4;                                            // raw chunks in flight per CTA (cp.async groups)
 constexpr int SG_IMG_TERMS = 3;                                       // pre-split weight images always carry three terms
 constexpr int SG_IMG_CHUNK = SG_IMG_TERMS * SG_TERM_BYTES;            // 12 KB per (128-row tile, K = 16 chunk)
+constexpr int SG_EPI_LD = SG_BN + 4;                                   // row stride (floats) of the epilogue's shared-memory tile
 constexpr uint32_t SG_TMEM_COLS = 256;      // two fp32 accumulators of 128 columns: main (x0 * y0) and cross (every other term product)
 
 template <int NT> struct SgCfg {
@@ -39,6 +40,7 @@ template <int NT> struct SgCfg {
     static constexpr int kStages = 2;
     static constexpr int kFifoOfs = kStages * kStageBytes;
     static constexpr int kBarOfs = kFifoOfs + SG_FIFO * 2 * SG_RAW_BYTES;
+    static_assert(kBarOfs >= SG_BM * SG_EPI_LD * 4, "the epilogue tile reuses the stage + FIFO area");
     static constexpr int kSmemBytes = kBarOfs + 128;                      // + barriers and the TMEM slot; NT = 3: 112.1 KB -> two CTAs per SM
 };
 
@@ -239,50 +241,63 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     if (nchunks > 0 && tid < SG_CONV) {
         mbar_wait(bar_done, 0);
         tc_fence_after();
-        // ---- epilogue: thread = accumulator row (TMEM lane), warps 0-3 columns 0-63, warps 4-7 columns 64-127
-        const int rowl = 32 * (warp & 3) + lane;
-        const int64_t m = m0 + rowl;
-        const int cb = 64 * (warp >> 2);
+        // ---- epilogue, part 1: TMEM -> shared memory.  Thread = accumulator row (TMEM lane), warps 0-3 columns 0-63, warps
+        // 4-7 columns 64-127; main + cross added here.  The tile goes to the (now idle) stage / FIFO area as 128 rows of
+        // SG_EPI_LD floats (padded: 16-byte stores of 8 consecutive rows hit 32 distinct banks).
+        float* tile_s = reinterpret_cast<float*>(smem);
+        {
+            const int rowl = 32 * (warp & 3) + lane;
+            const int cb = 64 * (warp >> 2);
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-            uint32_t v[16], vx[16];
-            tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb + 16 * cc), v);
-            tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 + cb + 16 * cc), vx);
-            tc_wait_ld();
-            pin16(v); pin16(vx);
-            const int64_t n = n0 + cb + 16 * cc;
-            if (m < g.Mdim && n < g.Ndim) {
-                float f[16];
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t v[16], vx[16];
+                tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb + 16 * cc), v);
+                tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 + cb + 16 * cc), vx);
+                tc_wait_ld();
+                pin16(v); pin16(vx);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(vx[j]);
-                if (EPI == EPI_FWD) {
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(tile_s + rowl * SG_EPI_LD + cb + 16 * cc + 4 * q) =
+                        make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(vx[4 * q]), __uint_as_float(v[4 * q + 1]) + __uint_as_float(vx[4 * q + 1]),
+                                    __uint_as_float(v[4 * q + 2]) + __uint_as_float(vx[4 * q + 2]), __uint_as_float(v[4 * q + 3]) + __uint_as_float(vx[4 * q + 3]));
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SG_CONV) : "memory");          // the 256 epilogue threads only
+        // ---- part 2: shared memory -> global, one warp per row at a time, lane = 4 consecutive columns (512 contiguous bytes)
+        const int64_t n = n0 + 4 * lane;
+        if (EPI == EPI_WGRAD) {
+            // split-K partial sums: one 128-byte run of atomics per instruction (lane = column)
+            for (int r = warp; r < SG_BM; r += SG_CONV / 32) {
+                const int64_t m = m0 + r;
+                if (m >= g.Mdim) break;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n) + q);
-                        float4 o = make_float4(f[4 * q] + bb.x, f[4 * q + 1] + bb.y, f[4 * q + 2] + bb.z, f[4 * q + 3] + bb.w);
-                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        reinterpret_cast<float4*>(g.C + m * g.ldc + n)[q] = o;
-                    }
-                } else if (EPI == EPI_DGRAD) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                        if (g.addend) {
-                            const float4 ad = reinterpret_cast<const float4*>(g.addend + m * g.ldadd + n)[q];
-                            o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                        }
-                        if (g.mask) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + m * g.ldm + n) + q);
-                            o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                            o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-                        }
-                        reinterpret_cast<float4*>(g.C + m * g.ldc + n)[q] = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < g.n_valid) atomicAdd(g.C + m * g.ldc + n + j, f[j]);
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t nn = n0 + 32 * q + lane;
+                    if (nn < g.n_valid) atomicAdd(g.C + m * g.ldc + nn, tile_s[r * SG_EPI_LD + 32 * q + lane]);
                 }
+            }
+        } else if (n < g.Ndim) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EPI_FWD) bb = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            for (int r = warp; r < SG_BM; r += SG_CONV / 32) {
+                const int64_t m = m0 + r;
+                if (m >= g.Mdim) break;
+                float4 o = *reinterpret_cast<const float4*>(tile_s + r * SG_EPI_LD + 4 * lane);
+                if (EPI == EPI_FWD) {
+                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                } else {
+                    if (g.addend) {
+                        const float4 ad = *reinterpret_cast<const float4*>(g.addend + m * g.ldadd + n);
+                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
+                    if (g.mask) {
+                        const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + m * g.ldm + n));
+                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                    }
+                }
+                *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = o;
             }
         }
     }
