@@ -469,7 +469,8 @@ static int gemm_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx,
     g.A = dY; g.lda = ldy; g.B = X; g.ldb = ldx; g.C = gW; g.ldc = K; g.Mdim = n_out; g.Ndim = Kpad; g.Kdim = Q;
     g.n_valid = K;
     if (gemm_on_tc()) {
-        NSB_TRY(split_gemm(g, EPI_WGRAD, st));
+        g.colsum = gb;                      // the bias gradient rides along (the kernel sees every dY element anyway)
+        return split_gemm(g, EPI_WGRAD, st);
     } else {
         const int tiles = (int)(cdiv(n_out, BM) * cdiv(Kpad, BN));
         int64_t splits = (int64_t)num_sms() * 2 / tiles;

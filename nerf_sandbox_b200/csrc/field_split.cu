@@ -110,7 +110,7 @@ __device__ __forceinline__ void sg_fetch(const float* __restrict__ P, int64_t ld
 }
 // read this thread's slot back, split, write the term images of the converted stage
 template <bool TR, int NT>
-__device__ __forceinline__ void sg_convert(const uint8_t* slot, uint8_t* img, int tid) {
+__device__ __forceinline__ float sg_convert(const uint8_t* slot, uint8_t* img, int tid) {
     float x[8];
     if (!TR) {
         const float4 a = *reinterpret_cast<const float4*>(slot + tid * 16), b = *reinterpret_cast<const float4*>(slot + SG_CONV * 16 + tid * 16);
@@ -119,12 +119,14 @@ __device__ __forceinline__ void sg_convert(const uint8_t* slot, uint8_t* img, in
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float*>(slot + j * (SG_CONV * 4) + tid * 4);
     }
+    const float sum8 = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));      // wgrad: this piece of the bias gradient
     int r, kg;
     sg_task<TR>(tid, r, kg);
     uint4 terms[NT];
     split8<NT>(x, terms);
 #pragma unroll
     for (int t = 0; t < NT; ++t) *reinterpret_cast<uint4*>(img + t * SG_TERM_BYTES + kg * 2048 + r * 16) = terms[t];
+    return sum8;
 }
 
 // BIMG: the B operand is a weight matrix whose term images were written once per optimiser step (split_pack_kernel): a
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     const uint64_t dhi = desc_hi(2048, 128);          // LBO: between the two 8-wide k groups of the K = 16 step; SBO: between 8-row groups
     if (tid < SG_CONV) {
         // ---- converters: raw FIFO -> bf16 term images of stage c % 2; nothing here waits for the MMA issue
+        float colsum = 0.f;                                      // wgrad: sum over this CTA's points of dY[., m0 + r] (this thread's k group)
         for (int64_t c = 0; c < nchunks; ++c) {
             fetch(c + SG_FIFO - 1);                              // into the slot chunk c-1 was read from (same thread, program order)
             cp_async_wait<SG_FIFO - 1>();                        // chunk c has landed (this thread's copies are all this thread reads)
@@ -194,10 +197,16 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
             if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((use - 1) & 1));      // the MMAs that read this stage have completed
             const uint8_t* slot = smem + Cfg::kFifoOfs + (c % SG_FIFO) * (2 * SG_RAW_BYTES);
             uint8_t* stage = smem + s * Cfg::kStageBytes;
-            sg_convert<AT, NT>(slot, stage, tid);
+            colsum += sg_convert<AT, NT>(slot, stage, tid);
             if (!BIMG) sg_convert<BT, NT>(slot + SG_RAW_BYTES, stage + NT * SG_TERM_BYTES, tid);
             fence_async_smem();
             mbar_arrive(bar_full + 8 * s);
+        }
+        // bias gradient = column sums of dY: the A pieces of a wgrad CTA are exactly that data; one column tile's CTAs report it
+        if (EPI == EPI_WGRAD && g.colsum != nullptr && tn == 0 && nchunks > 0) {
+            int r, kg;
+            sg_task<AT>(tid, r, kg);
+            if (m0 + r < g.Mdim) atomicAdd(g.colsum + m0 + r, colsum);
         }
     } else if (warp == SG_CONV / 32) {
         if (lane == 0) {
@@ -417,9 +426,9 @@ int split_gemm(const GemmArgs& g, int role, cudaStream_t st) {
 // Test hook (not in include/nsb.h): one GEMM of the given role on caller buffers.
 extern "C" int nsb_debug_split_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                                     int64_t N, int64_t K, int role, const float* bias, int relu, const float* mask, int64_t ldm,
-                                    const float* addend, int64_t ldadd, int n_valid, void* stream) {
+                                    const float* addend, int64_t ldadd, int n_valid, float* colsum, void* stream) {
     nsb::GemmArgs g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.Mdim = M; g.Ndim = N; g.Kdim = K;
-    g.bias = bias; g.relu = relu; g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd; g.n_valid = n_valid;
+    g.bias = bias; g.relu = relu; g.mask = mask; g.ldm = ldm; g.addend = addend; g.ldadd = ldadd; g.n_valid = n_valid; g.colsum = colsum;
     return nsb::split_gemm(g, role, nsb::as_stream(stream));
 }

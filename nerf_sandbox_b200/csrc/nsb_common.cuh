@@ -159,6 +159,7 @@ struct GemmArgs {
     const float* addend; int64_t ldadd; // DGRAD: += addend
     int n_valid;                        // WGRAD: columns < n_valid are written
     int64_t k_per_split;                // WGRAD: contraction rows per split
+    float* colsum;                      // WGRAD on the tensor cores: += column sums of A (the bias gradient), or null
     const uint8_t* b_img;               // FWD / DGRAD on the tensor cores: pre-split term images of B (split_pack), or null
 };
 // field_split.cu: role = EPI_* (FWD: A, B k-contiguous; DGRAD: B stored [k][n]; WGRAD: both stored [k][.], split-K with atomics)

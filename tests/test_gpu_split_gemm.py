@@ -16,7 +16,7 @@ def _fn():
     fn = L.nsb_debug_split_gemm
     fn.restype = C.c_int
     p, i64, i32 = C.c_void_p, C.c_int64, C.c_int
-    fn.argtypes = [p, i64, p, i64, p, i64, i64, i64, i64, i32, p, i32, p, i64, p, i64, i32, p]
+    fn.argtypes = [p, i64, p, i64, p, i64, i64, i64, i64, i32, p, i32, p, i64, p, i64, i32, p, p]
     return fn, _lib
 
 
@@ -34,7 +34,7 @@ def test_forward_role(M, N, K):
     b = torch.randn(N, device=dev, generator=g)
     for relu in (0, 1):
         Y = torch.full((M, N), float("nan"), device=dev)
-        _lib.check(fn(_lib.ptr(X), K, _lib.ptr(W), K, _lib.ptr(Y), N, M, N, K, FWD, _lib.ptr(b), relu, None, 0, None, 0, 0, _lib.stream()),
+        _lib.check(fn(_lib.ptr(X), K, _lib.ptr(W), K, _lib.ptr(Y), N, M, N, K, FWD, _lib.ptr(b), relu, None, 0, None, 0, 0, None, _lib.stream()),
                    "split_gemm fwd")
         ref = X.double() @ W.double().T + b.double()
         if relu:
@@ -59,14 +59,14 @@ def test_dgrad_role_mask_addend_and_tiny_gradients():
         add = torch.randn(M, 256, device=dev, generator=g) * scale
         dX = torch.full((M, 256), float("nan"), device=dev)
         _lib.check(fn(_lib.ptr(dY), n_out, _lib.ptr(W), kpad, _lib.ptr(dX), 256, M, 256, n_out, DGRAD, None, 0, _lib.ptr(mask), 300,
-                      _lib.ptr(add), 256, 0, _lib.stream()), "split_gemm dgrad")
+                      _lib.ptr(add), 256, 0, None, _lib.stream()), "split_gemm dgrad")
         ref = (dY.double() @ W.double()[:, :256] + add.double()) * (mask[:, :256] > 0)
         assert _rel(dX, ref) < 2e-6, (scale, _rel(dX, ref))
         # no mask, no addend, n_out = 128 (color_fc)
         dC = torch.randn(M, 128, device=dev, generator=g) * scale
         Wc = torch.randn(128, 288, device=dev, generator=g) * 0.1
         dF = torch.full((M, 256), float("nan"), device=dev)
-        _lib.check(fn(_lib.ptr(dC), 128, _lib.ptr(Wc), 288, _lib.ptr(dF), 256, M, 256, 128, DGRAD, None, 0, None, 0, None, 0, 0, _lib.stream()),
+        _lib.check(fn(_lib.ptr(dC), 128, _lib.ptr(Wc), 288, _lib.ptr(dF), 256, M, 256, 128, DGRAD, None, 0, None, 0, None, 0, 0, None, _lib.stream()),
                    "split_gemm dgrad")
         ref = dC.double() @ Wc.double()[:, :256]
         assert _rel(dF, ref) < 2e-6, (scale, _rel(dF, ref))
@@ -81,8 +81,10 @@ def test_wgrad_role(P, n_out, K, Kpad):
     X = torch.randn(P, Kpad, device=dev, generator=g)
     X[:, K:] = 0
     gW = torch.zeros(n_out, K, device=dev)
+    gb = torch.zeros(n_out, device=dev)                        # bias gradient = column sums of dY, accumulated by the same launch
     ref = dY.double().T @ X.double()[:, :K]
     for times in (1, 2):                                       # accumulates INTO the buffer (split-K atomics)
         _lib.check(fn(_lib.ptr(dY), n_out, _lib.ptr(X), Kpad, _lib.ptr(gW), K, n_out, Kpad, P, WGRAD, None, 0, None, 0, None, 0, K,
-                      _lib.stream()), "split_gemm wgrad")
+                      _lib.ptr(gb), _lib.stream()), "split_gemm wgrad")
+        assert _rel(gb, times * dY.double().sum(0)) < 1e-5
         assert _rel(gW, times * ref) < 1e-5, (times, _rel(gW, times * ref))    # 40,000 random-sign terms per element: fp32 accumulation noise
