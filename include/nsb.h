@@ -37,7 +37,8 @@ extern "C" {
 #define NSB_SIGMA_SOFTPLUS 8u    /* render_utils.py:243-246: sigma = softplus(raw) instead of relu(raw) (raw entry points) */
 
 /* arithmetic mode of the field (encoder + MLP) kernels */
-#define NSB_MODE_FP32 0  /* CUDA-core FFMA, fp32 everywhere: the 1e-4 parity mode           */
+#define NSB_MODE_FP32 0  /* fp32 activations / gradients in HBM, the 1e-4 parity mode: layer GEMMs on tcgen05 with
+                          * operands split into three bf16 terms (fp32-grade products), NSB_FP32_GEMM=ffma: CUDA cores */
 #define NSB_MODE_BF16 1  /* tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM     */
 
 /* NeRF(63,27,8,256,skip_pos=4) -- models/mlps.py:41-134.  Flat parameter order is the reference's
@@ -128,7 +129,8 @@ int nsb_encode(const float* x, float* out, int64_t Q, int D, int L, int include_
 
 /* Packed weights of one NeRF: fp32 padded rows for the FFMA path, and images in tcgen05 operand layout for the tensor
  * paths -- bf16 (training forward), transposed bf16 (dgrad), fp16 (inference forward) and the fp16 low halves of the
- * split used by the fp32-accurate inference forward.  Sizes in bytes. */
+ * split used by the fp32-accurate inference forward, and bf16 term images (w = w0 + w1 + w2) of every weight matrix, plain
+ * and transposed, for the fp32 mode's tensor-core layer GEMMs.  Sizes in bytes. */
 size_t nsb_packed_weights_bytes(void);
 /* params: flat fp32 [NSB_N_PARAMS] in state_dict order -> packed (call after every optimiser step).
  * mode selects which section is refreshed: NSB_MODE_FP32, NSB_MODE_BF16, or -1 for both; OR-ing NSB_PACK_TRAIN_ONLY into it
