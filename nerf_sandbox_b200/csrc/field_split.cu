@@ -352,10 +352,8 @@ static int launch_split_gemm(const GemmArgs& g, cudaStream_t st) {
     auto kern = split_gemm_kernel<AT, BT, EPI, NT, BIMG>;
     static bool configured = false;          // per instantiation
     if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
-            cudaGetLastError();
-            return NSB_E_CUDA;
-        }
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(split_gemm_kernel)");
         configured = true;
     }
     const int64_t tiles_m = cdiv(g.Mdim, SG_BM), tiles_n = cdiv(g.Ndim, SG_BN);
@@ -407,6 +405,7 @@ int split_pack(const float* params, void* packed, cudaStream_t st) {
 }
 
 int split_gemm(const GemmArgs& g, int role, cudaStream_t st) {
+    NSB_TRY(check_arch());
     // alignment contract of the loaders / epilogues (all layer buffers of field_fp32.cu satisfy it)
     if ((g.lda & 3) || (g.ldb & 3) || (role != EPI_WGRAD && ((g.Kdim & 15) || (g.ldc & 3) || (g.Ndim & 15)))) return NSB_E_BADARG;
     const bool t3 = split_terms() == 3;

@@ -1592,7 +1592,7 @@ int tc_pack(const float* const* params, void* const* packed_bf16, int n_nets, bo
     return NSB_OK;
 }
 
-static int check_arch() {
+int check_arch() {
     static int ok = -1;
     if (ok < 0) {
         int dev = 0, major = 0;

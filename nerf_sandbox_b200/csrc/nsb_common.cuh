@@ -15,6 +15,7 @@ int check_launch(const char* what);  // cudaGetLastError -> NSB_E_CUDA
 extern thread_local const uint64_t* g_step_dev;
 extern thread_local uint64_t* g_pack_counter;
 int num_sms();
+int check_arch();                   // field_tc.cu: NSB_E_ARCH unless the current device is sm_100 (tcgen05 kernels)
 
 #define NSB_LAUNCH_CHECK(name)                        \
     do {                                              \
