@@ -253,17 +253,18 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
 }
 
 // =====================================================================================================================
-// Run layout (N <= 256 samples per ray -- every vanilla shape: 64 coarse, 192 merged): lane l of the ray's warp owns the
+// Run layout (N <= 256 samples per ray -- every vanilla shape: 64 coarse, 192 merged; 256 < N <= 1024: the multi-warp variant
+// further down): lane l of the ray's warp owns the
 // CONTIGUOUS run [l R, l R + R) of samples, R = ceil(N / 32) <= 8, all in registers.  The exclusive cumprod is a serial
 // product inside the run plus ONE multiplicative warp scan over the 32 run products per ray (instead of one scan per 32
 // samples), the loads of a run are issued up front (R independent 16-byte loads per lane in flight), and the backward keeps
 // alpha / T / rgb / pre-activations of its run in registers between the two passes: no shared memory, no recompute of the
 // activations.  Head activations use MUFU-based fast paths (ex2 / rcp: relative error ~2e-7, far inside the 1e-4 bar).
-// The strided kernels above remain for N > 256.
+// The strided kernels above remain for N > 1024.
 // =====================================================================================================================
 constexpr int kRunWarps = 4;
 // NSB_K3_STRIDED=1 forces the strided kernels for every N (A/B timing and debugging)
-static const int kRunMaxN = [] { const char* e = getenv("NSB_K3_STRIDED"); return (e && e[0] == '1') ? 0 : 256; }();
+static const int kRunMaxN = [] { const char* e = getenv("NSB_K3_STRIDED"); return (e && e[0] == '1') ? 0 : 1024; }();   // up to 4 warps per ray
 
 // 1 / (1 + 2^(-x log2 e)): FMUL + MUFU.EX2 + FADD + MUFU.RCP (relative error ~4e-7; saturates to 0 / 1, NaN propagates)
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
@@ -281,7 +282,7 @@ template <bool RAW, int R, bool FULL>
 __device__ __forceinline__ float run_forward(RunSamples<RAW, R>& s, const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma,
                                              const float* __restrict__ noise, float noise_std, bool add_noise, bool softplus,
                                              uint64_t seed, uint64_t offset, const float* __restrict__ zrow, int64_t q0, int start, int cnt,
-                                             int N, bool inf_last, float rn, bool has_rn, float eps, int64_t idx0) {
+                                             int N, bool inf_last, float rn, bool has_rn, float eps, int64_t idx0, bool multi_warp = false) {
     float4 v[R];
     float nz[R];
 #pragma unroll
@@ -298,7 +299,8 @@ __device__ __forceinline__ float run_forward(RunSamples<RAW, R>& s, const float*
             }
         }
     }
-    const float z_next_lane = __shfl_down_sync(0xffffffffu, s.z[0], 1);      // first z of the next lane's run
+    float z_next_lane = __shfl_down_sync(0xffffffffu, s.z[0], 1);            // first z of the next lane's run
+    if (multi_warp && (threadIdx.x & 31) == 31 && start + R < N) z_next_lane = __ldg(zrow + start + R);   // ... which the next WARP owns
     if (RAW && add_noise && !noise) {
         const uint32_t key = hash_key(seed, offset, (uint64_t)(q0 + idx0));
 #pragma unroll
@@ -484,6 +486,190 @@ composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
     }
 }
 
+// ---- 256 < N <= 1024: the same run layout with W = ceil(N / 256) warps per ray (one block = one ray at a time).  Warp w owns
+// samples [256 w, 256 w + 256) with R = 8 per lane; transmittance is multiplicative, so each warp works relative to its own
+// first sample and the products of the earlier warps' segments (exchanged through shared memory) scale it afterwards; the
+// per-ray sums and the backward's suffix sums are combined the same way.  No serial pass over the ray, same registers.
+constexpr int kRunR = 8;
+template <bool RAW, int W>
+__global__ void __launch_bounds__(W * 32)
+composite_fwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
+                          float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, float* __restrict__ comp,
+                          float* __restrict__ weights, float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N,
+                          uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0) {
+    constexpr int R = kRunR;
+    if (step_dev) offset += 8 * *step_dev;
+    __shared__ float s_prod[2][W], s_sum[2][W][5];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
+    const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
+    const bool has_rn = ray_norm != nullptr;
+    const int start = warp * 32 * R + lane * R;
+    const int cnt = max(0, min(R, N - start));
+    int par = 0;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x, par ^= 1) {
+        const float rn = has_rn ? __ldg(ray_norm + b) : 1.0f;
+        const int64_t q0 = b * N + start;
+        RunSamples<RAW, R> s;
+        const float prod = run_forward<RAW, R, false>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
+                                                cnt, N, inf_last, rn, has_rn, eps, idx0, true);
+        const float incl = warp_scan_mul(prod, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        if (lane == 31) s_prod[par][warp] = incl;
+        __syncthreads();
+        float carry = 1.0f;                                                  // product over the earlier warps' segments
+#pragma unroll
+        for (int v = 0; v < W; ++v) if (v < warp) carry *= s_prod[par][v];
+        excl *= carry;
+        float sw = 0.f, swz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (k < cnt) {
+                float w = (excl * s.Tl[k]) * s.alpha[k];
+                if (!isfinite(w)) w = 0.0f;
+                if (weights) weights[q0 + k] = w;
+                sw += w; swz = fmaf(w, s.z[k], swz); sr = fmaf(w, s.r[k], sr); sg = fmaf(w, s.g[k], sg); sb = fmaf(w, s.b[k], sb);
+            }
+        }
+        sw = warp_sum(sw); swz = warp_sum(swz); sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+        if (lane == 0) { s_sum[par][warp][0] = sw; s_sum[par][warp][1] = swz; s_sum[par][warp][2] = sr; s_sum[par][warp][3] = sg; s_sum[par][warp][4] = sb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sw = swz = sr = sg = sb = 0.f;
+#pragma unroll
+            for (int v = 0; v < W; ++v) { sw += s_sum[par][v][0]; swz += s_sum[par][v][1]; sr += s_sum[par][v][2]; sg += s_sum[par][v][3]; sb += s_sum[par][v][4]; }
+            const float acc = fminf(fmaxf(sw, 0.0f), 1.0f);
+            const float bg = white ? (1.0f - acc) : 0.0f;
+            comp[b * 3 + 0] = finalize_color(sr + bg);
+            comp[b * 3 + 1] = finalize_color(sg + bg);
+            comp[b * 3 + 2] = finalize_color(sb + bg);
+            if (acc_out) acc_out[b] = acc;
+            if (depth_out) depth_out[b] = swz / (acc + eps);
+        }
+    }
+}
+
+template <bool RAW, int W>
+__global__ void __launch_bounds__(W * 32)
+composite_bwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
+                          float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
+                          const float* __restrict__ g_weights, const float* __restrict__ g_acc, const float* __restrict__ g_depth,
+                          float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma, int64_t B, int N, uint32_t flags, float eps,
+                          uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0, const float* __restrict__ target,
+                          float loss_scale) {
+    constexpr int R = kRunR;
+    if (step_dev) offset += 8 * *step_dev;
+    __shared__ float s_prod[2][W], s_sum[2][W][5], s_tot[2][W];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool white = flags & NSB_WHITE_BKGD, inf_last = flags & NSB_INFINITE_LAST_BIN;
+    const bool add_noise = RAW && (flags & NSB_TRAINING) && noise_std > 0.0f;
+    const bool softplus = RAW && (flags & NSB_SIGMA_SOFTPLUS);
+    const bool has_rn = ray_norm != nullptr;
+    const int start = warp * 32 * R + lane * R;
+    const int cnt = max(0, min(R, N - start));
+    int par = 0;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x, par ^= 1) {
+        const float rn = has_rn ? __ldg(ray_norm + b) : 1.0f;
+        const int64_t q0 = b * N + start;
+        RunSamples<RAW, R> s;
+        const float prod = run_forward<RAW, R, false>(s, rgb_or_raw, sigma, noise, noise_std, add_noise, softplus, seed, offset, z + b * N, q0, start,
+                                                cnt, N, inf_last, rn, has_rn, eps, idx0, true);
+        float gwv[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) gwv[k] = (g_weights && k < cnt) ? __ldg(g_weights + q0 + k) : 0.0f;
+        const float incl = warp_scan_mul(prod, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        if (lane == 31) s_prod[par][warp] = incl;
+        __syncthreads();
+        float carry = 1.0f;
+#pragma unroll
+        for (int v = 0; v < W; ++v) if (v < warp) carry *= s_prod[par][v];
+        excl *= carry;
+        float sw = 0.f, swz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+        float T[R], w[R];
+        bool fin[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            T[k] = excl * s.Tl[k];
+            const float wraw = T[k] * s.alpha[k];
+            fin[k] = isfinite(wraw);
+            w[k] = (k < cnt && fin[k]) ? wraw : 0.0f;
+            sw += w[k]; swz = fmaf(w[k], s.z[k], swz); sr = fmaf(w[k], s.r[k], sr); sg = fmaf(w[k], s.g[k], sg); sb = fmaf(w[k], s.b[k], sb);
+        }
+        sw = warp_sum(sw); swz = warp_sum(swz); sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+        if (lane == 0) { s_sum[par][warp][0] = sw; s_sum[par][warp][1] = swz; s_sum[par][warp][2] = sr; s_sum[par][warp][3] = sg; s_sum[par][warp][4] = sb; }
+        __syncthreads();
+        sw = swz = sr = sg = sb = 0.f;                                       // every thread: the ray's totals, same order in every thread
+#pragma unroll
+        for (int v = 0; v < W; ++v) { sw += s_sum[par][v][0]; swz += s_sum[par][v][1]; sr += s_sum[par][v][2]; sg += s_sum[par][v][3]; sb += s_sum[par][v][4]; }
+        const float acc = fminf(fmaxf(sw, 0.0f), 1.0f);
+        const float bg = white ? (1.0f - acc) : 0.0f;
+        float gc[3];
+        {
+            const float craw[3] = {sr + bg, sg + bg, sb + bg};
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gc[c] = (isfinite(craw[c]) && craw[c] >= 0.0f && craw[c] <= 1.0f) ? comp_grad(g_comp, target, loss_scale, craw[c], b * 3 + c) : 0.0f;
+        }
+        const float inv = 1.0f / (acc + eps);
+        const float gd = g_depth ? __ldg(g_depth + b) : 0.0f;
+        float g_accv = g_acc ? __ldg(g_acc + b) : 0.0f;
+        if (white) g_accv -= gc[0] + gc[1] + gc[2];
+        g_accv -= gd * swz * inv * inv;
+        const float g_s = (sw >= 0.0f && sw <= 1.0f) ? g_accv : 0.0f;
+        float G[R], lane_total = 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            G[k] = 0.f;
+            if (k < cnt && fin[k]) G[k] = gwv[k] + g_s + s.r[k] * gc[0] + s.g[k] * gc[1] + s.b[k] * gc[2] + gd * s.z[k] * inv;
+            lane_total = fmaf(G[k], w[k], lane_total);
+        }
+        float sfx = lane_total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_down_sync(0xffffffffu, sfx, d);
+            if (lane + d < 32) sfx += t;
+        }
+        if (lane == 0) s_tot[par][warp] = sfx;                               // this warp's segment total of G w
+        __syncthreads();
+        float suffix = sfx - lane_total;                                     // later lanes of this warp ...
+#pragma unroll
+        for (int v = 0; v < W; ++v) if (v > warp) suffix += s_tot[par][v];   // ... and the later warps' segments
+#pragma unroll
+        for (int k = R - 1; k >= 0; --k) {
+            if (k < cnt) {
+                const float f = (1.0f - s.alpha[k]) + eps;
+                const float d_alpha = G[k] * T[k] - suffix * rcp_approx(f);
+                suffix = fmaf(G[k], w[k], suffix);
+                const float d_sdt = d_alpha * (1.0f - s.alpha[k]);
+                const float sd = s.sigma[k] * s.delta[k];
+                const float ds = (sd >= 0.0f && sd <= 60.0f) ? d_sdt * s.delta[k] : 0.0f;
+                if (RAW) {
+                    float4 o;
+                    o.x = w[k] * gc[0] * s.r[k] * (1.0f - s.r[k]);
+                    o.y = w[k] * gc[1] * s.g[k] * (1.0f - s.g[k]);
+                    o.z = w[k] * gc[2] * s.b[k] * (1.0f - s.b[k]);
+                    o.w = softplus ? (s.pre[k] > 20.0f ? ds : ds * fast_sigmoid(s.pre[k])) : (s.pre[k] > 0.0f ? ds : 0.0f);
+                    reinterpret_cast<float4*>(d_rgb_or_raw)[q0 + k] = o;
+                } else {
+                    d_rgb_or_raw[(q0 + k) * 3 + 0] = w[k] * gc[0];
+                    d_rgb_or_raw[(q0 + k) * 3 + 1] = w[k] * gc[1];
+                    d_rgb_or_raw[(q0 + k) * 3 + 2] = w[k] * gc[2];
+                    d_sigma[q0 + k] = ds;
+                }
+            }
+        }
+    }
+}
+
+static int runw_grid(int64_t B, int W) {
+    const int64_t cap = (int64_t)num_sms() * (64 / W);       // up to 64 warps per SM
+    return (int)(B < cap ? (B > 0 ? B : 1) : cap);
+}
+
 static int run_grid(int64_t B) {
     const int64_t want = cdiv(B, kRunWarps);
     const int64_t cap = (int64_t)num_sms() * 32;
@@ -496,6 +682,15 @@ static int launch_fwd_run(const float* a, const float* sigma, const float* noise
                           uint64_t off, void* stream, int64_t idx0 = 0) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
+    if (N > 256) {
+        const int W = (N + 255) / 256, gridw = runw_grid(B, W);
+        if (W == 2) composite_fwd_runw_kernel<RAW, 2><<<gridw, 64, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
+        else if (W == 3) composite_fwd_runw_kernel<RAW, 3><<<gridw, 96, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
+        else if (W == 4) composite_fwd_runw_kernel<RAW, 4><<<gridw, 128, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
+        else return NSB_E_BADARG;
+        NSB_LAUNCH_CHECK("composite_fwd_runw_kernel");
+        return NSB_OK;
+    }
     const int grid = run_grid(B);
 #define NSB_RUN_FWD(RR)                                                                                                              \
     case RR:                                                                                                                         \
@@ -518,6 +713,15 @@ static int launch_bwd_run(const float* a, const float* sigma, const float* noise
                           float loss_scale = 0.f) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
+    if (N > 256) {
+        const int W = (N + 255) / 256, gridw = runw_grid(B, W);
+        if (W == 2) composite_bwd_runw_kernel<RAW, 2><<<gridw, 64, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
+        else if (W == 3) composite_bwd_runw_kernel<RAW, 3><<<gridw, 96, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
+        else if (W == 4) composite_bwd_runw_kernel<RAW, 4><<<gridw, 128, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
+        else return NSB_E_BADARG;
+        NSB_LAUNCH_CHECK("composite_bwd_runw_kernel");
+        return NSB_OK;
+    }
     const int grid = run_grid(B);
 #define NSB_RUN_BWD(RR)                                                                                                             \
     case RR:                                                                                                                         \

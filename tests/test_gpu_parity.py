@@ -148,20 +148,54 @@ def test_compositor_fwd_bwd(nsb, tag, white, inf_last, use_rn):
 
 def test_compositor_ragged_and_long_rays(nsb):
     rng = np.random.default_rng(3)
-    for B, Nn in [(1, 1), (3, 7), (5, 33), (2, 768), (1, 1500)]:
+    # 1..256: one warp per ray; 257..1024: two to four warps per ray; beyond: the strided kernels
+    for B, Nn in [(1, 1), (3, 7), (5, 33), (3, 256), (3, 257), (2, 300), (2, 512), (3, 513), (2, 768), (2, 1000), (2, 1024), (2, 1025), (1, 1500)]:
         z = np.sort(rng.uniform(2, 6, (B, Nn)).astype(np.float32), -1)
         rgb = rng.uniform(0, 1, (B, Nn, 3)).astype(np.float32); sig = rng.uniform(0, 3, (B, Nn)).astype(np.float32)
         rn = rng.uniform(1, 1.1, (B, 1)).astype(np.float32)
         comp, w, acc, depth, cache = O.volume_render_rays(rgb, sig, z, rn, True, 1e-10, True, keep=True)
         tr, ts = T(rgb).requires_grad_(), T(sig).requires_grad_()
         c2, w2, a2, d2 = nsb.volume_render_rays(tr, ts, T(z), T(rn), True, 1e-10, True)
-        close(N(c2), comp); close(N(w2), w, 1e-4, 1e-7); close(N(a2), acc); close(N(d2), depth, 1e-4, 1e-5)
+        # weights: alpha = 1 - exp(-sigma delta) carries the ABSOLUTE error of exp near 1 (1 ulp = 6e-8), whatever its own size
+        close(N(c2), comp); close(N(w2), w, 1e-4, 2.5e-7); close(N(a2), acc); close(N(d2), depth, 1e-4, 1e-5)
         gc = rng.standard_normal((B, 3)).astype(np.float32)
         drgb, dsig = O.volume_render_backward(cache, gc)
         gr = torch.autograd.grad((c2 * T(gc)).sum(), [tr, ts])
         close(N(gr[0]), drgb, 1e-4, 1e-6); close(N(gr[1]), dsig, 5e-4, 2e-5)
     assert nsb.volume_render_rays(torch.zeros((0, 4, 3), device=DEV), torch.zeros((0, 4), device=DEV),
                                   torch.zeros((0, 4), device=DEV))[0].shape == (0, 3)
+
+
+@pytest.mark.parametrize("Nn", [192, 257, 320, 576, 768, 1024, 1100])
+def test_raw_compositor_one_to_four_warps_per_ray(nsb, Nn):
+    """The fused raw -> activations -> composite kernels (forward and backward, explicit sigma noise) at sample counts on both
+    sides of every kernel boundary (256 / 512 / 768 / 1024) against the oracle's compositor and the chain rule in float64."""
+    from nerf_sandbox_b200 import _lib
+    L = _lib.lib(); st = _lib.stream()
+    rng = np.random.default_rng(Nn)
+    B = 5
+    raw = rng.standard_normal((B, Nn, 4)).astype(np.float32); raw[..., 3] = raw[..., 3] * 2 + 0.5
+    noise = rng.standard_normal((B, Nn)).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (B, Nn)).astype(np.float32), -1)
+    rn = rng.uniform(1, 1.1, (B, 1)).astype(np.float32)
+    rgb = 1 / (1 + np.exp(-raw[..., :3].astype(np.float64)))
+    pre = raw[..., 3].astype(np.float64) + noise.astype(np.float64) * 0.7
+    sig = np.maximum(pre, 0)
+    comp, w, acc, depth, cache = O.volume_render_rays(rgb.astype(np.float32), sig.astype(np.float32), z, rn, True, 1e-10, False, keep=True)
+    t_raw, t_noise, t_z, t_rn = T(raw.reshape(-1, 4)), T(noise), T(z), T(rn.reshape(-1))
+    comp_d = torch.empty(B, 3, device=DEV); w_d = torch.empty(B, Nn, device=DEV); acc_d = torch.empty(B, device=DEV); dep_d = torch.empty(B, device=DEV)
+    flags = _lib.WHITE_BKGD | _lib.TRAINING
+    _lib.check(L.nsb_composite_raw_fwd(_lib.ptr(t_raw), _lib.ptr(t_noise), 0.7, _lib.ptr(t_z), _lib.ptr(t_rn), _lib.ptr(comp_d), _lib.ptr(w_d),
+                                       _lib.ptr(acc_d), _lib.ptr(dep_d), B, Nn, flags, 0, 0, st))
+    close(N(comp_d), comp); close(N(w_d), w, 1e-4, 2.5e-7); close(N(acc_d), acc.reshape(-1)); close(N(dep_d), depth.reshape(-1), 1e-4, 1e-5)
+    gc = rng.standard_normal((B, 3)).astype(np.float32)
+    drgb, dsig = O.volume_render_backward(cache, gc)
+    d_ref = np.concatenate([drgb * rgb * (1 - rgb), (dsig * (pre > 0))[..., None]], -1)
+    d_raw = torch.empty(B * Nn, 4, device=DEV)
+    _lib.check(L.nsb_composite_raw_bwd(_lib.ptr(t_raw), _lib.ptr(t_noise), 0.7, _lib.ptr(t_z), _lib.ptr(t_rn), _lib.ptr(T(gc)), _lib.ptr(d_raw),
+                                       B, Nn, flags, 0, 0, st))
+    got = N(d_raw).reshape(B, Nn, 4)
+    close(got[..., :3], d_ref[..., :3], 2e-4, 1e-6); close(got[..., 3], d_ref[..., 3], 5e-4, 2e-5)
 
 
 # ---------------------------------------------------------------------------------------------------- K1 MLP (fp32 mode)
