@@ -253,7 +253,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
 }
 
 // =====================================================================================================================
-// Run layout (N <= 256 samples per ray -- every vanilla shape: 64 coarse, 192 merged; 256 < N <= 1024: the multi-warp variant
+// Run layout (N <= 192 samples per ray -- every vanilla shape: 64 coarse, 192 merged; 192 < N <= 1024: the multi-warp variant
 // further down): lane l of the ray's warp owns the
 // CONTIGUOUS run [l R, l R + R) of samples, R = ceil(N / 32) <= 8, all in registers.  The exclusive cumprod is a serial
 // product inside the run plus ONE multiplicative warp scan over the 32 run products per ray (instead of one scan per 32
@@ -263,6 +263,9 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
 // The strided kernels above remain for N > 1024.
 // =====================================================================================================================
 constexpr int kRunWarps = 4;
+// One warp per ray up to 192 samples (R <= 6); above, 2-4 warps per ray with R = 4..6 each (7, 8 beyond 768): measured, the R = 8
+// single-warp kernels (120-160 registers) stream at 0.53-0.58 of the HBM roof where R <= 6 reaches 0.7-0.86.
+constexpr int kRunOneWarpMaxN = 192;
 // NSB_K3_STRIDED=1 forces the strided kernels for every N (A/B timing and debugging)
 static const int kRunMaxN = [] { const char* e = getenv("NSB_K3_STRIDED"); return (e && e[0] == '1') ? 0 : 1024; }();   // up to 4 warps per ray
 
@@ -486,18 +489,16 @@ composite_bwd_run_kernel(const float* __restrict__ rgb_or_raw, const float* __re
     }
 }
 
-// ---- 256 < N <= 1024: the same run layout with W = ceil(N / 256) warps per ray (one block = one ray at a time).  Warp w owns
-// samples [256 w, 256 w + 256) with R = 8 per lane; transmittance is multiplicative, so each warp works relative to its own
+// ---- 192 < N <= 1024: the same run layout with W = 2..4 warps per ray (one block = one ray at a time).  Warp w owns
+// samples [32 R w, 32 R (w + 1)) with R = ceil(N / (32 W)) per lane (an even split: no warp is left with a stub); transmittance is multiplicative, so each warp works relative to its own
 // first sample and the products of the earlier warps' segments (exchanged through shared memory) scale it afterwards; the
 // per-ray sums and the backward's suffix sums are combined the same way.  No serial pass over the ray, same registers.
-constexpr int kRunR = 8;
-template <bool RAW, int W>
+template <bool RAW, int W, int R>
 __global__ void __launch_bounds__(W * 32)
 composite_fwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
                           float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, float* __restrict__ comp,
                           float* __restrict__ weights, float* __restrict__ acc_out, float* __restrict__ depth_out, int64_t B, int N,
                           uint32_t flags, float eps, uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0) {
-    constexpr int R = kRunR;
     if (step_dev) offset += 8 * *step_dev;
     __shared__ float s_prod[2][W], s_sum[2][W][5];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,7 +552,7 @@ composite_fwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __r
     }
 }
 
-template <bool RAW, int W>
+template <bool RAW, int W, int R>
 __global__ void __launch_bounds__(W * 32)
 composite_bwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ sigma, const float* __restrict__ noise,
                           float noise_std, const float* __restrict__ z, const float* __restrict__ ray_norm, const float* __restrict__ g_comp,
@@ -559,7 +560,6 @@ composite_bwd_runw_kernel(const float* __restrict__ rgb_or_raw, const float* __r
                           float* __restrict__ d_rgb_or_raw, float* __restrict__ d_sigma, int64_t B, int N, uint32_t flags, float eps,
                           uint64_t seed, uint64_t offset, const uint64_t* step_dev, int64_t idx0, const float* __restrict__ target,
                           float loss_scale) {
-    constexpr int R = kRunR;
     if (step_dev) offset += 8 * *step_dev;
     __shared__ float s_prod[2][W], s_sum[2][W][5], s_tot[2][W];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -682,12 +682,16 @@ static int launch_fwd_run(const float* a, const float* sigma, const float* noise
                           uint64_t off, void* stream, int64_t idx0 = 0) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
-    if (N > 256) {
-        const int W = (N + 255) / 256, gridw = runw_grid(B, W);
-        if (W == 2) composite_fwd_runw_kernel<RAW, 2><<<gridw, 64, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
-        else if (W == 3) composite_fwd_runw_kernel<RAW, 3><<<gridw, 96, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
-        else if (W == 4) composite_fwd_runw_kernel<RAW, 4><<<gridw, 128, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
+    if (N > kRunOneWarpMaxN) {
+        const int W = N <= 768 ? (N + 191) / 192 : 4, RW = (N + 32 * W - 1) / (32 * W), gridw = runw_grid(B, W);
+#define NSB_RUNW_FWD(WW, RR) \
+        else if (W == WW && RW == RR) composite_fwd_runw_kernel<RAW, WW, RR><<<gridw, WW * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, comp, weights, acc, depth, B, N, flags, eps, seed, off, g_step_dev, idx0);
+        if (false) {}
+        NSB_RUNW_FWD(2, 4) NSB_RUNW_FWD(2, 5) NSB_RUNW_FWD(2, 6)
+        NSB_RUNW_FWD(3, 5) NSB_RUNW_FWD(3, 6)
+        NSB_RUNW_FWD(4, 5) NSB_RUNW_FWD(4, 6) NSB_RUNW_FWD(4, 7) NSB_RUNW_FWD(4, 8)
         else return NSB_E_BADARG;
+#undef NSB_RUNW_FWD
         NSB_LAUNCH_CHECK("composite_fwd_runw_kernel");
         return NSB_OK;
     }
@@ -713,12 +717,16 @@ static int launch_bwd_run(const float* a, const float* sigma, const float* noise
                           float loss_scale = 0.f) {
     const int R = (N + 31) / 32;
     cudaStream_t st = as_stream(stream);
-    if (N > 256) {
-        const int W = (N + 255) / 256, gridw = runw_grid(B, W);
-        if (W == 2) composite_bwd_runw_kernel<RAW, 2><<<gridw, 64, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
-        else if (W == 3) composite_bwd_runw_kernel<RAW, 3><<<gridw, 96, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
-        else if (W == 4) composite_bwd_runw_kernel<RAW, 4><<<gridw, 128, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
+    if (N > kRunOneWarpMaxN) {
+        const int W = N <= 768 ? (N + 191) / 192 : 4, RW = (N + 32 * W - 1) / (32 * W), gridw = runw_grid(B, W);
+#define NSB_RUNW_BWD(WW, RR) \
+        else if (W == WW && RW == RR) composite_bwd_runw_kernel<RAW, WW, RR><<<gridw, WW * 32, 0, st>>>(a, sigma, noise, noise_std, z, rn, g_comp, g_w, g_a, g_d, d0, d1, B, N, flags, eps, seed, off, g_step_dev, idx0, target, loss_scale);
+        if (false) {}
+        NSB_RUNW_BWD(2, 4) NSB_RUNW_BWD(2, 5) NSB_RUNW_BWD(2, 6)
+        NSB_RUNW_BWD(3, 5) NSB_RUNW_BWD(3, 6)
+        NSB_RUNW_BWD(4, 5) NSB_RUNW_BWD(4, 6) NSB_RUNW_BWD(4, 7) NSB_RUNW_BWD(4, 8)
         else return NSB_E_BADARG;
+#undef NSB_RUNW_BWD
         NSB_LAUNCH_CHECK("composite_bwd_runw_kernel");
         return NSB_OK;
     }

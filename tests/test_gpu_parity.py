@@ -148,8 +148,8 @@ def test_compositor_fwd_bwd(nsb, tag, white, inf_last, use_rn):
 
 def test_compositor_ragged_and_long_rays(nsb):
     rng = np.random.default_rng(3)
-    # 1..256: one warp per ray; 257..1024: two to four warps per ray; beyond: the strided kernels
-    for B, Nn in [(1, 1), (3, 7), (5, 33), (3, 256), (3, 257), (2, 300), (2, 512), (3, 513), (2, 768), (2, 1000), (2, 1024), (2, 1025), (1, 1500)]:
+    # 1..192: one warp per ray; 193..1024: two to four warps per ray; beyond: the strided kernels
+    for B, Nn in [(1, 1), (3, 7), (5, 33), (3, 192), (3, 193), (3, 256), (3, 257), (2, 300), (2, 512), (3, 513), (2, 768), (2, 1000), (2, 1024), (2, 1025), (1, 1500)]:
         z = np.sort(rng.uniform(2, 6, (B, Nn)).astype(np.float32), -1)
         rgb = rng.uniform(0, 1, (B, Nn, 3)).astype(np.float32); sig = rng.uniform(0, 3, (B, Nn)).astype(np.float32)
         rn = rng.uniform(1, 1.1, (B, 1)).astype(np.float32)
@@ -166,7 +166,7 @@ def test_compositor_ragged_and_long_rays(nsb):
                                   torch.zeros((0, 4), device=DEV))[0].shape == (0, 3)
 
 
-@pytest.mark.parametrize("Nn", [192, 257, 320, 576, 768, 1024, 1100])
+@pytest.mark.parametrize("Nn", [192, 200, 257, 320, 400, 576, 600, 768, 800, 1024, 1100])
 def test_raw_compositor_one_to_four_warps_per_ray(nsb, Nn):
     """The fused raw -> activations -> composite kernels (forward and backward, explicit sigma noise) at sample counts on both
     sides of every kernel boundary (256 / 512 / 768 / 1024) against the oracle's compositor and the chain rule in float64."""
