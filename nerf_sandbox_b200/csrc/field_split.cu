@@ -24,7 +24,10 @@
 namespace nsb {
 namespace tc {
 
-constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16;                   // one K = 16 MMA step per chunk
+constexpr int SG_BM = 128, SG_BK = 16;                                // output rows per CTA; one K = 16 MMA step per chunk
+// output columns per CTA (BN): 128 with two CTAs per SM (forward, dgrad: frequent epilogues overlap the other CTA's main loop),
+// 256 with one CTA per SM for wgrad (long contraction, rare epilogue): the A pieces are converted once for both column halves
+// and each MMA reads A once for 256 columns -- 1.8x less shared-memory traffic per FLOP
 constexpr int SG_CONV = 256;                                          // converter threads = pieces per operand chunk: 128 rows x 2 groups of 8 k
 constexpr int SG_THREADS = SG_CONV + 64;                              // + the MMA warp + the weight-image producer warp
 constexpr int SG_TERM_BYTES = SG_BM * SG_BK * 2;                      // one bf16 term image of a 128 x 16 operand chunk: [k/8][row][8]
@@ -32,16 +35,19 @@ constexpr int SG_RAW_BYTES = SG_BM * SG_BK * 4;                       // the sam
 constexpr int SG_FIFO = 4;                                            // raw chunks in flight per CTA (cp.async groups)
 constexpr int SG_IMG_TERMS = 3;                                       // pre-split weight images always carry three terms
 constexpr int SG_IMG_CHUNK = SG_IMG_TERMS * SG_TERM_BYTES;            // 12 KB per (128-row tile, K = 16 chunk)
-constexpr int SG_EPI_LD = SG_BN + 4;                                   // row stride (floats) of the epilogue's shared-memory tile
-constexpr uint32_t SG_TMEM_COLS = 256;      // two fp32 accumulators of 128 columns: main (x0 * y0) and cross (every other term product)
+// TMEM: two fp32 accumulators of BN columns: main (x0 * y0) and cross (every other term product)
 
-template <int NT> struct SgCfg {
-    static constexpr int kStageBytes = 2 * NT * SG_TERM_BYTES;            // converted stage: A terms then B terms
+template <int NT, int BN> struct SgCfg {
+    static constexpr int kBTiles = BN / 128;                              // B is handled as 128-row operand chunks
+    static constexpr int kStageBytes = (1 + kBTiles) * NT * SG_TERM_BYTES;   // converted stage: A terms, then B terms ([term][k/8][BN rows][8])
     static constexpr int kStages = 2;
     static constexpr int kFifoOfs = kStages * kStageBytes;
-    static constexpr int kBarOfs = kFifoOfs + SG_FIFO * 2 * SG_RAW_BYTES;
-    static_assert(kBarOfs >= SG_BM * SG_EPI_LD * 4, "the epilogue tile reuses the stage + FIFO area");
-    static constexpr int kSmemBytes = kBarOfs + 128;                      // + barriers and the TMEM slot; NT = 3: 112.1 KB -> two CTAs per SM
+    static constexpr int kFifoSlot = (1 + kBTiles) * SG_RAW_BYTES;        // raw chunk: A, then B
+    static constexpr int kBarOfs = kFifoOfs + SG_FIFO * kFifoSlot;
+    static constexpr int kEpiLd = BN + 4;                                 // row stride (floats) of the epilogue's shared-memory tile
+    static_assert(kBarOfs >= SG_BM * kEpiLd * 4, "the epilogue tile reuses the stage + FIFO area");
+    static constexpr int kSmemBytes = kBarOfs + 128;                      // + barriers and the TMEM slot; NT = 3: 112.1 KB (BN 128) / 168.1 KB (BN 256)
+    static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16_pair(float lo, float hi) {
@@ -109,8 +115,8 @@ __device__ __forceinline__ void sg_fetch(const float* __restrict__ P, int64_t ld
     }
 }
 // read this thread's slot back, split, write the term images of the converted stage
-template <bool TR, int NT>
-__device__ __forceinline__ float sg_convert(const uint8_t* slot, uint8_t* img, int tid) {
+template <bool TR, int NT, int ROWS = 128>       // ROWS: rows of the operand image this piece belongs to (k-group stride = 16 ROWS bytes)
+__device__ __forceinline__ float sg_convert(const uint8_t* slot, uint8_t* img, int tid, int row_ofs = 0) {
     float x[8];
     if (!TR) {
         const float4 a = *reinterpret_cast<const float4*>(slot + tid * 16), b = *reinterpret_cast<const float4*>(slot + SG_CONV * 16 + tid * 16);
@@ -125,16 +131,17 @@ __device__ __forceinline__ float sg_convert(const uint8_t* slot, uint8_t* img, i
     uint4 terms[NT];
     split8<NT>(x, terms);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) *reinterpret_cast<uint4*>(img + t * SG_TERM_BYTES + kg * 2048 + r * 16) = terms[t];
+    for (int t = 0; t < NT; ++t) *reinterpret_cast<uint4*>(img + t * (ROWS * SG_BK * 2) + kg * (ROWS * 16) + (row_ofs + r) * 16) = terms[t];
     return sum8;
 }
 
 // BIMG: the B operand is a weight matrix whose term images were written once per optimiser step (split_pack_kernel): a
 // producer thread bulk-copies the 4 KB term images of each chunk straight into the converted stage, and the converter
 // threads only handle A.
-template <bool AT, bool BT, int EPI, int NT, bool BIMG>
-__global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArgs g, int tiles_n, int tiles_mn) {
-    using Cfg = SgCfg<NT>;
+template <bool AT, bool BT, int EPI, int NT, bool BIMG, int BN>
+__global__ void __launch_bounds__(SG_THREADS, BN == 128 ? 2 : 1) split_gemm_kernel(const GemmArgs g, int tiles_n, int tiles_mn) {
+    using Cfg = SgCfg<NT, BN>;
+    static_assert(BN == 128 || !BIMG, "weight images are tiled for 128 columns");
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar_empty = sbase + Cfg::kBarOfs;                               // per converted stage: its MMAs have completed
@@ -152,15 +159,19 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
         kend = kbeg + g.k_per_split < g.Kdim ? kbeg + g.k_per_split : g.Kdim;
     }
     const int64_t tn = tile % tiles_n;
-    const int64_t m0 = (tile / tiles_n) * SG_BM, n0 = tn * SG_BN;
+    const int64_t m0 = (tile / tiles_n) * SG_BM, n0 = tn * BN;
     const int64_t nchunks = kend > kbeg ? (kend - kbeg + SG_BK - 1) / SG_BK : 0;
 
     // raw chunks 0 .. SG_FIFO-2 on their way before anything else
     auto fetch = [&](int64_t c) {
         if (c < nchunks && tid < SG_CONV) {
-            const uint32_t slot = sbase + Cfg::kFifoOfs + (uint32_t)(c % SG_FIFO) * (2 * SG_RAW_BYTES);
+            const uint32_t slot = sbase + Cfg::kFifoOfs + (uint32_t)(c % SG_FIFO) * Cfg::kFifoSlot;
             sg_fetch<AT>(g.A, g.lda, m0, g.Mdim, kbeg + c * SG_BK, kend, tid, slot);
-            if (!BIMG) sg_fetch<BT>(g.B, g.ldb, n0, g.Ndim, kbeg + c * SG_BK, kend, tid, slot + SG_RAW_BYTES);
+            if (!BIMG) {
+#pragma unroll
+                for (int h = 0; h < Cfg::kBTiles; ++h)
+                    sg_fetch<BT>(g.B, g.ldb, n0 + 128 * h, g.Ndim, kbeg + c * SG_BK, kend, tid, slot + (1 + h) * SG_RAW_BYTES);
+            }
         }
         cp_async_commit();                                   // one group per chunk index, possibly empty: keeps the wait count uniform
     };
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     }
     if (warp == SG_CONV / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                     "r"(SG_TMEM_COLS)
+                     "r"(Cfg::kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -183,9 +194,11 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // kind::f16, D = f32, A = B = bf16, both K-major, N = 128, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SG_BN >> 3) << 17) | ((uint32_t)(SG_BM >> 4) << 24);
+    // kind::f16, D = f32, A = B = bf16, both K-major, N = BN, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SG_BM >> 4) << 24);
     const uint64_t dhi = desc_hi(2048, 128);          // LBO: between the two 8-wide k groups of the K = 16 step; SBO: between 8-row groups
+    const uint64_t dhi_b = desc_hi(BN * 16, 128);     // the B image has BN rows per k group
+    constexpr int kBTerm = BN * SG_BK * 2;            // bytes of one B term image
     if (tid < SG_CONV) {
         // ---- converters: raw FIFO -> bf16 term images of stage c % 2; nothing here waits for the MMA issue
         float colsum = 0.f;                                      // wgrad: sum over this CTA's points of dY[., m0 + r] (this thread's k group)
@@ -195,10 +208,14 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
             const int s = (int)(c % Cfg::kStages);
             const int64_t use = c / Cfg::kStages;
             if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((use - 1) & 1));      // the MMAs that read this stage have completed
-            const uint8_t* slot = smem + Cfg::kFifoOfs + (c % SG_FIFO) * (2 * SG_RAW_BYTES);
+            const uint8_t* slot = smem + Cfg::kFifoOfs + (c % SG_FIFO) * Cfg::kFifoSlot;
             uint8_t* stage = smem + s * Cfg::kStageBytes;
             colsum += sg_convert<AT, NT>(slot, stage, tid);
-            if (!BIMG) sg_convert<BT, NT>(slot + SG_RAW_BYTES, stage + NT * SG_TERM_BYTES, tid);
+            if (!BIMG) {
+#pragma unroll
+                for (int h = 0; h < Cfg::kBTiles; ++h)
+                    sg_convert<BT, NT, BN>(slot + (1 + h) * SG_RAW_BYTES, stage + NT * SG_TERM_BYTES, tid, 128 * h);
+            }
             fence_async_smem();
             mbar_arrive(bar_full + 8 * s);
         }
@@ -226,11 +243,11 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
 #pragma unroll
                     for (int ta = 0; ta <= sum; ++ta) {
                         const int tb = sum - ta;
-                        tc_mma(tmem_base + 128, desc_at(dhi, a0 + ta * SG_TERM_BYTES), desc_at(dhi, b0 + tb * SG_TERM_BYTES), idesc,
+                        tc_mma(tmem_base + BN, desc_at(dhi, a0 + ta * SG_TERM_BYTES), desc_at(dhi_b, b0 + tb * kBTerm), idesc,
                                (c == 0 && sum == NT - 1 && ta == 0) ? 0u : 1u);
                     }
                 }
-                tc_mma(tmem_base, desc_at(dhi, a0), desc_at(dhi, b0), idesc, c == 0 ? 0u : 1u);
+                tc_mma(tmem_base, desc_at(dhi, a0), desc_at(dhi_b, b0), idesc, c == 0 ? 0u : 1u);
                 tc_commit(bar_empty + 8 * s);
                 if (c + 1 == nchunks) tc_commit(bar_done);
             }
@@ -250,23 +267,24 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     if (nchunks > 0 && tid < SG_CONV) {
         mbar_wait(bar_done, 0);
         tc_fence_after();
-        // ---- epilogue, part 1: TMEM -> shared memory.  Thread = accumulator row (TMEM lane), warps 0-3 columns 0-63, warps
-        // 4-7 columns 64-127; main + cross added here.  The tile goes to the (now idle) stage / FIFO area as 128 rows of
-        // SG_EPI_LD floats (padded: 16-byte stores of 8 consecutive rows hit 32 distinct banks).
+        // ---- epilogue, part 1: TMEM -> shared memory.  Thread = accumulator row (TMEM lane), warps 0-3 the first half of the
+        // columns, warps 4-7 the second; main + cross added here.  The tile goes to the (now idle) stage / FIFO area as 128
+        // rows of kEpiLd floats (padded: 16-byte stores of 8 consecutive rows hit 32 distinct banks).
+        constexpr int LD = Cfg::kEpiLd;
         float* tile_s = reinterpret_cast<float*>(smem);
         {
             const int rowl = 32 * (warp & 3) + lane;
-            const int cb = 64 * (warp >> 2);
+            const int cb = (BN / 2) * (warp >> 2);
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < BN / 32; ++cc) {
                 uint32_t v[16], vx[16];
                 tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb + 16 * cc), v);
-                tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 + cb + 16 * cc), vx);
+                tc_ld16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(BN + cb + 16 * cc), vx);
                 tc_wait_ld();
                 pin16(v); pin16(vx);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(tile_s + rowl * SG_EPI_LD + cb + 16 * cc + 4 * q) =
+                    *reinterpret_cast<float4*>(tile_s + rowl * LD + cb + 16 * cc + 4 * q) =
                         make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(vx[4 * q]), __uint_as_float(v[4 * q + 1]) + __uint_as_float(vx[4 * q + 1]),
                                     __uint_as_float(v[4 * q + 2]) + __uint_as_float(vx[4 * q + 2]), __uint_as_float(v[4 * q + 3]) + __uint_as_float(vx[4 * q + 3]));
             }
@@ -280,18 +298,18 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
                 const int64_t m = m0 + r;
                 if (m >= g.Mdim) break;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < BN / 32; ++q) {
                     const int64_t nn = n0 + 32 * q + lane;
-                    if (nn < g.n_valid) atomicAdd(g.C + m * g.ldc + nn, tile_s[r * SG_EPI_LD + 32 * q + lane]);
+                    if (nn < g.n_valid) atomicAdd(g.C + m * g.ldc + nn, tile_s[r * LD + 32 * q + lane]);
                 }
             }
-        } else if (n < g.Ndim) {
+        } else if (BN == 128 && n < g.Ndim) {
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (EPI == EPI_FWD) bb = __ldg(reinterpret_cast<const float4*>(g.bias + n));
             for (int r = warp; r < SG_BM; r += SG_CONV / 32) {
                 const int64_t m = m0 + r;
                 if (m >= g.Mdim) break;
-                float4 o = *reinterpret_cast<const float4*>(tile_s + r * SG_EPI_LD + 4 * lane);
+                float4 o = *reinterpret_cast<const float4*>(tile_s + r * LD + 4 * lane);
                 if (EPI == EPI_FWD) {
                     o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -314,7 +332,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) split_gemm_kernel(const GemmArg
     __syncthreads();
     if (warp == SG_CONV / 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(SG_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
     }
 }
 
@@ -346,22 +364,22 @@ __global__ void __launch_bounds__(256) split_pack_kernel(const float* __restrict
     }
 }
 
-template <bool AT, bool BT, int EPI, int NT, bool BIMG>
+template <bool AT, bool BT, int EPI, int NT, bool BIMG, int BN = 128>
 static int launch_split_gemm(const GemmArgs& g, cudaStream_t st) {
-    using Cfg = SgCfg<NT>;
-    auto kern = split_gemm_kernel<AT, BT, EPI, NT, BIMG>;
+    using Cfg = SgCfg<NT, BN>;
+    auto kern = split_gemm_kernel<AT, BT, EPI, NT, BIMG, BN>;
     static bool configured = false;          // per instantiation
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(split_gemm_kernel)");
         configured = true;
     }
-    const int64_t tiles_m = cdiv(g.Mdim, SG_BM), tiles_n = cdiv(g.Ndim, SG_BN);
+    const int64_t tiles_m = cdiv(g.Mdim, SG_BM), tiles_n = cdiv(g.Ndim, BN);
     int64_t splits = 1;
     GemmArgs a = g;
     if (EPI == EPI_WGRAD) {
-        // split the contraction (points) so that every SM holds two CTAs; k_per_split a multiple of the chunk
-        int64_t want = (int64_t)num_sms() * 2 / (tiles_m * tiles_n);
+        // split the contraction (points) so that every SM holds its two CTAs (one for BN = 256); k_per_split a multiple of the chunk
+        int64_t want = (int64_t)num_sms() * (BN == 128 ? 2 : 1) / (tiles_m * tiles_n);
         if (want < 1) want = 1;
         int64_t kps = cdiv(cdiv(g.Kdim, want), SG_BK) * SG_BK;
         if (kps < 256) kps = 256;
@@ -404,6 +422,12 @@ int split_pack(const float* params, void* packed, cudaStream_t st) {
     return NSB_OK;
 }
 
+// NSB_SPLIT_WGRAD_WIDE=0: 128-column CTAs for wgrad too (A/B timing)
+static bool wgrad_wide() {
+    static const bool w = [] { const char* e = getenv("NSB_SPLIT_WGRAD_WIDE"); return !(e && e[0] == '0'); }();
+    return w;
+}
+
 int split_gemm(const GemmArgs& g, int role, cudaStream_t st) {
     NSB_TRY(check_arch());
     // alignment contract of the loaders / epilogues (all layer buffers of field_fp32.cu satisfy it)
@@ -414,7 +438,23 @@ int split_gemm(const GemmArgs& g, int role, cudaStream_t st) {
     switch (role) {
         case EPI_FWD: return img ? NSB_SG(false, false, EPI_FWD, true) : NSB_SG(false, false, EPI_FWD, false);
         case EPI_DGRAD: return img ? NSB_SG(false, true, EPI_DGRAD, true) : NSB_SG(false, true, EPI_DGRAD, false);
-        case EPI_WGRAD: return NSB_SG(true, true, EPI_WGRAD, false);
+        case EPI_WGRAD: {
+            // 256-column CTAs over the whole multiples of 256 columns of B, 128-column CTAs over the rest (gamma(x) / gamma(d)
+            // columns of the skip and colour layers, layer 0); the bias gradient rides with the first launch only
+            const int64_t wide = wgrad_wide() ? g.Ndim / 256 * 256 : 0;
+            if (wide > 0) {
+                GemmArgs a = g;
+                a.Ndim = wide; a.n_valid = g.n_valid < wide ? g.n_valid : (int)wide;
+                NSB_TRY(t3 ? (tc::launch_split_gemm<true, true, EPI_WGRAD, 3, false, 256>(a, st)) : (tc::launch_split_gemm<true, true, EPI_WGRAD, 2, false, 256>(a, st)));
+            }
+            if (wide < g.Ndim) {
+                GemmArgs a = g;
+                a.B = g.B + wide; a.C = g.C + wide; a.Ndim = g.Ndim - wide; a.n_valid = g.n_valid - (int)wide;
+                if (wide > 0) a.colsum = nullptr;
+                if (a.n_valid > 0) return t3 ? (tc::launch_split_gemm<true, true, EPI_WGRAD, 3, false, 128>(a, st)) : (tc::launch_split_gemm<true, true, EPI_WGRAD, 2, false, 128>(a, st));
+            }
+            return NSB_OK;
+        }
     }
 #undef NSB_SG
     return NSB_E_BADARG;
