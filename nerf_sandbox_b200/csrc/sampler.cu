@@ -331,19 +331,23 @@ __global__ void resample_merge_kernel(const float* __restrict__ zc, const float*
 // edges, zc, fine, merged row) live in shared memory; every loop is unrolled and every search has a fixed trip count.
 // Same arithmetic, operation by operation, as resample_merge_kernel (this file is compiled with -fmad=false).
 // ---------------------------------------------------------------------------------------------------
+#define PD(i) ((i) + ((i) >> 5))
 template <int NCL, int NFL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict__ w_c, float* __restrict__ z_all, float* __restrict__ z_fine,
                            int64_t B, int deterministic, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
     constexpr int NC = 32 * NCL, NF = 32 * NFL, M = NC - 1, NT = NC + NF;
     if (step_dev) offset += 8 * *step_dev;
-    __shared__ float sm[kWarpsPerBlock][3 * NC + NF + NT];
+    // tables are indexed through PD(i) = i + i / 32 (one pad word per 32): lane-strided accesses (stride NCL or NFL, powers of two)
+    // and unit-stride accesses are then both free of bank conflicts
+    constexpr int PNC = NC + NC / 32, PNF = NF + NF / 32, PNT = NT + NT / 32;
+    __shared__ float sm[kWarpsPerBlock][3 * PNC + PNF + PNT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* zrow = sm[warp];
-    float* edges = zrow + NC;
-    float* cdf = edges + NC;
-    float* fine = cdf + NC;
-    float* merged = fine + NF;
+    float* edges = zrow + PNC;
+    float* cdf = edges + PNC;
+    float* fine = cdf + PNC;
+    float* merged = fine + PNF;
     const unsigned full = 0xffffffffu;
     for (int64_t b = blockIdx.x * (int64_t)kWarpsPerBlock + warp; b < B; b += (int64_t)gridDim.x * kWarpsPerBlock) {
         // ---- this lane's coarse samples and weights (NCL consecutive floats: one vector load each when NCL is 2 or 4)
@@ -353,7 +357,7 @@ resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict
         z[NCL] = __shfl_down_sync(full, z[0], 1);                 // first sample of the next lane (unused on lane 31)
         w[NCL] = __shfl_down_sync(full, w[0], 1);
 #pragma unroll
-        for (int k = 0; k < NCL; ++k) zrow[lane * NCL + k] = z[k];
+        for (int k = 0; k < NCL; ++k) zrow[PD(lane * NCL + k)] = z[k];
         // ---- midpoints m_j = 0.5 (z_{j+1} + z_j), j < M  (:926) and the two before this lane's first
         float m[NCL];
 #pragma unroll
@@ -373,7 +377,7 @@ resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict
             if (j == 0) e = mj - 0.5f * (mjp1 - mj);
             else if (j == M) e = mjm1 + 0.5f * (mjm1 - mjm2);
             else e = 0.5f * (mj + mjm1);
-            edges[j] = e;
+            edges[PD(j)] = e;
         }
         // ---- pdf and cdf: weights_bins = 0.5 (w_{j+1} + w_j) + 1e-5 (:927-928), + 1e-5 and clamp (sampling_utils.py:38)
         float pw[NCL], local = 0.f;
@@ -394,11 +398,11 @@ resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict
             if (lane >= d) incl_c += t;
         }
         const float excl_c = incl_c - run_c;
-        if (lane == 0) cdf[0] = 0.f;
+        if (lane == 0) cdf[0] = 0.f;                              // PD(0) = 0
 #pragma unroll
         for (int k = 0; k < NCL; ++k) {
             const int j = lane * NCL + k;
-            if (j < M) cdf[j + 1] = excl_c + pw[k];
+            if (j < M) cdf[PD(j + 1)] = excl_c + pw[k];
         }
         __syncwarp();
         // ---- this lane's block of the sorted uniforms
@@ -439,22 +443,22 @@ resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict
 #pragma unroll
             for (int step = NC; step > 0; step >>= 1) {
                 const int mid = ind + step;
-                if (mid <= NC && cdf[mid - 1] <= u[q]) ind = mid;
+                if (mid <= NC && cdf[PD(mid - 1)] <= u[q]) ind = mid;
             }
             const int below = min(max(ind - 1, 0), M), above = min(max(ind, 1), M);             // :52-53
-            const float c_lo = cdf[below], c_hi = cdf[above];
+            const float c_lo = cdf[PD(below)], c_hi = cdf[PD(above)];
             float denom = c_hi - c_lo;
             if (denom < 1e-5f) denom = 1.0f;                      // :62
             const float t = (u[q] - c_lo) / denom;
-            const float e_lo = edges[below], e_hi = edges[above];
+            const float e_lo = edges[PD(below)], e_hi = edges[PD(above)];
             const float zf = e_lo + t * (e_hi - e_lo);            // :64
-            fine[s] = zf;
+            fine[PD(s)] = zf;
             if (z_fine) z_fine[b * NF + s] = zf;
             int r = below;                                        // #{zc <= zf}: at most zc[below .. below+2] (see resample_merge_kernel)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) r += (below + k < NC && zrow[min(below + k, NC - 1)] <= zf) ? 1 : 0;
-            if (r == below + 3) { while (r < NC && zrow[r] <= zf) ++r; }
-            merged[s + r] = zf;
+            for (int k = 0; k < 3; ++k) r += (below + k < NC && zrow[PD(min(below + k, NC - 1))] <= zf) ? 1 : 0;
+            if (r == below + 3) { while (r < NC && zrow[PD(r)] <= zf) ++r; }
+            merged[PD(s + r)] = zf;
         }
         __syncwarp();
         // ---- coarse samples: position i + #{fine < zc[i]} (coarse first on ties)
@@ -464,16 +468,18 @@ resample_merge_fast_kernel(const float* __restrict__ zc, const float* __restrict
 #pragma unroll
             for (int step = NF; step > 0; step >>= 1) {
                 const int mid = lo + step;
-                if (mid <= NF && fine[mid - 1] < z[k]) lo = mid;
+                if (mid <= NF && fine[PD(mid - 1)] < z[k]) lo = mid;
             }
-            merged[lane * NCL + k + lo] = z[k];
+            merged[PD(lane * NCL + k + lo)] = z[k];
         }
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < NCL + NFL; ++t) z_all[b * NT + t * 32 + lane] = merged[t * 32 + lane];
+        for (int t = 0; t < NCL + NFL; ++t) z_all[b * NT + t * 32 + lane] = merged[t * 32 + lane + t];   // PD(32 t + lane)
         __syncwarp();
     }
 }
+
+#undef PD
 
 static int grid_for_rays(int64_t B) {
     const int64_t want = cdiv(B, kWarpsPerBlock);
