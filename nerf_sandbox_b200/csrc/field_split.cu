@@ -8,14 +8,18 @@
 // the cross products in a second one (see the MMA loop for why).  NT = 3 carries 24 significand bits per operand -- the same
 // information as the FFMA path.
 //
-// One CTA = one 128 x 128 output tile; 512 converter threads (one piece each) + an MMA warp.  Per K = 16 chunk every converter thread owns one 8-element piece of the fp32 A or
-// B tile: cp.async brings it into a thread-private shared-memory slot (three chunks in flight per CTA, no
-// registers held, no barrier), the thread splits it and writes the bf16 term images into a shared-memory stage in the
-// canonical K-major core-matrix layout -- operands stored with the OTHER index contiguous
-// (dgrad's weights, both wgrad operands) are transposed by the same pass, so every MMA is K-major (an MN-major MMA costs
-// 3-4x more).  A ninth warp issues the MMAs of a chunk once its 512 pieces are written (mbarrier) and
-// commits them to the stage's "empty" barrier; the stage is rewritten only after that commit has arrived.  Two CTAs share an SM (112 KB of shared memory, 256 TMEM columns each), so
-// one CTA's conversion overlaps the other's MMAs.  Epilogues as in field_fp32.cu: bias + ReLU; addend + mask; split-K atomics.
+// One CTA = one 128 x BN output tile (BN = 128 for forward / dgrad with two CTAs per SM, 256 for wgrad with one): 256
+// converter threads, an MMA warp and a producer warp.  Per K = 16 chunk every converter thread owns one 8-element piece of
+// the fp32 A tile and one (two for BN = 256) of the B tile: cp.async brings it into a thread-private shared-memory slot
+// (three chunks in flight per CTA, no registers held, no barrier), the thread splits it and writes the bf16 term images
+// into a shared-memory stage in the canonical K-major core-matrix layout -- operands stored with the OTHER index
+// contiguous (dgrad's weights, both wgrad operands) are transposed by the same pass, so every MMA is K-major (an MN-major
+// MMA costs 3-4x more).  The MMA warp issues the products of a chunk once all its pieces are written
+// (mbarrier) and commits them to the stage's "empty" barrier; the stage is rewritten only after that commit has arrived.
+// Forward and dgrad take B from term images of the weights written once per optimiser step (split_pack_kernel): the
+// producer warp bulk-copies them straight into the stage.  Epilogues as in field_fp32.cu -- bias + ReLU; addend + mask;
+// split-K atomics, plus the bias gradient (column sums of wgrad's A pieces) -- staged through shared memory so that global
+// memory sees whole 512-byte rows.  What bounds it is shared-memory bandwidth, not the tensor cores.
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include "nsb_common.cuh"
