@@ -88,3 +88,33 @@ def test_wgrad_role(P, n_out, K, Kpad):
                       _lib.ptr(gb), _lib.stream()), "split_gemm wgrad")
         assert _rel(gb, times * dY.double().sum(0)) < 1e-5
         assert _rel(gW, times * ref) < 1e-5, (times, _rel(gW, times * ref))    # 40,000 random-sign terms per element: fp32 accumulation noise
+
+
+def test_error_anatomy_matches_an_fp32_gemm():
+    """What DESIGN section 2 claims about the split product, as assertions: in units of sum|terms| per output element, mixed-sign
+    operands land at the error of cuBLAS's fp32 GEMM, and the truncating tensor-core accumulate shows up only as a small negative
+    bias on same-sign sums (x0 * y0 alone in the main accumulator: K / 16 truncations, not 6 K / 16)."""
+    fn, _lib = _fn()
+    dev = torch.device("cuda", 0)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device=dev).manual_seed(0)
+        M, N, K = 1024, 256, 256
+        b = torch.zeros(N, device=dev)
+        for same_sign in (False, True):
+            X = torch.rand(M, K, device=dev, generator=g) if same_sign else torch.randn(M, K, device=dev, generator=g)
+            W = torch.rand(N, K, device=dev, generator=g) if same_sign else torch.randn(N, K, device=dev, generator=g)
+            Y = torch.empty(M, N, device=dev)
+            _lib.check(fn(_lib.ptr(X), K, _lib.ptr(W), K, _lib.ptr(Y), N, M, N, K, FWD, _lib.ptr(b), 0, None, 0, None, 0, 0, None, _lib.stream()), "gemm")
+            ref = X.double() @ W.double().T
+            scale = X.double().abs() @ W.double().abs().T
+            e = (Y.double() - ref) / scale
+            e32 = ((X @ W.T).double() - ref) / scale
+            rms, rms32 = float(e.pow(2).mean().sqrt()), float(e32.pow(2).mean().sqrt())
+            if same_sign:
+                assert -6e-7 < float(e.mean()) < 0 and rms < 3 * rms32, (float(e.mean()), rms, rms32)     # measured -3.1e-7 / 3.2e-7 vs 2.2e-7
+            else:
+                assert abs(float(e.mean())) < 1e-9 and rms < 2 * rms32, (float(e.mean()), rms, rms32)     # measured 2.3e-8 vs 2.8e-8
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
