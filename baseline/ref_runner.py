@@ -123,3 +123,39 @@ def make_cpu_step(batch_fn, *, nc=64, nf=128, threads=None, seed=0):
         opt.step()
         return float(out["loss"].detach())
     return step, {"threads": torch.get_num_threads(), "torch": torch.__version__}
+
+
+def make_cpu_render(rays_fn, *, nc=64, nf=128, near=2.0, far=6.0, threads=None, seed=0, eval_chunk=16384):
+    """Returns (render, info): ``render()`` runs the reference's render_image_chunked (utils/render_utils.py:285-424:
+    coarse pass, sample_pdf, merge, fine pass; fp32 on a CPU device) on the rays ``rays_fn()`` returns -- a dict with the
+    trainer's batch keys for an H x W tile, H * W rays -- and returns the rgb image.  SURVEY 8d's eval CPU baseline."""
+    import torch
+    _, RU = import_reference()
+    inst = sys.modules.get("nerf_sandbox_b200.install")
+    if inst is not None:
+        inst.uninstall()
+    from nerf_sandbox.source.models.encoders import get_vanilla_nerf_encoders
+    from nerf_sandbox.source.models.mlps import NeRF
+    threads = int(threads or os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    pos_enc, dir_enc = get_vanilla_nerf_encoders()
+    nerf_c = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu")
+    nerf_f = NeRF(63, 27, 8, 256, skip_pos=4, sigma_activation="relu")
+    with torch.no_grad():
+        nerf_c.sigma_out.bias.fill_(0.3); nerf_f.sigma_out.bias.fill_(0.3)
+    nerf_c.eval(); nerf_f.eval()
+
+    def render():
+        r = {k: torch.from_numpy(v) for k, v in rays_fn().items()}
+        n = r["rays_o_marching"].shape[0]
+        H = int(round(n ** 0.5))
+        while n % H:
+            H -= 1
+        W = n // H
+        out = RU.render_image_chunked(r["rays_o_marching"], r["rays_d_marching_unit"], r["rays_d_marching_norm"], H, W, near, far,
+                                      pos_enc, dir_enc, nerf_c, nerf_f, nc, nf, True, torch.device("cpu"), eval_chunk=eval_chunk,
+                                      perturb=False, sigma_activation="relu", viewdirs_world_unit=r["rays_d_world_unit"],
+                                      infinite_last_bin=True)
+        return out["rgb"]
+    return render, {"threads": torch.get_num_threads(), "torch": torch.__version__}

@@ -479,6 +479,20 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": RAYS * n / dt, "unit": "rays/s", "cores": threads, "kind": kind,
                "sample": f"{n} full steps (fwd+bwd+Adam) of {RAYS} rays x (64+192) samples after 1 warm-up: {what}"}
+        # SURVEY 8d's eval baseline: the reference's render_image_chunked on a tile of the frame, extrapolated to 800x800
+        if kind == "reference" and not args.no_frame:
+            try:
+                from baseline import ref_runner
+                tile = 64 * 64
+                rr = np.random.default_rng(7)
+                render, info = ref_runner.make_cpu_render(lambda: blender_rays(rr, tile, 1000), nc=NC, nf=NF, threads=threads)
+                render()
+                t0 = time.perf_counter(); render(); dt = time.perf_counter() - t0
+                extra["render_cpu_baseline"] = {"rays_per_s": tile / dt, "frames_per_s_extrapolated": tile / dt / (H * W), "cores": info["threads"],
+                                                "kind": "reference", "sample": f"render_image_chunked (baseline/_ref, unmodified) on a {tile}-ray tile, "
+                                                f"64 + 128 samples, fp32 CPU, second of two calls"}
+            except Exception as exc:
+                extra["render_cpu_baseline"] = {"unavailable": repr(exc)[:200]}
 
     if rank == 0:
         ws_gb = L.nsb_train_workspace_bytes(RAYS, NC, NF, tr.mode) / 1e9
