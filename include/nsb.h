@@ -13,7 +13,12 @@
  *   - `stream` is a cudaStream_t passed as void*; no call synchronises or allocates;
  *   - return 0 on success, a negative NSB_E_* code otherwise (nsb_error_string explains it);
  *     the Python wrappers raise RuntimeError/ValueError like the reference does;
- *   - nullable arguments are marked [opt].
+ *   - nullable arguments are marked [opt];
+ *   - threading: the library keeps no state per call except (a) thread-local markers set for the duration of nsb_train_step
+ *     and (b) ONE helper stream + event pair per device, created on first use, on which nsb_train_fwd_bwd / nsb_train_step
+ *     run half batches and the coarse backward chain.  Calls on different devices are independent; on one device, two host
+ *     threads must not be inside nsb_train_fwd_bwd / nsb_train_step at the same time (the reference is single-threaded,
+ *     single-stream; NSB_SIDE_STREAM=0 removes the helper stream and with it this restriction).
  */
 #ifndef NSB_H_
 #define NSB_H_
@@ -28,7 +33,7 @@ extern "C" {
 #define NSB_E_BADARG (-1)     /* shape / flag the path does not support                         */
 #define NSB_E_WORKSPACE (-2)  /* workspace too small (see nsb_field_workspace_bytes)            */
 #define NSB_E_CUDA (-3)       /* a CUDA runtime call or launch failed; see nsb_last_cuda_error  */
-#define NSB_E_ARCH (-4)       /* device is not sm_100 (tensor-core mode only)                   */
+#define NSB_E_ARCH (-4)       /* device is not sm_100 (every tcgen05 kernel: both modes' defaults) */
 
 /* flags for the compositor / forward pass */
 #define NSB_WHITE_BKGD 1u        /* render_utils.py:161-162 */

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -172,8 +173,10 @@ SideStream* side_stream() {
     static SideStream table[64];
     static int state[64];          // 0 = not tried, 1 = ready, -1 = unavailable
     static const bool enabled = [] { const char* e = getenv("NSB_SIDE_STREAM"); return !(e && e[0] == '0'); }();
+    static std::mutex init_mutex;  // first use from two host threads (one per device) must not race on the table
     int dev = 0;
     if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(init_mutex);
     if (state[dev] == 0) {
         SideStream& s = table[dev];
         state[dev] = (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
