@@ -25,42 +25,57 @@ __device__ __forceinline__ float coarse_z_step(int i, int Nc, float step, float 
 // uniform in [0,1) on the 2^-24 grid from a 32-bit counter hash (jitter draws need no more than that)
 __device__ __forceinline__ float hash_u01(uint32_t key, uint32_t idx) { return u01(mix32(idx * 0x9E3779B1u + key)); }
 
+// G samples per thread per trip (4, or 8 when Nc is a multiple of 8: the neighbours' z values and the index arithmetic are
+// shared by twice as many samples); a group never straddles two rays, so it leaves as 16-byte stores.
+template <int G>
 __global__ void stratified_kernel(float* __restrict__ z, const float* __restrict__ U, int64_t B, int Nc,
                                   float near_, float far_, int jitter, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
     if (step_dev) offset += 8 * *step_dev;
     const int64_t total = B * (int64_t)Nc;
-    const bool vec = (Nc & 3) == 0;                 // a group of four samples never straddles two rays: 16-byte stores
+    const bool vec = (Nc % G) == 0;
     const float step = Nc > 1 ? 1.0f / (float)(Nc - 1) : 0.0f;
-    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; base < total;
-         base += (int64_t)gridDim.x * blockDim.x * 4) {
+    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * G; base < total;
+         base += (int64_t)gridDim.x * blockDim.x * G) {
         const uint32_t key = hash_key(seed, offset, (uint64_t)base);
         if (vec) {
             // (a 64-bit modulo is ~100 instructions: stay in 32 bits whenever the sample count allows)
             const int i0 = total <= 0x7fffffffLL ? (int)((uint32_t)base % (uint32_t)Nc) : (int)(base % Nc);
-            // z_{i0-1} .. z_{i0+4}: six evaluations of trainer.py:902 serve the four samples' lower/upper bounds
-            float zz[6];
+            // z_{i0-1} .. z_{i0+G}: G + 2 evaluations of trainer.py:902 serve the G samples' lower/upper bounds
+            float zz[G + 2];
 #pragma unroll
-            for (int e = 0; e < 6; ++e) zz[e] = coarse_z_step(min(max(i0 - 1 + e, 0), Nc - 1), Nc, step, near_, far_);
-            float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jitter) uu = U ? *reinterpret_cast<const float4*>(U + base)
-                               : make_float4(hash_u01(key, (uint32_t)base), hash_u01(key, (uint32_t)base + 1), hash_u01(key, (uint32_t)base + 2),
-                                             hash_u01(key, (uint32_t)base + 3));
-            const float u4[4] = {uu.x, uu.y, uu.z, uu.w};
-            float o[4];
+            for (int e = 0; e < G + 2; ++e) zz[e] = coarse_z_step(min(max(i0 - 1 + e, 0), Nc - 1), Nc, step, near_, far_);
+            float uu[G];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < G; ++e) uu[e] = 0.f;
+            if (jitter) {
+                if (U) {
+#pragma unroll
+                    for (int v = 0; v < G / 4; ++v) {
+                        const float4 t = *reinterpret_cast<const float4*>(U + base + 4 * v);
+                        uu[4 * v] = t.x; uu[4 * v + 1] = t.y; uu[4 * v + 2] = t.z; uu[4 * v + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < G; ++e) uu[e] = hash_u01(key, (uint32_t)base + e);
+                }
+            }
+            float o[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) {
                 const int i = i0 + e;
                 const float zi = zz[e + 1];
                 if (!jitter) { o[e] = zi; continue; }
                 const float lower = i > 0 ? 0.5f * (zi + zz[e]) : zi;           // :904-905  (mids = 0.5*(z[1:]+z[:-1]))
                 const float upper = i < Nc - 1 ? 0.5f * (zz[e + 2] + zi) : zi;  // :906
-                o[e] = lower + (upper - lower) * u4[e];                        // :907 (the sort at :908 is the identity)
+                o[e] = lower + (upper - lower) * uu[e];                        // :907 (the sort at :908 is the identity)
             }
-            *reinterpret_cast<float4*>(z + base) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int v = 0; v < G / 4; ++v)
+                *reinterpret_cast<float4*>(z + base + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
             continue;
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < G; ++e) {
             const int64_t idx = base + e;
             if (idx >= total) break;
             const int i = (int)(idx % Nc);
@@ -496,9 +511,11 @@ extern "C" int nsb_stratified_z(float* z, const float* U, int64_t B, int Nc, flo
     if (B == 0) return NSB_OK;
     if (!z || B < 0 || Nc < 1) return NSB_E_BADARG;
     const int64_t total = B * Nc;
-    const int64_t want = cdiv(total, 256 * 4);
+    const int G = (Nc % 8) == 0 ? 8 : 4;
+    const int64_t want = cdiv(total, 256 * G);
     const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
-    stratified_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset, g_step_dev);
+    if (G == 8) stratified_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset, g_step_dev);
+    else stratified_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(z, U, B, Nc, near_, far_, jitter, seed, offset, g_step_dev);
     NSB_LAUNCH_CHECK("stratified_kernel");
     return NSB_OK;
 }
